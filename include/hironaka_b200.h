@@ -1,0 +1,155 @@
+/*
+ * hironaka_b200.h — C-ABI of the B200-native batched Hironaka game engine.
+ *
+ * This is the drop-in boundary for the reference's env-step path.  The reference
+ * (honglu2875/hironaka) has one C-ABI precedent,
+ *     extern "C" void getNewtonPolytope_approx(long* points, int batchNum, int m, int n, long* newPoints)
+ *     (hironaka/cpp/cppUtil.cpp:58-63, bound with ctypes in hironaka/src/_np_ops.py:6-15),
+ * and this header keeps its conventions (caller-owned contiguous row-major [B, N, d]
+ * buffers, plain pointers and sizes, ctypes-loadable) and extends them with an `int`
+ * status return, a CUDA stream and a mode bitfield, so that one library serves the three
+ * de-facto seams of the reference:
+ *   (1) TensorPoints / hironaka.src._torch_ops   (hironaka/core/tensor_points.py:11-126,
+ *                                                 hironaka/src/_torch_ops.py:8-146)
+ *   (2) the functional JAX step API              (hironaka/jax/util.py:22-214,
+ *                                                 hironaka/src/_jax_ops.py:15-123)
+ *   (3) the per-op signatures op(points, ..., inplace, padding_value).
+ *
+ * Device entry points (hk_*) take RAW DEVICE POINTERS into caller-owned contiguous
+ * buffers and a cudaStream_t (passed as void*); they never allocate, never synchronise
+ * and keep no global state, so they are re-entrant and CUDA-graph capturable.
+ * Host entry points (hk_session_*) own device buffers for one shard of games and take
+ * HOST pointers; they are what a ctypes/numpy caller (the style of _np_ops.py) binds.
+ *
+ * No torch types appear here.  All functions return HK_OK (0), a negative HK_ERR_* code
+ * for argument errors, or a positive cudaError_t.
+ */
+#ifndef HIRONAKA_B200_H
+#define HIRONAKA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HK_VERSION 100 /* major*100 + minor */
+
+/* ---- status codes ---------------------------------------------------------------- */
+#define HK_OK 0
+#define HK_ERR_BAD_ARG (-1)     /* null pointer, non-positive size, bad flag combination   */
+#define HK_ERR_UNSUPPORTED (-2) /* shape outside HK_MAX_* or op not defined for the dtype   */
+#define HK_ERR_ALIGN (-3)       /* state pointer not 4-byte aligned                         */
+
+/* ---- limits ------------------------------------------------------------------------ */
+#define HK_MAX_DIM 10          /* reference caps dimension at _MAX_DIM-1 = 10
+                                  (hironaka/jax/host_action_preprocess.py:27,62)            */
+#define HK_MAX_POINTS 1024     /* max_num_points per game                                   */
+#define HK_MAX_GAME_WORDS 4096 /* N*d 32-bit words per game (16 KiB of shared memory)       */
+
+/* ---- element type of the point tensor ---------------------------------------------- */
+#define HK_DTYPE_I32 0 /* int32 state, padding is the integer -1 (the engine's native form) */
+#define HK_DTYPE_F32 1 /* float32 state, the reference's storage (TensorPoints default)     */
+
+/* ---- ops; a step executes the selected ones in THIS order ----------------------------
+ * shift -> reposition -> newton -> rescale is get_take_actions (hironaka/jax/util.py:117-123);
+ * shift -> newton -> rescale is FusedGame.agent_move (hironaka/trainer/fused_game.py:150-162). */
+#define HK_OP_SHIFT (1u << 0)      /* x_a <- sum_{j in S} x_j       (_torch_ops.py:46-110, _jax_ops.py:76-90)   */
+#define HK_OP_REPOSITION (1u << 1) /* per coord subtract min over live rows (_torch_ops.py:113-133, _jax_ops.py:114-123) */
+#define HK_OP_NEWTON (1u << 2)     /* dedupe + dominance filter     (_fn.py:192-213, _torch_ops.py:8-39, _jax_ops.py:32-73) */
+#define HK_OP_RESCALE (1u << 3)    /* divide live entries by the game max; F32 state only (_torch_ops.py:136-146, _jax_ops.py:93-111) */
+
+/* ---- semantics flags ---------------------------------------------------------------- */
+#define HK_F_NOOP_INVALID (1u << 0)   /* torch: axis not in S  => state unchanged (_torch_ops.py:90-91). Unset = JAX: applied anyway */
+#define HK_F_FREEZE_ENDED (1u << 1)   /* torch ignore_ended_games: <2 live points => no shift (_torch_ops.py:92-93) */
+#define HK_F_ACT_DISCRETE (1u << 2)   /* host_action[] holds discrete ids 0..2^d-d-2 (HostActionEncoder, _fn.py:241-325;
+                                         decode_table, host_action_preprocess.py:8-24). Unset = coordinate bitmask, bit k <=> coordinate k */
+#define HK_F_ROLE_AGENT (1u << 3)     /* reward = -(done & !prev_done) (util.py:142-144); unset = host role (+) */
+#define HK_F_OBS_RESCALE (1u << 4)    /* observation features are rescaled (scale_observation, util.py:183) */
+#define HK_F_OBS_SORT_COORD0 (1u << 5)/* rows sorted by coordinate 0, descending, stable (TensorPoints.get_features, tensor_points.py:72-74) */
+#define HK_F_OBS_SORT_LEX (1u << 6)   /* rows sorted descending lexicographically, LAST coordinate primary, stable (util.py:195) */
+
+/* ---- introspection ------------------------------------------------------------------ */
+int hk_version(void);
+const char* hk_error_string(int code);
+/* 1 if (N,d) runs on the register-resident thread-per-game kernel, 0 if on the generic
+ * warp-per-game kernel, <0 if unsupported. */
+int hk_kernel_class(int N, int d);
+
+/* ---- the fused step ------------------------------------------------------------------
+ * One launch = one game-step for B independent games:
+ *   prev_done -> [shift] -> [reposition] -> [newton] -> [rescale] -> done / reward / num_points
+ *   -> [observation features]
+ * Replaces shift_torch + get_newton_polytope_torch + rescale_torch + ended_batch_in_tensor +
+ * FusedGame._default_reward (fused_game.py:150-182) and take_actions + get_dones + reward_fn +
+ * feature_fn (util.py:34-35,82-149,172-214).
+ *
+ *   state_in / state_out  [B,N,d] dtype; may be the same pointer (in place = the reference's
+ *                         inplace=True) or disjoint (inplace=False).  Dead rows are negative in
+ *                         coordinate 0 and are rewritten with padding_value.
+ *   host_action [B] int32 coordinate bitmask or discrete id (HK_F_ACT_DISCRETE); required with HK_OP_SHIFT
+ *   axis        [B] int32 agent's coordinate; required with HK_OP_SHIFT
+ *   done        [B] uint8  (#live rows <= 1 after the step), nullable        (util.py:34-35)
+ *   reward      [B] float  +-(done & !prev_done), nullable                   (util.py:136-144)
+ *   num_points  [B] int32  live rows after the step, nullable                (tensor_points.py:65-70)
+ *   obs         [B, N*d (+d if obs_coord)] float, nullable: features of the new state
+ *   obs_coord   [B] int32  coordinate set appended to obs as d floats 0/1 (make_agent_obs, util.py:22-31), nullable
+ *   exceed_flag [1] int32  set to 1 if any live entry >= value_threshold (TensorPoints.exceed_threshold,
+ *                         tensor_points.py:57-63), nullable; never cleared by the library
+ */
+int hk_step(const void* state_in, void* state_out, const int32_t* host_action, const int32_t* axis,
+            uint8_t* done, float* reward, int32_t* num_points, float* obs, const int32_t* obs_coord,
+            int32_t* exceed_flag, int64_t B, int32_t N, int32_t d, int32_t dtype, uint32_t ops,
+            uint32_t flags, float padding_value, float value_threshold, void* stream);
+
+/* ---- per-op entry points (the reference's hironaka.src op surface) ---------------------
+ * Each is one launch of the same kernel family with a single op selected. */
+int hk_shift(const void* state_in, void* state_out, const int32_t* host_action, const int32_t* axis,
+             int64_t B, int32_t N, int32_t d, int32_t dtype, uint32_t flags, float padding_value,
+             void* stream);
+int hk_reposition(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d,
+                  int32_t dtype, float padding_value, void* stream);
+int hk_newton_polytope(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d,
+                       int32_t dtype, float padding_value, void* stream);
+int hk_rescale(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d, int32_t dtype,
+               float padding_value, void* stream); /* F32 only */
+int hk_features(const void* state_in, float* obs, const int32_t* obs_coord, int64_t B, int32_t N,
+                int32_t d, int32_t dtype, uint32_t flags, float padding_value, void* stream);
+int hk_dones(const void* state_in, uint8_t* done, int32_t* num_points, int64_t B, int32_t N, int32_t d,
+             int32_t dtype, void* stream);
+
+/* ---- multi-step rollout ------------------------------------------------------------------
+ * T consecutive steps with the state held on chip between steps: one read and one write of
+ * the state per T steps.  Action streams are [T,B].  Outputs per step are optional:
+ *   done_t [T,B] uint8, reward_t [T,B] float; done_count [T] int32 is incremented atomically
+ *   (number of finished games after each step, the quantity compute_rho reads every step,
+ *   hironaka/jax/jax_trainer.py:533-534); length [B] int32 = first step index (1-based) after
+ *   which the game was done, 0 if done at entry, T+1 if never. All nullable. */
+int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action_t, const int32_t* axis_t,
+               uint8_t* done_t, float* reward_t, int32_t* done_count, int32_t* length, int64_t B,
+               int32_t N, int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags,
+               float padding_value, void* stream);
+
+/* ---- host-buffer sessions (numpy / ctypes callers; the _np_ops.py calling style) -------
+ * A session owns the device state of one shard of B games on one GPU plus staging buffers
+ * and a stream.  All pointers below are HOST pointers (pinned or pageable). */
+typedef struct hk_session hk_session;
+
+int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                      float padding_value);
+int hk_session_destroy(hk_session* s);
+int hk_session_set_state(hk_session* s, const void* state_host);   /* H2D of [B,N,d]            */
+int hk_session_get_state(hk_session* s, void* state_host);         /* D2H of [B,N,d], blocking   */
+/* One step: H2D(host_action, axis) -> hk_step -> D2H(done, reward, done_count), blocking.
+ * done_host / reward_host / done_count_host are nullable; done_count_host receives the
+ * number of finished games after the step (a single int32). */
+int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_t* axis_host,
+                    uint8_t* done_host, float* reward_host, int32_t* done_count_host, uint32_t ops,
+                    uint32_t flags);
+void* hk_session_state_ptr(hk_session* s); /* device pointer of the resident state (zero-copy interop) */
+void* hk_session_stream(hk_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIRONAKA_B200_H */

@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — game-steps/sec of the batched Hironaka env step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm (oracle C port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] — dim=3, max_num_points=20
+random-play rollout: root states randint[0,20) -> newton -> reposition,
+then per step a uniform random host action id and a uniform random agent axis over ALL d axes
+(invalid actions occur; JAX semantics apply them), step = shift -> reposition -> newton ->
+done/reward.  All inputs are generated on the CPU from a seed and copied (never device RNG).
+1 Mi games per GPU (weak scaling; the state, 252 MB, exceeds the 126 MB L2, so every step
+streams from HBM).  A "step" is one game-step of all B slots = one hk_step launch; consecutive
+steps walk through independent 20-step rollouts, each on its own pre-generated batch, so the
+live-point dynamics are those of real play and nothing but steps sits in the timed region.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "game_steps_per_sec"
+UNIT = "game-steps/s"
+N_POINTS, DIM, T_ROLLOUT, MAX_VALUE = 20, 3, 20, 20
+GAMES_PER_GPU = 1 << 20
+MAX_RESIDENT_ROLLOUTS = 10  # distinct pre-generated batches; beyond K = 200 they are restored from pristine copies
+BYTES_PER_GAME_STEP = 8 * N_POINTS * DIM + 13  # int32 state r+w, 2 x int32 action, u8 done, f32 reward
+OPS_PER_GAME_STEP = N_POINTS * (N_POINTS - 1) * (DIM + 1) + 3 * N_POINTS * DIM + N_POINTS
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "C2: test/jax_config.yml shape (dim=3, max_num_points=20) random-play rollout, "
+                    "random host vs random agent, JAX semantics with reposition",
+        "games_per_gpu": GAMES_PER_GPU, "global_batch": GAMES_PER_GPU * n_gpus, "max_num_points": N_POINTS,
+        "dimension": DIM, "rollout_length": T_ROLLOUT, "max_value": MAX_VALUE,
+        "parallelism": f"batch-sharded x{n_gpus}, no collective on the step path",
+        "l2_policy": "inputs larger than L2 (252 MB int32 state per GPU vs 126 MB L2); a new batch every 20 steps",
+        "bytes_per_game_step": BYTES_PER_GAME_STEP, "int_ops_per_game_step": OPS_PER_GAME_STEP,
+    }
+
+
+def make_inputs(seed: int, B: int, n_rollouts: int):
+    """Seeded CPU inputs: raw root points [R,B,N,d] int32 and action streams [R,T,B] int32."""
+    rng = np.random.default_rng(seed)
+    ncls = 2 ** DIM - DIM - 1
+    pts = rng.integers(0, MAX_VALUE, size=(n_rollouts, B, N_POINTS, DIM), dtype=np.int32)
+    ha = rng.integers(0, ncls, size=(n_rollouts, T_ROLLOUT, B), dtype=np.int32)
+    ax = rng.integers(0, DIM, size=(n_rollouts, T_ROLLOUT, B), dtype=np.int32)
+    return pts, ha, ax
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_per_launch():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("hk_small_kernel_i32_20x3_bytes_per_launch_1Mi")
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls NVML (SM clock + throttle reasons) from a thread while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, uuid: str | None = None):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if uuid and not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_rate(sample_games: int, steps: int, warmup: int, seed: int = 1234, threads: int | None = None):
+    """Times the oracle's C port (all host threads) on a bounded sample of the same workload.
+    This is the only place the bench executes oracle/ — as the measured CPU baseline."""
+    from oracle import cport
+    from oracle import hk_oracle as O
+    if threads:
+        cport.set_threads(threads)
+    cores = cport.threads()
+    n_roll = max(1, -(-(steps + warmup) // T_ROLLOUT))
+    pts, ha, ax = make_inputs(seed, sample_games, n_roll)
+    ops_step = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    states = [cport.step(pts[r], None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0] for r in range(n_roll)]
+    out = np.empty_like(states[0])
+    k = 0
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        r, t = divmod(k, T_ROLLOUT)
+        r %= n_roll
+        cport.step(states[r], ha[r, t], ax[r, t], ops_step, O.F_ACT_DISCRETE, out=out)
+        states[r], out = out, states[r]
+        k += 1
+    dt = time.perf_counter() - t0
+    return sample_games * steps / dt, cores, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = 1 << 18
+    rate, cores, dt = cpu_rate(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} games x {args.steps} steps of the C2 workload, oracle/hk_oracle.c over "
+                                   f"{cores} pthreads (the reference itself is Python/torch and cannot travel; "
+                                   f"JAX-CPU cannot be timed: jax is not installed)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import hironaka_b200 as hb
+    from hironaka_b200 import GameBatch, constants as C, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = GAMES_PER_GPU, args.steps, args.warmup
+    n_roll = min(-(-K // T_ROLLOUT), MAX_RESIDENT_ROLLOUTS)
+    n_warm = 1
+    pts, ha, ax = make_inputs(1000 + rank, B, n_roll + n_warm)
+    op_step = C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON
+    flags = C.HK_F_ACT_DISCRETE
+    # resident inputs: filtered root states (generate_pts: newton -> reposition) and action streams
+    batches = []
+    for r in range(n_roll + n_warm):
+        gb = GameBatch(torch.from_numpy(pts[r]).to(dev), semantics="jax", reposition=True, initial_filter=True)
+        batches.append(gb)
+    wraps = K > n_roll * T_ROLLOUT
+    pristine = [b.points.clone() for b in batches[:n_roll]] if wraps else None
+    ha_d = torch.from_numpy(ha).to(dev)
+    ax_d = torch.from_numpy(ax).to(dev)
+    done = torch.empty(B, dtype=torch.uint8, device=dev)
+    reward = torch.empty(B, dtype=torch.float32, device=dev)
+    lib = hb._lib.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def launch_step(r, t):
+        st = batches[r].points
+        rc = lib.hk_step(st.data_ptr(), st.data_ptr(), ha_d[r, t].data_ptr(), ax_d[r, t].data_ptr(), done.data_ptr(),
+                         reward.data_ptr(), None, None, None, None, B, N_POINTS, DIM, C.HK_DTYPE_I32, op_step, flags,
+                         -1.0, 1e8, stream)
+        if rc != 0:
+            raise RuntimeError(f"hk_step failed: {rc}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank, uuid=str(torch.cuda.get_device_properties(dev).uuid))
+    # ---- warm-up (untimed) ----
+    for i in range(max(W, 3)):
+        r, t = divmod(i, T_ROLLOUT)
+        launch_step(n_roll + (r % n_warm), t)
+    barrier()
+    # ---- timed region: EXACTLY K steps, device-timed on the launching stream ----
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(K):
+        r, t = divmod(i, T_ROLLOUT)
+        if r >= n_roll:  # K > 200: reuse a batch; its restore (one D2D copy) is charged to the timed region
+            r %= n_roll
+            if t == 0:
+                batches[r].points.copy_(pristine[r])
+        launch_step(r, t)
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    # keep the device busy a little longer so that NVML has samples under load
+    t_end = time.perf_counter() + 0.4
+    i = 0
+    while time.perf_counter() < t_end:
+        launch_step(n_roll + (i % n_warm), i % T_ROLLOUT)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+
+    if world > 1:
+        tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_ms_max = float(tmax.item())
+    else:
+        total_ms_max = total_ms
+    value = B * world * K / (total_ms_max * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    achieved = B * BYTES_PER_GAME_STEP / avg_launch_s / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "hk::hk_small_kernel<int,20,3,false>", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": B * BYTES_PER_GAME_STEP, "avg_launch_ms": avg_launch_s * 1e3,
+        "min_launch_ms": float(np.min(per_launch_ms)), "max_launch_ms": float(np.max(per_launch_ms)),
+        "int_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s,
+    }
+    cpu = None
+    if True:
+        try:
+            rate, cores, dt = cpu_rate(1 << 18, 40, 5)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{1 << 18} games x 40 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
+                             f"(C port of the reference step) over {cores} pthreads"}
+        except Exception as e:  # the CPU baseline must never take the GPU line down
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
+        "library": os.path.relpath(hb.LIB_PATH, ROOT),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist):
+    """Same K steps through GameBatch.step_host: every step copies that step's actions from
+    pinned host memory and reads the step's result (finished-game count) back to the host."""
+    ha_pin = torch.from_numpy(ha[:n_roll]).pin_memory()
+    ax_pin = torch.from_numpy(ax[:n_roll]).pin_memory()
+    batches = [GameBatch(torch.from_numpy(pts[r]).to(dev), semantics="jax", reposition=True, initial_filter=True)
+               for r in range(n_roll)]
+    warm = GameBatch(torch.from_numpy(pts[0]).to(dev), semantics="jax", reposition=True, initial_filter=True)
+    for t in range(3):
+        warm.step_host(ha_pin[0, t], ax_pin[0, t])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    total_done = 0
+    pristine = [b.points.clone() for b in batches] if K > n_roll * T_ROLLOUT else None
+    for i in range(K):
+        r, t = divmod(i, T_ROLLOUT)
+        if r >= n_roll:
+            r %= n_roll
+            if t == 0:
+                batches[r].points.copy_(pristine[r])
+        total_done += batches[r].step_host(ha_pin[r, t], ax_pin[r, t])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)  # host-blocking API: wall clock covers it too
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return {"value": B * world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4,
+            "ms_per_step": ms / K, "api": "GameBatch.step_host(pinned host_action, pinned axis) -> finished count",
+            "checksum_done": int(total_done)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,38 @@
+"""hironaka_b200 — B200-native batched Hironaka game engine (env-step path of honglu2875/hironaka).
+
+Layers (bottom up):
+  csrc/            hand-written sm_100a kernels + the extern "C" boundary (include/hironaka_b200.h)
+  _lib, ops        ctypes loader and tensor-level launch wrappers (no fallback path)
+  src              drop-in for hironaka.src torch ops (shift_torch, get_newton_polytope_torch, ...)
+  TensorPoints     drop-in for hironaka.core.TensorPoints (the `point_cls=` seam)
+  functional       drop-in for hironaka/jax/util.py (take_actions, get_dones, reward_fn, feature_fn, ...)
+  GameBatch        resident int32 batches, fused T-step rollouts, sharding + rollout all-gather
+  HostSession      NumPy host-buffer sessions over hk_session_*
+"""
+from . import constants
+from .constants import *  # noqa: F401,F403
+from ._lib import HironakaB200Error, LIB_PATH
+
+__version__ = "0.1.0"
+
+
+def __getattr__(name):  # lazy: importing the package must not require torch or a built library
+    if name in ("TensorPoints", "CudaTensorPoints"):
+        from .tensor_points import TensorPoints
+        return TensorPoints
+    if name == "PointsBase":
+        from .points_base import PointsBase
+        return PointsBase
+    if name in ("GameBatch", "shard_range", "gather_rollout"):
+        from . import engine
+        return getattr(engine, name)
+    if name == "HostSession":
+        from .session import HostSession
+        return HostSession
+    if name == "HostActionEncoder":
+        from .host_action import HostActionEncoder
+        return HostActionEncoder
+    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build"):
+        import importlib
+        return importlib.import_module(f".{name}", __name__)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

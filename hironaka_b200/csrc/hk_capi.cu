@@ -1,0 +1,423 @@
+// hk_capi.cu — the extern "C" boundary declared in include/hironaka_b200.h.
+//
+// Device entry points validate arguments, pick the kernel family for (dtype, N, d) and launch
+// on the caller's stream; they never allocate or synchronise.  Host-buffer sessions own the
+// device state of one shard and wrap the same launches with explicit H2D / D2H copies.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hk_generic.cuh"
+#include "hk_small.cuh"
+
+using hk::StepParams;
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+struct DevInfo {
+    std::atomic<int> sms{0};
+};
+DevInfo g_dev[kMaxDevices];
+
+int device_sms(int dev) {
+    if (dev < 0 || dev >= kMaxDevices) return 148;
+    int v = g_dev[dev].sms.load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        g_dev[dev].sms.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// per-kernel, per-device launch facts (dynamic smem opt-in + resident CTAs per SM), computed once
+struct KernelFacts {
+    std::atomic<int> ctas_per_sm[kMaxDevices];
+    KernelFacts() {
+        for (auto& c : ctas_per_sm) c.store(0);
+    }
+};
+
+template <typename K>
+int kernel_ctas_per_sm(K kernel, KernelFacts& facts, int dev, int threads, size_t smem, cudaError_t* err) {
+    int v = facts.ctas_per_sm[dev].load(std::memory_order_acquire);
+    if (v > 0) return v;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        *err = e;
+        return 0;
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem);
+    if (e != cudaSuccess) {
+        *err = e;
+        return 0;
+    }
+    if (v < 1) v = 1;
+    facts.ctas_per_sm[dev].store(v, std::memory_order_release);
+    return v;
+}
+
+// ---- small (thread-per-game) family -----------------------------------------------------------
+template <typename T, int N, int D, bool OBS>
+int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
+    using L = hk::SmallLayout<N, D, OBS>;
+    static KernelFacts facts;
+    auto kernel = hk::hk_small_kernel<T, N, D, OBS>;
+    cudaError_t err = cudaSuccess;
+    const int threads = hk::SMALL_WARPS * 32;
+    const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
+    if (err != cudaSuccess) return (int)err;
+    const long long ntiles = (p.B + 31) / 32;
+    long long ctas = (ntiles + hk::SMALL_WARPS - 1) / hk::SMALL_WARPS;
+    const long long cap = (long long)device_sms(dev) * per_sm;  // persistent: one wave
+    if (ctas > cap) ctas = cap;
+    kernel<<<(unsigned)ctas, threads, L::SMEM_BYTES, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, bool OBS>
+int dispatch_small(const StepParams& p, int dev, cudaStream_t stream) {
+    if (p.d == 3) {
+        if (p.N == 20) return launch_small<T, 20, 3, OBS>(p, dev, stream);
+        if (p.N == 10) return launch_small<T, 10, 3, OBS>(p, dev, stream);
+        if (p.N == 5) return launch_small<T, 5, 3, OBS>(p, dev, stream);
+    }
+    return HK_ERR_UNSUPPORTED;
+}
+
+bool is_small(int N, int d) { return d == 3 && (N == 20 || N == 10 || N == 5); }
+
+// ---- generic (warp-per-game) family -------------------------------------------------------------
+template <typename T, int D, bool OBS>
+int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
+    static KernelFacts facts[9];  // indexed by warps per CTA (1..8)
+    auto kernel = hk::hk_generic_kernel<T, D, OBS>;
+    const int W = p.N * D;
+    const int Wpad = (W + 3) & ~3;
+    const int R = (p.N + 31) / 32;
+    const int slot_words = Wpad * (OBS ? 2 : 1) + ((R + 3) & ~3);
+    int warps = 8;
+    while (warps > 1 && 128 + (size_t)warps * slot_words * 4 > 160 * 1024) warps >>= 1;
+    const size_t smem = 128 + (size_t)warps * slot_words * 4;
+    cudaError_t err = cudaSuccess;
+    // the smem opt-in depends on N; always (re)apply the max so that a later larger N works
+    static std::atomic<size_t> smem_set[kMaxDevices];
+    if (smem > smem_set[dev].load(std::memory_order_acquire)) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        smem_set[dev].store(smem, std::memory_order_release);
+    }
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
+    if (err != cudaSuccess) return (int)err;
+    if (per_sm < 1) per_sm = 1;
+    (void)facts;
+    long long ctas = (p.B + warps - 1) / warps;
+    const long long cap = (long long)device_sms(dev) * per_sm;
+    if (ctas > cap) ctas = cap;
+    kernel<<<(unsigned)ctas, warps * 32, smem, stream>>>(p, warps, slot_words);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, bool OBS>
+int dispatch_generic(const StepParams& p, int dev, cudaStream_t stream) {
+    switch (p.d) {
+        case 1: return launch_generic<T, 1, OBS>(p, dev, stream);
+        case 2: return launch_generic<T, 2, OBS>(p, dev, stream);
+        case 3: return launch_generic<T, 3, OBS>(p, dev, stream);
+        case 4: return launch_generic<T, 4, OBS>(p, dev, stream);
+        case 5: return launch_generic<T, 5, OBS>(p, dev, stream);
+        case 6: return launch_generic<T, 6, OBS>(p, dev, stream);
+        case 7: return launch_generic<T, 7, OBS>(p, dev, stream);
+        case 8: return launch_generic<T, 8, OBS>(p, dev, stream);
+        case 9: return launch_generic<T, 9, OBS>(p, dev, stream);
+        case 10: return launch_generic<T, 10, OBS>(p, dev, stream);
+        default: return HK_ERR_UNSUPPORTED;
+    }
+}
+
+int check_shape(long long B, int N, int d, int dtype) {
+    if (B < 0 || N < 1 || d < 1) return HK_ERR_BAD_ARG;
+    if (dtype != HK_DTYPE_I32 && dtype != HK_DTYPE_F32) return HK_ERR_BAD_ARG;
+    if (d > HK_MAX_DIM || N > HK_MAX_POINTS || (long long)N * d > HK_MAX_GAME_WORDS) return HK_ERR_UNSUPPORTED;
+    return HK_OK;
+}
+
+int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
+    int rc = check_shape(p.B, p.N, p.d, dtype);
+    if (rc != HK_OK) return rc;
+    if (p.in == nullptr) return HK_ERR_BAD_ARG;
+    if ((((uintptr_t)p.in) & 3u) || (((uintptr_t)p.out) & 3u)) return HK_ERR_ALIGN;
+    if ((p.ops & HK_OP_SHIFT) && (p.host_action == nullptr || p.axis == nullptr)) return HK_ERR_BAD_ARG;
+    if ((p.ops & HK_OP_RESCALE) && dtype != HK_DTYPE_F32) return HK_ERR_UNSUPPORTED;
+    if (p.ops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON | HK_OP_RESCALE | HK_OP_DEDUPE)) return HK_ERR_BAD_ARG;
+    if ((p.flags & HK_F_OBS_SORT_COORD0) && (p.flags & HK_F_OBS_SORT_LEX)) return HK_ERR_BAD_ARG;
+    if (p.T < 1) return HK_ERR_BAD_ARG;
+    if (p.B == 0) return HK_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    const bool obs = p.obs != nullptr;
+    const bool small = is_small(p.N, p.d) && !force_generic;
+    if (dtype == HK_DTYPE_I32) {
+        if (small) return obs ? dispatch_small<int32_t, true>(p, dev, stream) : dispatch_small<int32_t, false>(p, dev, stream);
+        return obs ? dispatch_generic<int32_t, true>(p, dev, stream) : dispatch_generic<int32_t, false>(p, dev, stream);
+    }
+    if (small) return obs ? dispatch_small<float, true>(p, dev, stream) : dispatch_small<float, false>(p, dev, stream);
+    return obs ? dispatch_generic<float, true>(p, dev, stream) : dispatch_generic<float, false>(p, dev, stream);
+}
+
+StepParams make_params(const void* in, void* out, long long B, int N, int d, float pad) {
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in;
+    p.out = out;
+    p.B = B;
+    p.N = N;
+    p.d = d;
+    p.T = 1;
+    p.pad = pad;
+    p.threshold = 1e8f;
+    return p;
+}
+
+std::atomic<int> g_force_generic{0};
+
+}  // namespace
+
+extern "C" {
+
+int hk_version(void) { return HK_VERSION; }
+
+const char* hk_error_string(int code) {
+    switch (code) {
+        case HK_OK: return "ok";
+        case HK_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or bad flag combination)";
+        case HK_ERR_UNSUPPORTED: return "unsupported shape or op for this dtype";
+        case HK_ERR_ALIGN: return "state pointer is not 4-byte aligned";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int hk_kernel_class(int N, int d) {
+    if (check_shape(1, N, d, HK_DTYPE_I32) != HK_OK) return HK_ERR_UNSUPPORTED;
+    return (is_small(N, d) && !g_force_generic.load()) ? 1 : 0;
+}
+
+// test hook: route small shapes through the generic warp-per-game kernel as well
+int hk_debug_force_generic(int on) {
+    g_force_generic.store(on ? 1 : 0);
+    return HK_OK;
+}
+
+int hk_step(const void* state_in, void* state_out, const int32_t* host_action, const int32_t* axis, uint8_t* done,
+            float* reward, int32_t* num_points, float* obs, const int32_t* obs_coord, int32_t* exceed_flag,
+            int64_t B, int32_t N, int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value,
+            float value_threshold, void* stream) {
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.host_action = host_action;
+    p.axis = axis;
+    p.done = done;
+    p.reward = reward;
+    p.num_points = num_points;
+    p.obs = obs;
+    p.obs_coord = obs_coord;
+    p.exceed_flag = exceed_flag;
+    p.ops = ops;
+    p.flags = flags;
+    p.threshold = value_threshold;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_shift(const void* state_in, void* state_out, const int32_t* host_action, const int32_t* axis, int64_t B,
+             int32_t N, int32_t d, int32_t dtype, uint32_t flags, float padding_value, void* stream) {
+    if (state_out == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.host_action = host_action;
+    p.axis = axis;
+    p.ops = HK_OP_SHIFT;
+    p.flags = flags;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_reposition(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                  float padding_value, void* stream) {
+    if (state_out == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.ops = HK_OP_REPOSITION;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_newton_polytope(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                       float padding_value, void* stream) {
+    if (state_out == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.ops = HK_OP_NEWTON;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_rescale(const void* state_in, void* state_out, int64_t B, int32_t N, int32_t d, int32_t dtype,
+               float padding_value, void* stream) {
+    if (state_out == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.ops = HK_OP_RESCALE;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_features(const void* state_in, float* obs, const int32_t* obs_coord, int64_t B, int32_t N, int32_t d,
+                int32_t dtype, uint32_t flags, float padding_value, void* stream) {
+    if (obs == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, nullptr, B, N, d, padding_value);
+    p.obs = obs;
+    p.obs_coord = obs_coord;
+    p.flags = flags;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_dones(const void* state_in, uint8_t* done, int32_t* num_points, int64_t B, int32_t N, int32_t d,
+             int32_t dtype, void* stream) {
+    if (done == nullptr && num_points == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, nullptr, B, N, d, -1.0f);
+    p.done = done;
+    p.num_points = num_points;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action_t, const int32_t* axis_t,
+               uint8_t* done_t, float* reward_t, int32_t* done_count, int32_t* length, int64_t B, int32_t N,
+               int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value,
+               void* stream) {
+    if (T < 1) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.host_action = host_action_t;
+    p.axis = axis_t;
+    p.done = done_t;
+    p.reward = reward_t;
+    p.done_count = done_count;
+    p.length = length;
+    p.T = T;
+    p.ops = ops;
+    p.flags = flags;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+// ---- host-buffer sessions ----------------------------------------------------------------------
+struct hk_session {
+    int device;
+    long long B;
+    int N, d, dtype;
+    float pad;
+    cudaStream_t stream;
+    void* state;
+    int32_t* host_action;
+    int32_t* axis;
+    uint8_t* done;
+    float* reward;
+    int32_t* done_count;
+};
+
+#define HK_CUDA(x)                       \
+    do {                                 \
+        cudaError_t e_ = (x);            \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                      float padding_value) {
+    if (out == nullptr || B < 1) return HK_ERR_BAD_ARG;
+    int rc = check_shape(B, N, d, dtype);
+    if (rc != HK_OK) return rc;
+    HK_CUDA(cudaSetDevice(device));
+    hk_session* s = new (std::nothrow) hk_session();
+    if (!s) return HK_ERR_BAD_ARG;
+    memset(s, 0, sizeof(*s));
+    s->device = device;
+    s->B = B;
+    s->N = N;
+    s->d = d;
+    s->dtype = dtype;
+    s->pad = padding_value;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->state, (size_t)B * N * d * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->host_action, (size_t)B * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->reward, (size_t)B * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_count, 4);
+    if (e != cudaSuccess) {
+        hk_session_destroy(s);
+        return (int)e;
+    }
+    *out = s;
+    return HK_OK;
+}
+
+int hk_session_destroy(hk_session* s) {
+    if (!s) return HK_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->state);
+    cudaFree(s->host_action);
+    cudaFree(s->axis);
+    cudaFree(s->done);
+    cudaFree(s->reward);
+    cudaFree(s->done_count);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return HK_OK;
+}
+
+int hk_session_set_state(hk_session* s, const void* state_host) {
+    if (!s || !state_host) return HK_ERR_BAD_ARG;
+    HK_CUDA(cudaSetDevice(s->device));
+    HK_CUDA(cudaMemcpyAsync(s->state, state_host, (size_t)s->B * s->N * s->d * 4, cudaMemcpyHostToDevice, s->stream));
+    HK_CUDA(cudaStreamSynchronize(s->stream));
+    return HK_OK;
+}
+
+int hk_session_get_state(hk_session* s, void* state_host) {
+    if (!s || !state_host) return HK_ERR_BAD_ARG;
+    HK_CUDA(cudaSetDevice(s->device));
+    HK_CUDA(cudaMemcpyAsync(state_host, s->state, (size_t)s->B * s->N * s->d * 4, cudaMemcpyDeviceToHost, s->stream));
+    HK_CUDA(cudaStreamSynchronize(s->stream));
+    return HK_OK;
+}
+
+int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_t* axis_host, uint8_t* done_host,
+                    float* reward_host, int32_t* done_count_host, uint32_t ops, uint32_t flags) {
+    if (!s) return HK_ERR_BAD_ARG;
+    if ((ops & HK_OP_SHIFT) && (!host_action_host || !axis_host)) return HK_ERR_BAD_ARG;
+    HK_CUDA(cudaSetDevice(s->device));
+    if (ops & HK_OP_SHIFT) {
+        HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, (size_t)s->B * 4, cudaMemcpyHostToDevice, s->stream));
+        HK_CUDA(cudaMemcpyAsync(s->axis, axis_host, (size_t)s->B * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
+    p.host_action = s->host_action;
+    p.axis = s->axis;
+    p.done = done_host ? s->done : nullptr;
+    p.reward = reward_host ? s->reward : nullptr;
+    p.ops = ops;
+    p.flags = flags;
+    if (done_count_host) {
+        HK_CUDA(cudaMemsetAsync(s->done_count, 0, 4, s->stream));
+        p.done_count = s->done_count;
+    }
+    int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
+    if (rc != HK_OK) return rc;
+    if (done_host) HK_CUDA(cudaMemcpyAsync(done_host, s->done, (size_t)s->B, cudaMemcpyDeviceToHost, s->stream));
+    if (reward_host) HK_CUDA(cudaMemcpyAsync(reward_host, s->reward, (size_t)s->B * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (done_count_host) HK_CUDA(cudaMemcpyAsync(done_count_host, s->done_count, 4, cudaMemcpyDeviceToHost, s->stream));
+    HK_CUDA(cudaStreamSynchronize(s->stream));
+    return HK_OK;
+}
+
+void* hk_session_state_ptr(hk_session* s) { return s ? s->state : nullptr; }
+void* hk_session_stream(hk_session* s) { return s ? (void*)s->stream : nullptr; }
+
+}  // extern "C"

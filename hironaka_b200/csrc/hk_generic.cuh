@@ -1,0 +1,347 @@
+// hk_generic.cuh — warp-per-game step kernel for any (N <= 1024, d <= 10).
+//
+// Mapping (DESIGN.md "K-warp"): one warp owns one game at a time; the game's N*d words live
+// in the warp's private shared-memory slot (TMA bulk load when the game is 16-byte sized and
+// aligned, cooperative LDG otherwise); lane l owns rows l, l+32, ...  The dominance filter
+// broadcasts candidate dominators j from shared memory (uniform address => one wavefront) and
+// iterates ONLY over live j (warp-uniform loop over the ballot words), so cost tracks the
+// number of live points rather than N.  This is the kernel for BASELINE config 5 (N=64, d=5).
+#pragma once
+#include "hk_common.cuh"
+
+namespace hk {
+
+constexpr int GEN_MAX_ROWS_PER_LANE = HK_MAX_POINTS / 32;
+
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// smem per warp: x[N*D] words, then (OBS) f[N*D] floats, then live-mask words lmw[ceil(N/32)]
+template <typename T, int D, bool OBS>
+__global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N;
+    const int W = N * D;
+    const int R = (N + 31) >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 128) + (size_t)warp * slot_words;
+    T* x = reinterpret_cast<T*>(slot);
+    const int Wpad = (W + 3) & ~3;
+    float* f = reinterpret_cast<float*>(slot + Wpad);
+    uint32_t* lmw = slot + Wpad + (OBS ? Wpad : 0);
+
+    const uint32_t* gin = reinterpret_cast<const uint32_t*>(p.in);
+    uint32_t* gout = reinterpret_cast<uint32_t*>(p.out);
+    const bool tma = aligned16(p.in) && aligned16(p.out) && ((W & 3) == 0);
+    const T padv = Elem<T>::pad(p.pad);
+    const int OW = W + (p.obs_coord ? D : 0);
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+
+    const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long nw = (long long)gridDim.x * warps_per_cta;
+    for (long long g = gw; g < p.B; g += nw) {
+        // ---- load the game ----
+        if (tma) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)W * 4u);
+                bulk_load(slot, gin + g * W, (uint32_t)W * 4u, bar);
+            }
+        } else {
+            for (int w = lane; w < W; w += 32) slot[w] = gin[g * W + w];
+        }
+        int32_t ha = 3, ax = 0;
+        if (p.ops & HK_OP_SHIFT) {
+            ha = __ldg(p.host_action + g);
+            ax = __ldg(p.axis + g);
+        }
+        if (tma) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            __syncwarp();
+        }
+
+        // ---- liveness ----
+        uint32_t mylive = 0;  // bit r <=> row lane + 32 r is live
+        int cnt = 0;
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            bool lv = false;
+            if (i < N) {
+                if constexpr (Elem<T>::is_float) {
+                    for (int k = 0; k < D; ++k) x[i * D + k] = x[i * D + k] + 0.0f;
+                }
+                lv = x[i * D] >= Elem<T>::zero();
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, lv);
+            cnt += __popc(bal);
+            mylive |= lv ? (1u << r) : 0u;
+        }
+        int32_t len = (cnt < 2) ? 0 : p.T + 1;
+        for (int st = 0; st < p.T; ++st) {
+            int32_t ha_n = 3, ax_n = 0;
+            if ((p.ops & HK_OP_SHIFT) && st + 1 < p.T) {
+                ha_n = __ldg(p.host_action + (long long)(st + 1) * p.B + g);
+                ax_n = __ldg(p.axis + (long long)(st + 1) * p.B + g);
+            }
+            const bool prev_done = cnt < 2;
+
+            // ---- shift ----
+            if (p.ops & HK_OP_SHIFT) {
+                const uint32_t cm = action_mask(ha, p.flags);
+                bool apply = (ax >= 0) && (ax < D);
+                if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                if (p.flags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
+                if (apply) {
+                    for (int r = 0; r < R; ++r) {
+                        if (!((mylive >> r) & 1u)) continue;
+                        const int i = lane + 32 * r;
+                        T s = Elem<T>::zero();
+    #pragma unroll
+                        for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + x[i * D + k] : s;
+                        x[i * D + ax] = s;
+                    }
+                }
+            }
+            // ---- reposition ----
+            if (p.ops & HK_OP_REPOSITION) {
+    #pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    T mn = Elem<T>::big();
+                    for (int r = 0; r < R; ++r) {
+                        if (!((mylive >> r) & 1u)) continue;
+                        T v = x[(lane + 32 * r) * D + k];
+                        mn = v < mn ? v : mn;
+                    }
+                    mn = warp_min<T>(mn);
+                    for (int r = 0; r < R; ++r) {
+                        if (!((mylive >> r) & 1u)) continue;
+                        x[(lane + 32 * r) * D + k] -= mn;
+                    }
+                }
+            }
+            // ---- dedupe alone (remove_repeated _fn.py:192-213) ----
+            if (p.ops & HK_OP_DEDUPE) {
+                __syncwarp();
+                uint32_t kill = 0;
+                for (int r = 0; r < R; ++r) {
+                    if (!((mylive >> r) & 1u)) continue;
+                    const int i = lane + 32 * r;
+                    bool rep = false;
+                    for (int j = 0; j < i; ++j) {
+                        bool eq = x[j * D] >= Elem<T>::zero();
+#pragma unroll
+                        for (int k = 0; k < D; ++k) eq = eq && (x[i * D + k] == x[j * D + k]);
+                        rep = rep || eq;
+                    }
+                    kill |= rep ? (1u << r) : 0u;
+                }
+                __syncwarp();
+                mylive &= ~kill;
+            }
+            // ---- newton: dedupe + dominance, reading the pre-removal state ----
+            if (p.ops & HK_OP_NEWTON) {
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, (mylive >> r) & 1u);
+                    if (lane == 0) lmw[r] = bal;
+                }
+                __syncwarp();
+                uint32_t kill = 0;
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    const bool lv = (mylive >> r) & 1u;
+                    T xi[D];
+    #pragma unroll
+                    for (int k = 0; k < D; ++k) xi[k] = lv ? x[i * D + k] : Elem<T>::big();
+                    int32_t acc = (int32_t)0x80000000;
+                    for (int r2 = 0; r2 < R; ++r2) {
+                        uint32_t m = lmw[r2];
+                        while (m) {
+                            const int j = 32 * r2 + __ffs((int)m) - 1;
+                            m &= m - 1;
+                            int32_t t = Elem<T>::bits(xi[0] - x[j * D]);
+    #pragma unroll
+                            for (int k = 1; k < D; ++k) t |= Elem<T>::bits(xi[k] - x[j * D + k]);
+                            t -= (j > i) ? 1 : 0;
+                            t = (j == i) ? (int32_t)0x80000000 : t;
+                            acc &= t;
+                        }
+                    }
+                    kill |= (acc >= 0) ? (1u << r) : 0u;
+                }
+                __syncwarp();
+                mylive &= ~kill;
+            }
+            // ---- rescale (float state) ----
+            if constexpr (Elem<T>::is_float) {
+                if (p.ops & HK_OP_RESCALE) {
+                    float mx = -1.0f;
+                    for (int r = 0; r < R; ++r) {
+                        if (!((mylive >> r) & 1u)) continue;
+                        const int i = lane + 32 * r;
+    #pragma unroll
+                        for (int k = 0; k < D; ++k) mx = fmaxf(mx, x[i * D + k]);
+                    }
+                    mx = warp_maxf(mx);
+                    if (mx == 0.0f) mx = 1.0f;
+                    if (mx > 0.0f) {
+                        for (int r = 0; r < R; ++r) {
+                            if (!((mylive >> r) & 1u)) continue;
+                            const int i = lane + 32 * r;
+    #pragma unroll
+                            for (int k = 0; k < D; ++k) x[i * D + k] = __fdiv_rn(x[i * D + k], mx);
+                        }
+                    }
+                }
+            }
+            // ---- per-step outputs ----
+            cnt = 0;
+            for (int r = 0; r < R; ++r) cnt += __popc(__ballot_sync(0xffffffffu, (mylive >> r) & 1u));
+            const bool dn = cnt < 2;
+            if (lane == 0) {
+                if (p.done) p.done[(long long)st * p.B + g] = dn ? 1 : 0;
+                if (p.reward) {
+                    float rw = (dn && !prev_done) ? 1.0f : 0.0f;
+                    p.reward[(long long)st * p.B + g] = (p.flags & HK_F_ROLE_AGENT) ? -rw : rw;
+                }
+                if (p.done_count && dn) atomicAdd(p.done_count + st, 1);
+            }
+            if (dn && !prev_done) len = st + 1;
+            ha = ha_n;
+            ax = ax_n;
+            __syncwarp();
+        }
+        // ---- outputs ----
+        bool exceed = false;
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + 32 * r;
+            const bool lv = (mylive >> r) & 1u;
+            if (i < N) {
+                if (lv) {
+                    if (p.exceed_flag) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) exceed |= Elem<T>::to_float(x[i * D + k]) >= p.threshold;
+                    }
+                } else if (p.ops) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[i * D + k] = padv;
+                }
+            }
+        }
+        if (lane == 0) {
+            if (p.num_points) p.num_points[g] = cnt;
+            if (p.length) p.length[g] = len;
+        }
+        if (p.exceed_flag) {
+            if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
+        }
+        bool stored = false;
+        if (gout) {
+            if (tma) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(gout + g * W, slot, (uint32_t)W * 4u);
+                    bulk_commit();
+                }
+                stored = true;
+            } else {
+                __syncwarp();
+                for (int w = lane; w < W; w += 32) gout[g * W + w] = slot[w];
+            }
+        }
+        // ---- observation features ----
+        if constexpr (OBS) {
+            if (p.obs) {
+                __syncwarp();
+                float mx = -1.0f;
+                for (int r = 0; r < R; ++r) {
+                    if (!((mylive >> r) & 1u)) continue;
+                    const int i = lane + 32 * r;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) mx = fmaxf(mx, Elem<T>::to_float(x[i * D + k]));
+                }
+                mx = warp_maxf(mx);
+                if (mx == 0.0f) mx = 1.0f;
+                const bool resc = (p.flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i >= N) continue;
+                    const bool lv = (mylive >> r) & 1u;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        float v = Elem<T>::to_float(x[i * D + k]);
+                        v = resc ? __fdiv_rn(v, mx) : v;
+                        f[i * D + k] = lv ? v : p.pad;
+                    }
+                }
+                __syncwarp();
+                float* gobs = p.obs + g * (long long)OW;
+                const bool sorted = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX);
+                const bool lex = p.flags & HK_F_OBS_SORT_LEX;
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i >= N) continue;
+                    float fi[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) fi[k] = f[i * D + k];
+                    int rank = i;
+                    if (sorted) {
+                        rank = 0;
+                        for (int j = 0; j < N; ++j) {
+                            bool gt = f[j * D] > fi[0];
+                            bool eq = f[j * D] == fi[0];
+                            if (lex) {
+#pragma unroll
+                                for (int k = 1; k < D; ++k) {
+                                    const float fj = f[j * D + k];
+                                    gt = (fj > fi[k]) || ((fj == fi[k]) && gt);
+                                    eq = eq && (fj == fi[k]);
+                                }
+                            }
+                            rank += (gt || (eq && j < i)) ? 1 : 0;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gobs[rank * D + k] = fi[k];
+                }
+                if (p.obs_coord && lane < D) {
+                    const uint32_t ocm = action_mask(__ldg(p.obs_coord + g), p.flags);
+                    gobs[W + lane] = (float)((ocm >> lane) & 1u);
+                }
+            }
+        }
+        __syncwarp();
+        if (stored && lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+}  // namespace hk

@@ -1,0 +1,455 @@
+// hk_small.cuh — thread-per-game step kernel for small games (N <= 32, N*d words in registers).
+//
+// Mapping (DESIGN.md "K-small"): one lane owns one game; a warp owns tiles of 32 consecutive
+// games.  Each warp runs a private STAGES-deep shared-memory ring: lane 0 issues one TMA bulk
+// load per tile (32*N*d*4 contiguous bytes), all lanes wait on the stage's mbarrier, read
+// their own game with conflict-free vector LDS (game stride N*d words: 16-byte reads are
+// conflict-free when N*d/4 is odd, 8-byte when N*d/2 is odd, 4-byte when N*d is odd — true for
+// (20,3), (10,3), (5,3)), run the whole step in registers with every loop fully unrolled, write
+// the new state back into the same stage and lane 0 issues one TMA bulk store.  No CTA-wide
+// barrier exists anywhere; warps drift freely, which overlaps one warp's loads with another's
+// ALU phase.
+#pragma once
+#include "hk_common.cuh"
+
+namespace hk {
+
+constexpr int SMALL_WARPS = 4;   // warps per CTA
+constexpr int SMALL_STAGES = 2;  // ring depth per warp
+constexpr int SMALL_BAR_BYTES = 128;
+
+template <int N, int D, bool OBS>
+struct SmallLayout {
+    static constexpr int W = N * D;
+    static constexpr int TILE_WORDS = 32 * W;
+    static constexpr int OBS_W = W + D;
+    static constexpr int OBS_WORDS = OBS ? 32 * OBS_W : 0;
+    static constexpr int WARP_WORDS = SMALL_STAGES * TILE_WORDS + OBS_WORDS;
+    static constexpr size_t SMEM_BYTES = SMALL_BAR_BYTES + (size_t)SMALL_WARPS * WARP_WORDS * 4;
+};
+
+// ---- game <-> shared memory -------------------------------------------------------------------
+template <typename T, int W>
+__device__ __forceinline__ void load_game(const uint32_t* s, T (&x)[W]) {
+    if constexpr (W % 4 == 0) {
+        const uint4* p = reinterpret_cast<const uint4*>(s);
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            uint4 v = p[q];
+            x[4 * q + 0] = Elem<T>::from_bits(v.x);
+            x[4 * q + 1] = Elem<T>::from_bits(v.y);
+            x[4 * q + 2] = Elem<T>::from_bits(v.z);
+            x[4 * q + 3] = Elem<T>::from_bits(v.w);
+        }
+    } else if constexpr (W % 2 == 0) {
+        const uint2* p = reinterpret_cast<const uint2*>(s);
+#pragma unroll
+        for (int q = 0; q < W / 2; ++q) {
+            uint2 v = p[q];
+            x[2 * q + 0] = Elem<T>::from_bits(v.x);
+            x[2 * q + 1] = Elem<T>::from_bits(v.y);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q) x[q] = Elem<T>::from_bits(s[q]);
+    }
+}
+
+template <typename T, int W>
+__device__ __forceinline__ void store_game(uint32_t* s, const T (&x)[W]) {
+    if constexpr (W % 4 == 0) {
+        uint4* p = reinterpret_cast<uint4*>(s);
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q)
+            p[q] = make_uint4((uint32_t)Elem<T>::bits(x[4 * q]), (uint32_t)Elem<T>::bits(x[4 * q + 1]),
+                              (uint32_t)Elem<T>::bits(x[4 * q + 2]), (uint32_t)Elem<T>::bits(x[4 * q + 3]));
+    } else if constexpr (W % 2 == 0) {
+        uint2* p = reinterpret_cast<uint2*>(s);
+#pragma unroll
+        for (int q = 0; q < W / 2; ++q)
+            p[q] = make_uint2((uint32_t)Elem<T>::bits(x[2 * q]), (uint32_t)Elem<T>::bits(x[2 * q + 1]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q) s[q] = (uint32_t)Elem<T>::bits(x[q]);
+    }
+}
+
+// ---- the per-game ops, state in registers --------------------------------------------------------
+template <typename T, int N, int D>
+__device__ __forceinline__ uint32_t live_mask(const T (&x)[N * D]) {
+    uint32_t lm = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) lm |= (x[i * D] >= Elem<T>::zero()) ? (1u << i) : 0u;
+    return lm;
+}
+
+// shift: x_a <- sum_{j in S} x_j on live rows (shift_torch _torch_ops.py:46-110, shift_jax _jax_ops.py:76-90)
+template <typename T, int N, int D>
+__device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm, int a, bool apply) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T s = Elem<T>::zero();
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if constexpr (Elem<T>::is_float) {
+                s = ((cm >> k) & 1u) ? s + x[i * D + k] : s;
+            } else {
+                s = (T)((uint32_t)s + (((cm >> k) & 1u) ? (uint32_t)x[i * D + k] : 0u));
+            }
+        }
+        const bool upd = apply && ((lm >> i) & 1u);
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[i * D + k] = (upd && k == a) ? s : x[i * D + k];
+    }
+}
+
+// reposition: per coordinate subtract the min over live rows (reposition_torch _torch_ops.py:113-133)
+template <typename T, int N, int D>
+__device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        T mn = Elem<T>::big();
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T v = ((lm >> i) & 1u) ? x[i * D + k] : Elem<T>::big();
+            mn = v < mn ? v : mn;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] - mn : x[i * D + k];
+    }
+}
+
+// Newton polytope (approx): fused dedupe + dominance (remove_repeated _fn.py:192-213 followed by
+// get_newton_polytope_approx_torch _torch_ops.py:8-39).  Row i dies iff some row j != i has
+// x_j <= x_i componentwise and (x_j != x_i or j < i).  With t = OR_k bits(x_i[k] - x_j[k]):
+//   sign(t) = 0  <=> x_j <= x_i;  t == 0 <=> equal.  For j > i the tie must not kill, which is
+//   sign(t - 1) = 0 <=> t > 0.  The AND over j of these words has sign 0 iff some j kills i.
+// Dead rows are parked at +BIG so they dominate nothing and no liveness test is needed per pair.
+template <typename T, int N, int D>
+__device__ __forceinline__ uint32_t op_newton(T (&x)[N * D], uint32_t lm) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] : Elem<T>::big();
+    }
+    uint32_t kill = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int32_t acc = (int32_t)0x80000000;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            int32_t t = Elem<T>::bits(x[i * D] - x[j * D]);
+#pragma unroll
+            for (int k = 1; k < D; ++k) t |= Elem<T>::bits(x[i * D + k] - x[j * D + k]);
+            if (j > i) t -= 1;
+            acc &= t;
+        }
+        kill |= (acc >= 0) ? (1u << i) : 0u;
+    }
+    return lm & ~kill;
+}
+
+// remove_repeated alone (_fn.py:192-213): row i dies iff an identical row j < i exists.
+template <typename T, int N, int D>
+__device__ __forceinline__ uint32_t op_dedupe(const T (&x)[N * D], uint32_t lm) {
+    uint32_t kill = 0;
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        bool rep = false;
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            bool eq = ((lm >> j) & 1u) != 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) eq = eq && (x[i * D + k] == x[j * D + k]);
+            rep = rep || eq;
+        }
+        kill |= rep ? (1u << i) : 0u;
+    }
+    return lm & ~kill;
+}
+
+// rescale (float state): live entries / game max, max == 0 -> 1 (rescale_torch _torch_ops.py:136-146)
+template <int N, int D>
+__device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm) {
+    float mx = -1.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) mx = ((lm >> i) & 1u) ? fmaxf(mx, x[i * D + k]) : mx;
+    }
+    if (mx == 0.0f) mx = 1.0f;
+    if (mx > 0.0f) {
+#pragma unroll
+        for (int i = 0; i < N * D; ++i) x[i] = __fdiv_rn(x[i], mx);
+    }
+}
+
+template <typename T, int N, int D>
+__device__ __forceinline__ bool exceeds(const T (&x)[N * D], uint32_t lm, float threshold) {
+    bool e = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) e |= ((lm >> i) & 1u) && (Elem<T>::to_float(x[i * D + k]) >= threshold);
+    }
+    return e;
+}
+
+// One full step of one game in registers.  Returns the new live mask; x holds garbage in dead rows.
+template <typename T, int N, int D>
+__device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
+                                              int32_t ax) {
+    if (ops & HK_OP_SHIFT) {
+        const uint32_t cm = action_mask(ha, flags);
+        bool apply = (ax >= 0) && (ax < D);
+        if (flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+        if (flags & HK_F_FREEZE_ENDED) apply = apply && (__popc(lm) >= 2);
+        op_shift<T, N, D>(x, lm, cm, ax, apply);
+    }
+    if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm);
+    if (ops & HK_OP_DEDUPE) lm = op_dedupe<T, N, D>(x, lm);
+    if (ops & HK_OP_NEWTON) lm = op_newton<T, N, D>(x, lm);
+    if constexpr (Elem<T>::is_float) {
+        if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm);
+    }
+    return lm;
+}
+
+// Observation features of one game: optional rescale, stable descending rank sort, scatter into
+// the lane's row of the obs tile.  (TensorPoints.get_features tensor_points.py:72-74;
+// order_and_rescale util.py:186-196.)
+template <typename T, int N, int D>
+__device__ __forceinline__ void game_features(const T (&x)[N * D], uint32_t lm, uint32_t flags, float padf,
+                                              float* row) {
+    float f[N * D];
+    float mx = -1.0f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float v = Elem<T>::to_float(x[i * D + k]);
+            f[i * D + k] = v;
+            mx = ((lm >> i) & 1u) ? fmaxf(mx, v) : mx;
+        }
+    }
+    if (mx == 0.0f) mx = 1.0f;
+    const bool resc = (flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float v = f[i * D + k];
+            v = resc ? __fdiv_rn(v, mx) : v;
+            f[i * D + k] = ((lm >> i) & 1u) ? v : padf;
+        }
+    }
+    int rank[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) rank[i] = i;
+    if (flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX)) {
+        const bool lex = flags & HK_F_OBS_SORT_LEX;
+#pragma unroll
+        for (int i = 0; i < N; ++i) rank[i] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                // does row j sort strictly before row i?  (ties: lower index first)
+                bool gt = f[j * D] > f[i * D];
+                if (lex) {
+#pragma unroll
+                    for (int k = 1; k < D; ++k)
+                        gt = (f[j * D + k] > f[i * D + k]) || ((f[j * D + k] == f[i * D + k]) && gt);
+                }
+                rank[i] += gt ? 1 : 0;
+                rank[j] += gt ? 0 : 1;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) row[rank[i] * D + k] = f[i * D + k];
+    }
+}
+
+// ---- tile movement -------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
+    for (int w = lane; w < words; w += 32) dst[w] = src[w];
+}
+
+template <typename T, int N, int D, bool OBS>
+__global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepParams p) {
+    using L = SmallLayout<N, D, OBS>;
+    constexpr int W = L::W;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp * SMALL_STAGES;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + SMALL_BAR_BYTES) + (size_t)warp * L::WARP_WORDS;
+    float* obs_tile = reinterpret_cast<float*>(ring + SMALL_STAGES * L::TILE_WORDS);
+
+    const long long B = p.B;
+    const long long ntiles = (B + 31) >> 5;
+    const long long gw = (long long)blockIdx.x * SMALL_WARPS + warp;
+    const long long nw = (long long)gridDim.x * SMALL_WARPS;
+    const uint32_t* gin = reinterpret_cast<const uint32_t*>(p.in);
+    uint32_t* gout = reinterpret_cast<uint32_t*>(p.out);
+    const bool tma_base = aligned16(p.in) && aligned16(p.out);
+    const int OW = W + (p.obs_coord ? D : 0);
+    const bool obs_tma = aligned16(p.obs);
+    const T padv = Elem<T>::pad(p.pad);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < SMALL_STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto tile_words = [&](long long t) -> int {
+        long long left = B - (t << 5);
+        return (int)(left < 32 ? left : 32) * W;
+    };
+    auto tile_tma = [&](long long t) -> bool { return tma_base && ((tile_words(t) & 3) == 0); };
+    auto issue_load = [&](long long t, int s) {
+        if (t < ntiles && tile_tma(t)) {
+            const uint32_t bytes = (uint32_t)tile_words(t) * 4u;
+            mbar_expect_tx(&bar[s], bytes);
+            bulk_load(ring + s * L::TILE_WORDS, gin + t * (long long)L::TILE_WORDS, bytes, &bar[s]);
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < SMALL_STAGES; ++s) issue_load(gw + s * nw, s);
+    }
+
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+    int s = 0;
+    for (long long t = gw; t < ntiles; t += nw) {
+        uint32_t* stage = ring + s * L::TILE_WORDS;
+        const long long g = (t << 5) + lane;
+        const bool valid = g < B;
+        const int words = tile_words(t);
+        const bool tma = tile_tma(t);
+
+        const bool shift = (p.ops & HK_OP_SHIFT) && valid;
+        int32_t ha = 3, ax = 0;
+        if (shift) {
+            ha = __ldg(p.host_action + g);
+            ax = __ldg(p.axis + g);
+        }
+
+        if (tma) {
+            mbar_wait(&bar[s], (phase_bits >> s) & 1u);
+            phase_bits ^= (1u << s);
+        } else {
+            warp_copy_words(stage, gin + t * (long long)L::TILE_WORDS, words, lane);
+            __syncwarp();
+        }
+
+        T x[W];
+        load_game<T, W>(stage + lane * W, x);
+        if constexpr (Elem<T>::is_float) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
+        }
+        uint32_t lm = live_mask<T, N, D>(x);
+        int cnt = __popc(lm);
+        int32_t len = (cnt < 2) ? 0 : p.T + 1;
+        // T consecutive steps with the state in registers (T == 1 for hk_step)
+        for (int st = 0; st < p.T; ++st) {
+            int32_t ha_n = 3, ax_n = 0;
+            if (shift && st + 1 < p.T) {  // prefetch the next step's actions
+                ha_n = __ldg(p.host_action + (long long)(st + 1) * B + g);
+                ax_n = __ldg(p.axis + (long long)(st + 1) * B + g);
+            }
+            const bool prev_done = cnt < 2;
+            lm = game_step<T, N, D>(x, lm, p.ops, p.flags, ha, ax);
+            cnt = __popc(lm);
+            const bool dn = cnt < 2;
+            if (valid) {
+                if (p.done) p.done[(long long)st * B + g] = dn ? 1 : 0;
+                if (p.reward) {
+                    float r = (dn && !prev_done) ? 1.0f : 0.0f;
+                    p.reward[(long long)st * B + g] = (p.flags & HK_F_ROLE_AGENT) ? -r : r;
+                }
+            }
+            if (p.done_count) {
+                const int c = __popc(__ballot_sync(0xffffffffu, valid && dn));
+                if (lane == 0 && c) atomicAdd(p.done_count + st, c);
+            }
+            if (dn && !prev_done) len = st + 1;
+            ha = ha_n;
+            ax = ax_n;
+        }
+        if (valid) {
+            if (p.num_points) p.num_points[g] = cnt;
+            if (p.length) p.length[g] = len;
+        }
+        if (p.exceed_flag) {
+            const bool e = valid && exceeds<T, N, D>(x, lm, p.threshold);
+            if (__any_sync(0xffffffffu, e) && lane == 0) *p.exceed_flag = 1;
+        }
+
+        bool stored = false;
+        if (gout) {
+            if (p.ops) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] : padv;
+                }
+            }
+            store_game<T, W>(stage + lane * W, x);
+            if (tma) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_store(gout + t * (long long)L::TILE_WORDS, stage, (uint32_t)words * 4u);
+                stored = true;
+            } else {
+                __syncwarp();
+                warp_copy_words(gout + t * (long long)L::TILE_WORDS, stage, words, lane);
+                __syncwarp();
+            }
+        }
+        if constexpr (OBS) {
+            if (p.obs) {
+                float* row = obs_tile + lane * OW;
+                game_features<T, N, D>(x, lm, p.flags, p.pad, row);
+                if (p.obs_coord) {
+                    const uint32_t ocm = valid ? action_mask(__ldg(p.obs_coord + g), p.flags) : 0u;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) row[W + k] = (float)((ocm >> k) & 1u);
+                }
+                const int owords = (words / W) * OW;
+                float* gobs = p.obs + t * 32ll * OW;
+                if (obs_tma && ((owords & 3) == 0)) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_store(gobs, obs_tile, (uint32_t)owords * 4u);
+                    stored = true;
+                } else {
+                    __syncwarp();
+                    warp_copy_words(reinterpret_cast<uint32_t*>(gobs), reinterpret_cast<uint32_t*>(obs_tile), owords,
+                                    lane);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (stored) {
+                bulk_commit();
+                bulk_wait_read<0>();  // the stage (and obs tile) may be overwritten from here on
+            }
+            issue_load(t + SMALL_STAGES * nw, s);
+        }
+        __syncwarp();
+        s = (s + 1 == SMALL_STAGES) ? 0 : s + 1;
+    }
+    if (lane == 0) bulk_wait_all<0>();  // all bulk stores globally complete before the warp retires
+}
+
+}  // namespace hk

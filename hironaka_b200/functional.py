@@ -1,0 +1,164 @@
+"""The functional env-step API of ``hironaka/jax/util.py`` on torch CUDA tensors.
+
+Same factory names and call signatures as the reference (file:line in each docstring) so that a
+``recurrent_fn`` (hironaka/jax/recurrent_fn.py:84-121) or ``compute_rho`` loop
+(hironaka/jax/jax_trainer.py:497-534) reads the same; arrays are torch CUDA float32 tensors
+instead of ``jnp`` arrays and every game operation is one launch of the sm_100a kernels.
+JAX semantics: shift is applied unconditionally (invalid axis included, ended games included),
+order is shift -> reposition -> newton -> rescale, padding is -1.
+
+``get_env_step`` is the fused form the reference composes by hand in ``recurrent_fn``:
+decode action -> step -> dones -> reward -> features in ONE launch.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import constants as C
+from . import ops as _ops
+from .host_action import (batch_encode, batch_encode_one_hot, decode_table, get_batch_decode,  # noqa: F401
+                          get_batch_decode_from_one_hot)
+
+
+def flatten(x: torch.Tensor) -> torch.Tensor:
+    """vmap(jnp.ravel) (util.py:19)."""
+    return x.reshape(x.shape[0], -1)
+
+
+def make_agent_obs(pts: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
+    """Flattened points concatenated with the host's coordinate set (util.py:22-31)."""
+    return torch.cat([flatten(pts), coords.to(pts.dtype)], dim=1)
+
+
+def get_dones(pts: torch.Tensor) -> torch.Tensor:
+    """done iff fewer than 2 live rows (util.py:34-35)."""
+    return _ops.dones(pts.contiguous())[0]
+
+
+def get_done_from_flatten(obs: torch.Tensor, role: str, dimension: int) -> torch.Tensor:
+    """util.py:38-39: #(entries >= 0) <= d (+ d for the agent's appended 0/1 coordinates), i.e.
+    at most one live row in the points part."""
+    width = obs.shape[-1] - (dimension if role == "agent" else 0)
+    pts = obs[..., :width].reshape(obs.shape[0], width // dimension, dimension)
+    return _ops.dones(pts.contiguous())[0]
+
+
+@functools.lru_cache()
+def get_preprocess_fns(role: str, spec: Tuple[int, int]) -> Tuple[Callable, Callable]:
+    """(obs_preprocess, coords_preprocess) for a role (util.py:42-79)."""
+    n, d = spec
+    if role == "host":
+        def obs_preprocess(observations):
+            return observations.reshape(-1, n, d)
+
+        def coords_preprocess(observations, actions):
+            return actions
+    elif role == "agent":
+        def obs_preprocess(observations):
+            return observations[:, : n * d].reshape(-1, n, d)
+
+        def coords_preprocess(observations, actions):
+            return observations[:, n * d: n * d + d]
+    else:
+        raise ValueError(f"role must be either host or agent. Got {role}.")
+    return obs_preprocess, coords_preprocess
+
+
+def _state_of(points: torch.Tensor) -> torch.Tensor:
+    if points.dtype not in (torch.float32, torch.int32):
+        points = points.to(torch.float32)
+    return points.contiguous()
+
+
+@functools.lru_cache()
+def get_take_actions(role: str, spec: Tuple[int, int], rescale_points: bool = False,
+                     reposition: bool = True) -> Callable:
+    """Factory of ``take_actions(observations, actions, axis) -> [B, N*d]`` (util.py:82-125)."""
+    obs_preprocess, coords_preprocess = get_preprocess_fns(role, spec)
+    n, d = spec
+    op_bits = C.HK_OP_SHIFT | C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | \
+        (C.HK_OP_RESCALE if rescale_points else 0)
+
+    def take_actions(observations: torch.Tensor, actions: torch.Tensor, axis: torch.Tensor) -> torch.Tensor:
+        points = _state_of(obs_preprocess(observations))
+        coords = coords_preprocess(observations, actions)
+        mask = _ops.coords_to_mask(coords, d, points.device)
+        r = _ops.step(points, mask, axis, ops=op_bits, flags=C.JAX_SEMANTICS, inplace=False)
+        return r.state.reshape(-1, n * d)
+
+    return take_actions
+
+
+@functools.lru_cache()
+def get_reward_fn(role: str) -> Callable:
+    """host: +1 on the step the game ends; agent: -1 (util.py:128-149)."""
+    if role not in ("host", "agent"):
+        raise ValueError(f"role must be either host or agent. Got {role}.")
+    sign = 1.0 if role == "host" else -1.0
+
+    def reward_fn(dones: torch.Tensor, prev_dones: torch.Tensor) -> torch.Tensor:
+        return (dones & ~prev_dones).to(torch.float32) * sign
+
+    return reward_fn
+
+
+@functools.lru_cache()
+def get_feature_fn(role: str, spec: Tuple, scale_observation: bool = True) -> Callable:
+    """Feature function: (rescale) + stable descending lexsort of rows, last coordinate primary;
+    the agent keeps its d coordinates appended unchanged (util.py:172-214)."""
+    assert len(spec) == 2
+    n, d = spec
+    flags = C.HK_F_OBS_SORT_LEX | (C.HK_F_OBS_RESCALE if scale_observation else 0)
+    if role == "host":
+        def feature_fn(observations: torch.Tensor) -> torch.Tensor:
+            pts = _state_of(observations.reshape(-1, n, d))
+            return _ops.features(pts, flags=flags)
+    elif role == "agent":
+        def feature_fn(observations: torch.Tensor) -> torch.Tensor:
+            pts = _state_of(observations[:, : n * d].reshape(-1, n, d))
+            coords = observations[:, n * d: n * d + d]
+            mask = _ops.coords_to_mask(coords, d, pts.device)
+            return _ops.features(pts, flags=flags, obs_coord=mask)
+    else:
+        raise ValueError(f"role must be either host or agent. Got {role}.")
+    return feature_fn
+
+
+def generate_pts(generator: Optional[torch.Generator], shape: Tuple[int, int, int], max_value: int,
+                 dtype=torch.float32, rescale: bool = True, reposition: bool = True, device="cuda") -> torch.Tensor:
+    """Root states: randint[0, max_value) -> newton -> (reposition) -> (rescale) (util.py:385-392).
+    The random draw is torch's (the reference uses jax.random); everything after it is one launch."""
+    pts = torch.randint(0, max_value, shape, generator=generator, device=device).to(dtype)
+    op_bits = C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | (C.HK_OP_RESCALE if rescale else 0)
+    _ops.step(pts, ops=op_bits, flags=0, inplace=True)
+    return pts
+
+
+@functools.lru_cache()
+def get_env_step(role: str, spec: Tuple[int, int], rescale_points: bool = False, reposition: bool = True,
+                 scale_observation: bool = True, discrete_host_action: bool = True,
+                 with_features: bool = True) -> Callable:
+    """Fused step for MCTS node expansion / rollouts: ONE launch does what recurrent_fn
+    composes from take_actions + get_dones + reward_fn + feature_fn (recurrent_fn.py:84-121).
+
+    Returns ``env_step(points[B,N,d], host_action[B], axis[B], next_coord=None) ->
+    (next_points[B,N,d], dones[B] bool, rewards[B] f32, features or None)``.  ``host_action`` holds
+    discrete ids (mctx actions) when ``discrete_host_action`` else coordinate bitmasks; the
+    reward sign follows ``role``; features are the role's network input (agent: next_coord
+    appended)."""
+    n, d = spec
+    op_bits = C.HK_OP_SHIFT | C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | \
+        (C.HK_OP_RESCALE if rescale_points else 0)
+    flags = (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
+        C.HK_F_OBS_SORT_LEX | (C.HK_F_OBS_RESCALE if scale_observation else 0)
+
+    def env_step(points: torch.Tensor, host_action: torch.Tensor, axis: torch.Tensor, next_coord=None,
+                 inplace: bool = False):
+        r = _ops.step(_state_of(points), host_action, axis, ops=op_bits, flags=flags, inplace=inplace,
+                      want_done=True, want_reward=True, want_obs=with_features, obs_coord=next_coord)
+        return r.state, r.done, r.reward, r.obs
+
+    return env_step

@@ -1,0 +1,67 @@
+"""Host-buffer sessions: the NumPy / ctypes calling style of the reference's own C binding
+(hironaka/src/_np_ops.py:6-15,57-84) on top of ``hk_session_*``.  All arrays are HOST arrays; the
+session owns the device state of one shard of games, and every call includes its H2D / D2H
+copies.  No torch involved."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import constants as C
+from ._lib import check, lib
+
+
+class HostSession:
+    def __init__(self, points: np.ndarray, device: int = 0, padding_value: float = -1.0):
+        if points.dtype == np.int32:
+            self.dtype = C.HK_DTYPE_I32
+        elif points.dtype == np.float32:
+            self.dtype = C.HK_DTYPE_F32
+        else:
+            raise TypeError("points must be int32 or float32")
+        if points.ndim != 3:
+            raise ValueError("points must be [B, N, d]")
+        self.B, self.N, self.d = points.shape
+        self._np_dtype = points.dtype
+        self._h = ctypes.c_void_p()
+        check(lib().hk_session_create(ctypes.byref(self._h), device, self.B, self.N, self.d, self.dtype,
+                                      float(padding_value)), "hk_session_create")
+        self.set_state(points)
+
+    def set_state(self, points: np.ndarray) -> None:
+        p = np.ascontiguousarray(points, dtype=self._np_dtype)
+        assert p.shape == (self.B, self.N, self.d)
+        check(lib().hk_session_set_state(self._h, p.ctypes.data), "hk_session_set_state")
+
+    def get_state(self) -> np.ndarray:
+        out = np.empty((self.B, self.N, self.d), dtype=self._np_dtype)
+        check(lib().hk_session_get_state(self._h, out.ctypes.data), "hk_session_get_state")
+        return out
+
+    def step(self, host_action: Optional[np.ndarray], axis: Optional[np.ndarray], ops: int, flags: int,
+             done: Optional[np.ndarray] = None, reward: Optional[np.ndarray] = None, want_done_count: bool = True):
+        """H2D(actions) -> one fused step -> D2H(done, reward, done_count); blocking.
+        `done` (uint8 [B]) / `reward` (float32 [B]) are caller-provided output buffers or None."""
+        ha = None if host_action is None else np.ascontiguousarray(host_action, dtype=np.int32)
+        ax = None if axis is None else np.ascontiguousarray(axis, dtype=np.int32)
+        cnt = ctypes.c_int32(0)
+        rc = lib().hk_session_step(self._h, None if ha is None else ha.ctypes.data,
+                                   None if ax is None else ax.ctypes.data,
+                                   None if done is None else done.ctypes.data,
+                                   None if reward is None else reward.ctypes.data,
+                                   ctypes.addressof(cnt) if want_done_count else None, ops, flags)
+        check(rc, "hk_session_step")
+        return cnt.value if want_done_count else None
+
+    def close(self) -> None:
+        if self._h:
+            lib().hk_session_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -58,6 +58,8 @@ extern "C" {
 #define HK_OP_REPOSITION (1u << 1) /* per coord subtract min over live rows (_torch_ops.py:113-133, _jax_ops.py:114-123) */
 #define HK_OP_NEWTON (1u << 2)     /* dedupe + dominance filter     (_fn.py:192-213, _torch_ops.py:8-39, _jax_ops.py:32-73) */
 #define HK_OP_RESCALE (1u << 3)    /* divide live entries by the game max; F32 state only (_torch_ops.py:136-146, _jax_ops.py:93-111) */
+#define HK_OP_DEDUPE (1u << 4)     /* remove_repeated alone: later copies of identical rows become padding (_fn.py:192-213,
+                                      _jax_ops.py:32-40); runs after reposition, before newton (which subsumes it) */
 
 /* ---- semantics flags ---------------------------------------------------------------- */
 #define HK_F_NOOP_INVALID (1u << 0)   /* torch: axis not in S  => state unchanged (_torch_ops.py:90-91). Unset = JAX: applied anyway */
@@ -75,10 +77,13 @@ const char* hk_error_string(int code);
 /* 1 if (N,d) runs on the register-resident thread-per-game kernel, 0 if on the generic
  * warp-per-game kernel, <0 if unsupported. */
 int hk_kernel_class(int N, int d);
+/* Test hook: when on != 0, shapes of the thread-per-game class are routed through the generic
+ * warp-per-game kernel too (so both kernel families are parity-tested on every shape). */
+int hk_debug_force_generic(int on);
 
 /* ---- the fused step ------------------------------------------------------------------
  * One launch = one game-step for B independent games:
- *   prev_done -> [shift] -> [reposition] -> [newton] -> [rescale] -> done / reward / num_points
+ *   prev_done -> [shift] -> [reposition] -> [dedupe] -> [newton] -> [rescale] -> done / reward / num_points
  *   -> [observation features]
  * Replaces shift_torch + get_newton_polytope_torch + rescale_torch + ended_batch_in_tensor +
  * FusedGame._default_reward (fused_game.py:150-182) and take_actions + get_dones + reward_fn +

@@ -146,6 +146,24 @@ static void parallel_for(int64_t B, range_fn fn, void* ctx) {
                 if (x[i * d] < 0)                                                                       \
                     for (int k = 0; k < d; ++k) x[i * d + k] = pad;                                     \
         }                                                                                               \
+        if (ops & HK_OP_DEDUPE) { /* remove_repeated hironaka/src/_fn.py:192-213 */                     \
+            uint8_t rep[HK_MAX_POINTS];                                                                 \
+            for (int i = 0; i < N; ++i) {                                                               \
+                rep[i] = 0;                                                                             \
+                for (int j = 0; j < i && !rep[i]; ++j) {                                                \
+                    int eq = 1;                                                                         \
+                    for (int k = 0; k < d; ++k)                                                         \
+                        if (x[i * d + k] != x[j * d + k]) {                                             \
+                            eq = 0;                                                                     \
+                            break;                                                                      \
+                        }                                                                               \
+                    rep[i] = (uint8_t)eq;                                                               \
+                }                                                                                       \
+            }                                                                                           \
+            for (int i = 0; i < N; ++i)                                                                 \
+                if (rep[i] || x[i * d] < 0)                                                             \
+                    for (int k = 0; k < d; ++k) x[i * d + k] = pad;                                     \
+        }                                                                                               \
         if (ops & HK_OP_NEWTON) {                                                                       \
             /* remove_repeated hironaka/src/_fn.py:192-213, then                                        \
                get_newton_polytope_approx_torch _torch_ops.py:8-39 (get_interior _jax_ops.py:43-57):    \

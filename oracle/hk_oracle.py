@@ -391,7 +391,7 @@ def zeillinger_fn(pts: np.ndarray) -> np.ndarray:
 # unified step used by the parity tests (same flag vocabulary as include/hironaka_b200.h)
 # --------------------------------------------------------------------------------------
 
-OP_SHIFT, OP_REPOSITION, OP_NEWTON, OP_RESCALE = 1, 2, 4, 8
+OP_SHIFT, OP_REPOSITION, OP_NEWTON, OP_RESCALE, OP_DEDUPE = 1, 2, 4, 8, 16
 F_NOOP_INVALID, F_FREEZE_ENDED, F_ACT_DISCRETE, F_ROLE_AGENT = 1, 2, 4, 8
 F_OBS_RESCALE, F_OBS_SORT_COORD0, F_OBS_SORT_LEX = 16, 32, 64
 
@@ -426,6 +426,8 @@ def step(points: np.ndarray, host_action, axis, ops: int, flags: int, padding_va
             p = shift_jax(p, coord, ax, padding_value)
     if ops & OP_REPOSITION:
         p = reposition_torch(p, padding_value)
+    if ops & OP_DEDUPE:
+        p = remove_repeated(p, padding_value)
     if ops & OP_NEWTON:
         p = get_newton_polytope_torch(p, padding_value)
     if ops & OP_RESCALE:

@@ -1,0 +1,146 @@
+"""CPU-only checks of the boundary and the host-side logic (no compute calls: there is no GPU
+here and the product has no CPU path)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hironaka_b200.h")
+
+
+def header_text():
+    return open(HEADER).read()
+
+
+def declared_functions():
+    txt = re.sub(r"/\*.*?\*/", "", header_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(hk_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import hironaka_b200
+    from hironaka_b200 import _lib
+    if not os.path.exists(hironaka_b200.LIB_PATH):
+        pytest.skip("library not built in this checkout (run python -m hironaka_b200.build)")
+    L = ctypes.CDLL(hironaka_b200.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree on the symbol list"
+    lib = _lib.lib()
+    assert lib.hk_version() == hironaka_b200.HK_VERSION
+    assert lib.hk_error_string(0) == b"ok" and b"unsupported" in lib.hk_error_string(-2)
+    assert lib.hk_kernel_class(20, 3) == 1 and lib.hk_kernel_class(64, 5) == 0
+    assert lib.hk_kernel_class(2000, 3) < 0 and lib.hk_kernel_class(4, 11) < 0
+
+
+def test_constants_match_header():
+    from hironaka_b200 import constants as C
+    txt = header_text()
+    defs = dict(re.findall(r"#define\s+(HK_[A-Z_0-9]+)\s+(\(?[-0-9a-zA-Z<< u]+\)?)", txt))
+    checked = 0
+    for name, expr in defs.items():
+        if not hasattr(C, name):
+            continue
+        val = eval(expr.replace("u", ""))
+        assert getattr(C, name) == val, name
+        checked += 1
+    assert checked >= 20
+
+
+def test_no_fallback_when_library_missing(tmp_path):
+    """The product must fail loudly without the CUDA extension, and on CPU tensors."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import hironaka_b200._lib as L\n"
+        "L.LIB_PATH = %r\n"
+        "try:\n"
+        "    L.lib()\n"
+        "    print('LOADED')\n"
+        "except L.HironakaB200Error as e:\n"
+        "    print('RAISED', 'no fallback' in str(e).lower())\n"
+    ) % (ROOT, str(tmp_path / "missing.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
+    import torch
+    from hironaka_b200 import HironakaB200Error, ops
+    with pytest.raises(HironakaB200Error):
+        ops.step(torch.zeros(2, 5, 3, dtype=torch.int32), ops=4)
+    with pytest.raises(HironakaB200Error):
+        from hironaka_b200 import TensorPoints
+        TensorPoints(torch.zeros(1, 2, 3), device="cpu")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hironaka_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+                assert "/root/reference" not in txt
+
+
+def test_host_action_closed_form_and_encoder():
+    from hironaka_b200.host_action import (HostActionEncoder, action_masks, batch_encode, batch_encode_one_hot,
+                                           decode_id, decode_table, encode_mask, get_batch_decode)
+    from oracle import hk_oracle as O
+    from tests import kat as K
+    import torch
+    for d in range(2, 11):
+        masks = action_masks(d)
+        assert len(masks) == 2 ** d - d - 1
+        for i, m in enumerate(masks):
+            assert decode_id(i) == m and encode_mask(m) == i  # the kernel's closed form == the table
+        assert np.array_equal(decode_table(d).numpy(), O.decode_table(d))
+    enc = HostActionEncoder(3)
+    assert enc.encode([0, 1]) == 0 and enc.decode(0) == [0, 1] and enc.decode(3) == [0, 1, 2]
+    assert enc.decode_tensor(torch.tensor([0, 1])).tolist() == [[1, 1, 0], [1, 0, 1]]
+    assert enc.encode_tensor(torch.tensor(K.ENCODE_IN)).tolist() == K.ENCODE_OUT.tolist()
+    assert batch_encode(torch.tensor(K.ENCODE_IN)).tolist() == K.ENCODE_OUT.tolist()
+    assert np.array_equal(batch_encode_one_hot(torch.tensor(K.ENCODE_IN)).numpy(), K.ENCODE_ONE_HOT_OUT)
+    assert np.array_equal(get_batch_decode(3)(torch.tensor(K.ENCODE_OUT)).numpy(), K.ENCODE_IN)
+
+
+def test_golden_tables_match_host_action(golden_dir):
+    from hironaka_b200.host_action import decode_table
+    g = np.load(os.path.join(golden_dir, "ref_tables.npz"))
+    for d in range(2, 8):
+        assert np.array_equal(decode_table(d).numpy(), g[f"decode_{d}"].astype(np.int32))
+
+
+def test_coords_to_mask_cpu():
+    import torch
+    from hironaka_b200.ops import coords_to_mask
+    assert coords_to_mask([[1, 2], [0, 2, 3]], 4, "cpu").tolist() == [0b0110, 0b1101]
+    assert coords_to_mask(torch.tensor([[0., 1., 1., 0.], [1., 0., 1., 1.]]), 4, "cpu").tolist() == [0b0110, 0b1101]
+    with pytest.raises(ValueError):
+        coords_to_mask([[4]], 4, "cpu")
+
+
+def test_shard_range_partitions():
+    from hironaka_b200.engine import shard_range
+    for total in (0, 1, 7, 8, 1000, 1 << 20):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_rho_from_counts():
+    import torch
+    from hironaka_b200.engine import GameBatch
+    # 10 games: 2 done at entry, then 3 / 6 / 6 finished after steps 1..3
+    rho = GameBatch.rho(2, torch.tensor([3, 6, 7]), 10)
+    # details (compute_rho, jax_trainer.py:519-555): [2, 1, 3, 10-7=3] -> rho = (1+3+3) / (1*1 + 2*3 + 3*3)
+    assert abs(rho - 7 / 16) < 1e-12

@@ -1,0 +1,279 @@
+"""GPU tests of the reference-facing Python surface: the drop-ins must behave like the classes
+and functions they replace (TensorPoints, hironaka.src ops, hironaka/jax/util.py), written the
+way the reference's own tests are (test/testTensorPoints.py, test/testJAX.py)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import cport  # noqa: E402
+from oracle import hk_oracle as O  # noqa: E402
+from tests import kat as K  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def eq(t, a):
+    return np.array_equal(t.detach().cpu().numpy(), np.asarray(a))
+
+
+# ---- hironaka.src op surface (test/testTensorPoints.py:48-63) ---------------------------------
+def test_src_functions():
+    from hironaka_b200.src import (get_newton_polytope_torch, remove_repeated, reposition_torch, rescale_torch,
+                                   shift_torch)
+    p = T(K.R_IN)
+    assert eq(get_newton_polytope_torch(p, inplace=False), K.R)
+    assert eq(p, K.R_IN)  # inplace=False leaves the input alone
+    assert get_newton_polytope_torch(p, inplace=True) is None
+    assert eq(p, K.R)
+    assert eq(shift_torch(p, [[1, 2], [0, 2, 3]], [1, 3], inplace=False), K.R2)
+    shift_torch(p, [[1, 2], [0, 2, 3]], [1, 3], inplace=True)
+    assert eq(p, K.R2)
+    assert eq(reposition_torch(p, inplace=False), K.R3)
+    reposition_torch(p, inplace=True)
+    assert eq(p, K.R3)
+    rescale_torch(p)
+    assert eq(p, K.RS)
+    q = T(K.REP_IN)
+    remove_repeated(q)
+    assert eq(q, K.REP_OUT)
+    # multi-binary tensor form of coord and float axis (FusedGame passes both as float, fused_game.py:155)
+    p = T(K.R)
+    shift_torch(p, T(K.R_COORD_BIN), T(K.R_AXIS.astype(np.float32)))
+    assert eq(p, K.R2)
+    # non-contiguous input is still updated in place
+    big = torch.zeros(2, 4, 8, device="cuda")
+    view = big[:, :, :4]
+    view.copy_(T(K.R_IN))
+    get_newton_polytope_torch(view)
+    assert eq(view, K.R)
+    with pytest.raises(Exception):
+        shift_torch(p, "bad", [1, 3])
+
+
+# ---- TensorPoints (test/testTensorPoints.py:65-200) -------------------------------------------
+def test_tensor_points_surface():
+    from hironaka_b200 import TensorPoints
+    pts = TensorPoints(T(K.R_IN))
+    assert pts.batch_size == 2 and pts.max_num_points == 4 and pts.dimension == 4
+    assert pts.get_newton_polytope() is pts and eq(pts.points, K.R)
+    pts.shift([[1, 2], [0, 2, 3]], [1, 3])
+    assert eq(pts.points, K.R2)
+    pts.reposition()
+    assert eq(pts.points, K.R3)
+    pts.rescale()
+    assert eq(pts.points, K.RS) and str(pts) == str(pts.points)
+
+    pts = TensorPoints(T(K.R_IN))
+    pts.get_newton_polytope()
+    pts.shift([[1], [0, 2, 3]], [0, 1])
+    assert eq(pts.points, K.R)  # both actions invalid: nothing happens
+    pts = TensorPoints(T(K.ENDED_P)).copy()
+    pts.shift([[0, 1]], [1], ignore_ended_games=True)
+    assert eq(pts.points, K.ENDED_P)
+    pts.shift([[0, 1]], [1], ignore_ended_games=False)
+    assert eq(pts.points, K.ENDED_Q)
+
+    p = TensorPoints(T(K.ORIGIN20_IN))
+    p.get_newton_polytope()
+    assert eq(p.points, K.ORIGIN20_OUT)
+    assert p.ended and p.ended_batch_in_tensor.tolist() == [True] and p.get_num_points().tolist() == [1]
+
+    point = TensorPoints(T(K.RESCALE0_IN))
+    point.rescale()
+    assert point.points.isfinite().all()
+
+    a = TensorPoints(torch.rand(100, 20, 3))
+    assert hash(a) == hash(a.copy()) and a.copy().points.data_ptr() != a.points.data_ptr()
+
+    point = TensorPoints(T(K.RESCALE0_IN), dtype=torch.float32)
+    point.type(torch.float16)
+    assert point.dtype == torch.float16 and point.points.dtype == torch.float16
+
+    # nested ragged list input with max_num_points (points_base / tensor_points.py:32-37)
+    lst = [[[1, 2, 3], [2, 3, 4]], [[0, 1, 2]]]
+    tp = TensorPoints(lst, max_num_points=3, padding_value=-1.0)
+    assert eq(tp.points, [[[1, 2, 3], [2, 3, 4], [-1, -1, -1]], [[0, 1, 2], [-1, -1, -1], [-1, -1, -1]]])
+    q = tp.get_newton_polytope(inplace=False)
+    assert q is not tp and eq(tp.points[0, 1], [2, 3, 4]) and eq(q.points[0, 1], [-1, -1, -1])
+    assert not tp.exceed_threshold()
+    tp2 = TensorPoints(T(np.array([[[1e9, 0, 0], [0, 1, 0]]], np.float32)))
+    assert tp2.exceed_threshold()
+    from hironaka_b200 import HironakaB200Error
+    with pytest.raises(HironakaB200Error):
+        TensorPoints(torch.zeros(1, 2, 3), device="cpu")
+
+
+def test_tensor_points_features_and_fused_game_flow():
+    """The FusedGame.step composition (fused_game.py:54-102) against the oracle, with the
+    experience filtering done the reference's way."""
+    from hironaka_b200 import HostActionEncoder, TensorPoints
+    rng = np.random.default_rng(3)
+    B, N, d = 256, 20, 3
+    x = rng.integers(0, 21, (B, N, d)).astype(np.float32)
+    pts = TensorPoints(T(x))
+    pts.get_newton_polytope()
+    pts.rescale()
+    ref = O.rescale_torch(O.get_newton_polytope_torch(x))
+    assert eq(pts.points, ref)
+    enc = HostActionEncoder(d)
+    for t in range(5):
+        obs = pts.get_features()
+        done = pts.ended_batch_in_tensor
+        assert eq(obs, O.get_features_torch(ref)) and eq(done, O.ended_batch(ref))
+        hid = rng.integers(0, 4, B)
+        host_move = enc.decode_tensor(T(hid))                   # [B, d] float multi-binary
+        actions = host_move.argmax(1)                           # ChooseFirst agent
+        pts.shift(host_move.type(pts.points.dtype), actions.type(pts.points.dtype))
+        pts.get_newton_polytope()
+        pts.rescale()
+        ref = O.fused_game_point_ops(ref, host_move.cpu().numpy(), actions.cpu().numpy(), True)
+        assert eq(pts.points, ref), t
+        next_done = pts.ended_batch_in_tensor
+        rew = next_done[~done].type(torch.float32)
+        assert eq(rew, O.default_reward("host", O.ended_batch(ref))[~done.cpu().numpy()])
+
+
+# ---- functional JAX-style API (test/testJAX.py:80-153,205-219,461-488) ------------------------
+def test_functional_api():
+    from hironaka_b200 import functional as F
+    obs = torch.ones((32, 60), device="cuda")
+    assert F.make_agent_obs(obs, torch.ones((32, 3), device="cuda")).shape == (32, 63)
+    host_obs = T(K.TA_HOST_OBS)
+    coords = T(K.TA_COORDS)
+    ones = torch.ones(2, device="cuda")
+    combined = torch.cat([host_obs.reshape(2, -1), coords], dim=1)
+    ta = F.get_take_actions("host", (4, 3), rescale_points=True, reposition=False)
+    out = ta(host_obs.reshape(2, -1), coords, ones)
+    assert eq(out, O.take_actions("host", (4, 3), K.TA_HOST_OBS.reshape(2, -1), K.TA_COORDS, np.ones(2, np.float32), True, False))
+    ta = F.get_take_actions("agent", (4, 3), rescale_points=False, reposition=False)
+    out = ta(combined, ones, ones)
+    assert eq(out, O.get_newton_polytope_jax(O.shift_jax(K.TA_HOST_OBS, K.TA_COORDS, np.ones(2))).reshape(2, -1))
+    assert eq(host_obs, K.TA_HOST_OBS)  # functional: inputs untouched
+
+    assert eq(F.get_feature_fn("host", (6, 3))(T(K.FEAT_IN.reshape(1, -1))), K.FEAT_SORTED)
+    assert eq(F.get_feature_fn("agent", (3, 3), scale_observation=False)(T(K.AGENT_FEAT_IN)), K.AGENT_FEAT_NOSCALE)
+    assert eq(F.get_feature_fn("agent", (3, 3), scale_observation=True)(T(K.AGENT_FEAT_IN)), K.AGENT_FEAT_SCALE)
+
+    assert eq(F.get_dones(T(K.R)), [False, False]) and eq(F.get_dones(T(K.ORIGIN20_OUT)), [True])
+    assert eq(F.get_done_from_flatten(T(K.AGENT_FEAT_IN), "agent", 3), [False, False])
+    d, pd = torch.tensor([True, True, False]).cuda(), torch.tensor([False, True, False]).cuda()
+    assert eq(F.get_reward_fn("host")(d, pd), [1, 0, 0]) and eq(F.get_reward_fn("agent")(d, pd), [-1, 0, 0])
+
+    assert eq(F.decode_table(3), K.DECODE_3)
+    assert eq(F.batch_encode(T(K.ENCODE_IN)), K.ENCODE_OUT)
+    assert eq(F.batch_encode_one_hot(T(K.ENCODE_IN)), K.ENCODE_ONE_HOT_OUT)
+    assert eq(F.get_batch_decode_from_one_hot(3)(T(K.ENCODE_ONE_HOT_OUT)), K.ENCODE_IN)
+    assert eq(F.get_batch_decode(3)(T(K.ENCODE_OUT)), K.ENCODE_IN)
+    with pytest.raises(ValueError):
+        F.get_batch_decode(11)
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pts = F.generate_pts(g, (64, 20, 3), 20, rescale=False, reposition=True)
+    again = pts.clone()
+    F.generate_pts  # root states are a fixed point of newton+reposition
+    from hironaka_b200 import ops, constants as C
+    ops.step(again, ops=C.HK_OP_NEWTON | C.HK_OP_REPOSITION, inplace=True)
+    assert torch.equal(again, pts)
+
+
+def test_fused_env_step_matches_composition():
+    """get_env_step (one launch) == take_actions + get_dones + reward_fn + feature_fn."""
+    from hironaka_b200 import functional as F
+    rng = np.random.default_rng(9)
+    B, N, d = 300, 20, 3
+    x = O.generate_pts(rng, (B, N, d), 20, rescale=False, reposition=True)
+    hid = rng.integers(0, 4, B)
+    ax = rng.integers(0, 3, B)
+    nxt = rng.integers(0, 4, B)
+    coords = O.decode_table(3)[hid].astype(np.float32)
+    for role in ("host", "agent"):
+        env_step = F.get_env_step(role, (N, d), reposition=True, scale_observation=True)
+        nx, done, rew, feat = env_step(T(x), T(hid.astype(np.int32)), T(ax.astype(np.int32)),
+                                       next_coord=T(nxt.astype(np.int32)) if role == "agent" else None)
+        exp = O.take_actions("host", (N, d), x.reshape(B, -1), coords, ax, False, True)
+        assert eq(nx.reshape(B, -1), exp)
+        exp_done = O.get_dones(exp.reshape(B, N, d))
+        assert eq(done, exp_done) and eq(rew, O.reward_fn(role, exp_done, O.get_dones(x)))
+        if role == "host":
+            assert eq(feat, O.feature_fn("host", (N, d), exp, True))
+        else:
+            agent_obs = O.make_agent_obs(exp.reshape(B, N, d), O.decode_table(3)[nxt].astype(np.float32))
+            assert eq(feat, O.feature_fn("agent", (N, d), agent_obs, True))
+
+
+def test_game_batch_and_rho():
+    from hironaka_b200 import GameBatch
+    rng = np.random.default_rng(21)
+    B, N, d, Tn = 4096, 20, 3, 12
+    x = rng.integers(0, 20, (B, N, d)).astype(np.int32)
+    ha = rng.integers(0, 4, (Tn, B)).astype(np.int32)
+    ax = rng.integers(0, 3, (Tn, B)).astype(np.int32)
+    gb = GameBatch(T(x), semantics="jax", reposition=True, initial_filter=True)
+    gb2 = GameBatch(T(x), semantics="jax", reposition=True, initial_filter=True)
+    o = cport.step(x, None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+    assert eq(gb.points, o)
+    d0 = int(gb.dones().sum())
+    counts = []
+    for t in range(Tn):
+        o, od, orw, _ = cport.step(o, ha[t], ax[t], O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE)
+        done, rew = gb.step(T(ha[t]), T(ax[t]))
+        assert eq(done, od.astype(bool)) and eq(rew, orw)
+        counts.append(int(od.sum()))
+    assert eq(gb.points, o)
+    _, _, dcount, length = gb2.rollout(T(ha), T(ax))
+    assert eq(gb2.points, o) and dcount.tolist() == counts
+    rho = GameBatch.rho(d0, dcount, B)
+    assert 0.0 < rho < 1.0
+    assert eq(gb.features("host"), cport.features(o, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE))
+
+
+def test_host_session_numpy_only():
+    """hk_session_*: host (NumPy) buffers in and out, no torch tensors involved."""
+    from hironaka_b200 import HostSession
+    rng = np.random.default_rng(4)
+    B, N, d = 5000, 20, 3
+    x = rng.integers(0, 20, (B, N, d)).astype(np.int32)
+    s = HostSession(x)
+    ops_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    assert s.step(None, None, O.OP_NEWTON | O.OP_REPOSITION, 0) >= 0
+    o = cport.step(x, None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+    assert np.array_equal(s.get_state(), o)
+    done = np.empty(B, np.uint8)
+    rew = np.empty(B, np.float32)
+    for t in range(4):
+        ha, ax = rng.integers(0, 4, B).astype(np.int32), rng.integers(0, 3, B).astype(np.int32)
+        cnt = s.step(ha, ax, ops_bits, O.F_ACT_DISCRETE, done=done, reward=rew)
+        o, od, orw, _ = cport.step(o, ha, ax, ops_bits, O.F_ACT_DISCRETE)
+        assert np.array_equal(done, od) and np.array_equal(rew, orw) and cnt == int(od.sum())
+    assert np.array_equal(s.get_state(), o)
+    s.close()
+
+
+def test_cuda_graph_capture_of_step():
+    """The device entry points neither allocate nor synchronise: a step can be captured in a
+    CUDA graph and replayed (MCTS node expansion)."""
+    from hironaka_b200 import ops, constants as C
+    rng = np.random.default_rng(8)
+    B, N, d = 512, 20, 3
+    x = rng.integers(0, 20, (B, N, d)).astype(np.int32)
+    state = T(x)
+    ha = T(rng.integers(0, 4, B).astype(np.int32))
+    ax = T(rng.integers(0, 3, B).astype(np.int32))
+    op_bits = C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON
+    ops.step(state, ha, ax, ops=op_bits, flags=C.HK_F_ACT_DISCRETE, inplace=True)  # warm up (smem opt-in)
+    state.copy_(T(x))
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        r = ops.step(state, ha, ax, ops=op_bits, flags=C.HK_F_ACT_DISCRETE, inplace=True, want_done=True)
+    o = x
+    for _ in range(3):
+        g.replay()
+        o = cport.step(o, ha.cpu().numpy(), ax.cpu().numpy(), op_bits, C.HK_F_ACT_DISCRETE)[0]
+    torch.cuda.synchronize()
+    assert eq(state, o) and eq(r.done, O.get_dones(o.astype(np.float32)))

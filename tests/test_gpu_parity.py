@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle, bit-exact.
+
+Run on a B200 with ``pytest -m gpu``.  Sources of truth, in order:
+  * the reference's known-answer vectors (tests/kat.py),
+  * outputs of the real reference (tests/golden/ref_*.npz),
+  * the oracle (oracle/hk_oracle.py for small cases, oracle/cport.py = C port for large ones)
+    on seeded random inputs, including BASELINE.json's full sizes.
+Both kernel families (thread-per-game and warp-per-game) are exercised on every small shape via
+the hk_debug_force_generic test hook.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import cport  # noqa: E402
+from oracle import hk_oracle as O  # noqa: E402
+from tests import kat as K  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+TORCH_FLAGS = O.F_NOOP_INVALID | O.F_FREEZE_ENDED
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hironaka_b200
+    from hironaka_b200 import ops
+    assert os.path.exists(hironaka_b200.LIB_PATH), "CUDA library not built"
+    ops.force_generic(False)
+    return hironaka_b200
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def run_step(hb, x_np, ha, ax, ops_bits, flags, pad=-1.0, want_obs=False, obs_coord=None):
+    from hironaka_b200 import ops
+    r = ops.step(dev(x_np), None if ha is None else dev(ha.astype(np.int32)),
+                 None if ax is None else dev(ax.astype(np.int32)), ops=ops_bits, flags=flags, padding_value=pad,
+                 inplace=False, want_done=True, want_reward=True, want_num_points=True, want_obs=want_obs,
+                 obs_coord=None if obs_coord is None else dev(obs_coord.astype(np.int32)))
+    return (r.state.cpu().numpy(), r.done.cpu().numpy(), r.reward.cpu().numpy(), r.num_points.cpu().numpy(),
+            None if r.obs is None else r.obs.cpu().numpy())
+
+
+@pytest.fixture(params=[False, True], ids=["family=auto", "family=generic"])
+def family(request, hb):
+    from hironaka_b200 import ops
+    ops.force_generic(request.param)
+    yield request.param
+    ops.force_generic(False)
+
+
+# ---------------------------------------------------------------- reference KATs
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_kat_ops(hb, family, dtype):
+    x = K.R_IN.astype(dtype)
+    n = run_step(hb, x, None, None, O.OP_NEWTON, 0)[0]
+    assert np.array_equal(n, K.R.astype(dtype))
+    s = run_step(hb, n, K.R_COORD_MASK, K.R_AXIS, O.OP_SHIFT, TORCH_FLAGS)[0]
+    assert np.array_equal(s, K.R2.astype(dtype))
+    r = run_step(hb, s, None, None, O.OP_REPOSITION, 0)[0]
+    assert np.array_equal(r, K.R3.astype(dtype))
+    f, done, rew, npts, _ = run_step(hb, n, K.R_COORD_MASK, K.R_AXIS, O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, 0)
+    assert np.array_equal(f, K.R3.astype(dtype))
+    assert done.tolist() == [False, False] and rew.tolist() == [0, 0] and npts.tolist() == [3, 2]
+    q = run_step(hb, n, np.array([0b0010, 0b1101]), np.array(K.INVALID_AXIS), O.OP_SHIFT, TORCH_FLAGS)[0]
+    assert np.array_equal(q, K.R.astype(dtype))
+    e = run_step(hb, K.ENDED_P.astype(dtype), np.array([0b11]), np.array([1]), O.OP_SHIFT, TORCH_FLAGS)[0]
+    assert np.array_equal(e, K.ENDED_P.astype(dtype))
+    e = run_step(hb, K.ENDED_P.astype(dtype), np.array([0b11]), np.array([1]), O.OP_SHIFT, O.F_NOOP_INVALID)[0]
+    assert np.array_equal(e, K.ENDED_Q.astype(dtype))
+    o, done, rew, npts, _ = run_step(hb, K.ORIGIN20_IN.astype(dtype), None, None, O.OP_NEWTON, 0)
+    assert np.array_equal(o, K.ORIGIN20_OUT.astype(dtype))
+    assert done.tolist() == [True] and rew.tolist() == [1.0] and npts.tolist() == [1]
+    assert np.array_equal(run_step(hb, K.REP_IN.astype(dtype), None, None, O.OP_NEWTON, 0)[0], K.REP_OUT.astype(dtype))
+    assert np.array_equal(run_step(hb, K.REP_IN.astype(dtype), None, None, O.OP_DEDUPE, 0)[0], K.REP_OUT.astype(dtype))
+    assert np.array_equal(run_step(hb, K.EXTREME_IN.astype(dtype), None, None, O.OP_NEWTON, 0)[0],
+                          K.EXTREME_OUT.astype(dtype))
+
+
+def test_kat_float(hb, family):
+    assert np.array_equal(run_step(hb, K.R3, None, None, O.OP_RESCALE, 0)[0], K.RS)
+    assert np.array_equal(run_step(hb, K.RESCALE_IN, None, None, O.OP_RESCALE, 0)[0], K.RESCALE_OUT)
+    assert np.isfinite(run_step(hb, K.RESCALE0_IN, None, None, O.OP_RESCALE, 0)[0]).all()
+    s = run_step(hb, K.FEAT_IN, np.array([0b110]), np.array([1]), O.OP_SHIFT, 0)[0]
+    assert np.array_equal(s, K.FSHIFT_OUT)
+    obs = run_step(hb, K.FEAT_IN, None, None, 0, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, want_obs=True)[4]
+    assert np.array_equal(obs, K.FEAT_SORTED)
+    pts = K.AGENT_FEAT_IN[:, :9].reshape(2, 3, 3).copy()
+    cm = np.array([0b110, 0b101])
+    for dt in (np.float32, np.int32):
+        o = run_step(hb, pts.astype(dt), None, None, 0, O.F_OBS_SORT_LEX, want_obs=True, obs_coord=cm)[4]
+        assert np.array_equal(o, K.AGENT_FEAT_NOSCALE)
+        o = run_step(hb, pts.astype(dt), None, None, 0, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, want_obs=True, obs_coord=cm)[4]
+        assert np.array_equal(o, K.AGENT_FEAT_SCALE)
+    # take_actions composition with discrete ids (test/testJAX.py:461-488)
+    s2 = run_step(hb, K.TA_HOST_OBS, np.array([2, 3]), np.array([1, 1]), O.OP_SHIFT | O.OP_NEWTON | O.OP_RESCALE,
+                  O.F_ACT_DISCRETE)[0]
+    ones = np.ones(2, np.float32)
+    assert np.array_equal(s2.reshape(2, -1),
+                          O.take_actions("host", (4, 3), K.TA_HOST_OBS.reshape(2, -1), K.TA_COORDS, ones, True, False))
+
+
+# ---------------------------------------------------------------- real-reference goldens
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_golden_rollouts(hb, family, golden_dir, dtype):
+    files = sorted(glob.glob(os.path.join(golden_dir, "ref_rollout_*.npz")))
+    assert files
+    for path in files:
+        g = np.load(path)
+        seed, B, N, d, T, mv, first, repos = g["meta"].tolist()
+        ops_bits = O.OP_SHIFT | O.OP_NEWTON | (O.OP_REPOSITION if repos else 0)
+        flags = TORCH_FLAGS | O.F_ACT_DISCRETE
+        x, done, _, npts, _ = run_step(hb, g["init"].astype(dtype), None, None, O.OP_NEWTON, 0)
+        assert np.array_equal(x.astype(np.float32), g["states"][0]), path
+        assert np.array_equal(done, g["dones"][0]) and np.array_equal(npts, g["num_points"][0])
+        for t in range(T):
+            x, done, rew, npts, obs = run_step(hb, x, g["host_ids"][t], g["axes"][t], ops_bits,
+                                               flags | O.F_OBS_SORT_COORD0, want_obs=True)
+            assert np.array_equal(x.astype(np.float32), g["states"][t + 1]), (path, t)
+            assert np.array_equal(done, g["dones"][t + 1]), (path, t)
+            assert np.array_equal(npts, g["num_points"][t + 1]), (path, t)
+            assert np.array_equal(rew, (g["dones"][t + 1] & ~g["dones"][t]).astype(np.float32)), (path, t)
+            feat = obs.reshape(B, N, d)
+            assert np.array_equal(feat[:, :, 0], g["features"][t][:, :, 0]), (path, t)
+            if N <= 16:
+                assert np.array_equal(feat, g["features"][t]), (path, t)
+        # the same rollout as ONE launch (hk_rollout) must end in the same state
+        from hironaka_b200 import ops
+        st0 = dev(g["states"][0].astype(dtype))
+        out, dn, rw, dcount, length = ops.rollout(st0, dev(g["host_ids"]), dev(g["axes"]), ops=ops_bits, flags=flags,
+                                                  inplace=False, want_done=True, want_reward=True, want_length=True)
+        assert np.array_equal(out.cpu().numpy().astype(np.float32), g["states"][T]), path
+        assert np.array_equal(dn.cpu().numpy(), g["dones"][1:]), path
+        assert np.array_equal(dcount.cpu().numpy(), g["dones"][1:].sum(1)), path
+        first_done = np.where(g["dones"][0], 0, np.where(g["dones"][1:].any(0), g["dones"][1:].argmax(0) + 1, T + 1))
+        assert np.array_equal(length.cpu().numpy(), first_done), path
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_golden_ops(hb, family, golden_dir, dtype):
+    for path in sorted(glob.glob(os.path.join(golden_dir, "ref_ops_*.npz"))):
+        g = np.load(path)
+        x = g["points"].astype(dtype)
+        B, N, d = x.shape
+        hid, ax = g["host_ids"], g["axes"]
+        c = lambda a: a.astype(np.float32)
+        fl = O.F_ACT_DISCRETE
+        assert np.array_equal(c(run_step(hb, x, hid, ax, O.OP_SHIFT, fl | TORCH_FLAGS)[0]), g["shift_ignore_ended"]), path
+        assert np.array_equal(c(run_step(hb, x, hid, ax, O.OP_SHIFT, fl | O.F_NOOP_INVALID)[0]), g["shift_force_ended"]), path
+        n = run_step(hb, x, None, None, O.OP_NEWTON, 0)[0]
+        assert np.array_equal(c(n), g["newton"]), path
+        assert np.array_equal(c(run_step(hb, x, None, None, O.OP_DEDUPE, 0)[0]), g["remove_repeated"]), path
+        assert np.array_equal(c(run_step(hb, x, None, None, O.OP_REPOSITION, 0)[0]), g["reposition"]), path
+        _, done0, _, npts0, _ = run_step(hb, x, None, None, 0, 0)
+        assert np.array_equal(npts0, g["num_points"]) and np.array_equal(done0, g["ended"])
+        obs = run_step(hb, n, None, None, 0, O.F_OBS_RESCALE, want_obs=True)[4]
+        assert np.array_equal(obs.reshape(B, N, d), g["rescale_after_newton"]), path
+        if dtype == np.float32:
+            assert np.array_equal(run_step(hb, x, None, None, O.OP_RESCALE, 0)[0], g["rescale"]), path
+            assert np.array_equal(run_step(hb, x, None, None, O.OP_NEWTON | O.OP_RESCALE, 0)[0],
+                                  g["rescale_after_newton"]), path
+
+
+# ---------------------------------------------------------------- seeded random vs oracle
+
+
+def random_state(rng, B, N, d, max_value, dead_frac=0.2, dup_frac=0.2):
+    x = rng.integers(0, max_value + 1, size=(B, N, d)).astype(np.int32)
+    dead = rng.random((B, N)) < dead_frac
+    x[dead] = -1
+    for b in np.nonzero(rng.random(B) < dup_frac)[0]:
+        i, j = rng.integers(0, N, 2)
+        x[b, j] = x[b, i]
+    return x
+
+
+SHAPES = [(1, 5, 3), (7, 5, 3), (33, 10, 3), (257, 20, 3), (1000, 20, 3), (64, 2, 2), (50, 7, 2), (40, 16, 4),
+          (37, 33, 3), (16, 64, 5), (5, 100, 3), (3, 300, 6), (9, 4, 10), (4, 1, 3), (2, 1024, 4)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_random_step_all_modes(hb, family, shape, dtype):
+    B, N, d = shape
+    rng = np.random.default_rng(B * 1000 + N * 10 + d)
+    ncls = 2 ** d - d - 1
+    for trial, (ops_bits, flags) in enumerate([
+        (O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, 0),                                  # JAX step
+        (O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS),                                          # FusedGame step
+        (O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE | O.F_ROLE_AGENT),  # discrete ids, agent reward
+        (O.OP_SHIFT, O.F_FREEZE_ENDED),
+        (O.OP_NEWTON, 0),
+        (O.OP_REPOSITION | O.OP_DEDUPE, 0),
+    ]):
+        x = random_state(rng, B, N, d, max_value=int(rng.choice([1, 3, 20, 1000]))).astype(dtype)
+        if flags & O.F_ACT_DISCRETE and ncls >= 1:
+            ha = rng.integers(0, ncls, B)
+        else:
+            ha = rng.integers(0, 2 ** d, B)  # arbitrary masks, including empty and singletons
+        ax = rng.integers(0, d, B)
+        got = run_step(hb, x, ha, ax, ops_bits, flags)
+        exp = cport.step(x, ha, ax, ops_bits, flags)
+        assert np.array_equal(got[0], exp[0]), (trial, "state")
+        assert np.array_equal(got[1], exp[1].astype(bool)), (trial, "done")
+        assert np.array_equal(got[2], exp[2]), (trial, "reward")
+        assert np.array_equal(got[3], exp[3]), (trial, "num_points")
+        if B * N * N * d <= 2_000_000:  # NumPy restatement as a second, independent checker
+            ref = O.step(x, ha, ax, ops_bits, flags)
+            assert np.array_equal(got[0].astype(np.float32), ref[0]), (trial, "state/numpy")
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+@pytest.mark.parametrize("shape", [(65, 20, 3), (33, 10, 3), (31, 5, 3), (12, 64, 5), (20, 16, 4), (6, 40, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_random_features(hb, family, shape, dtype):
+    B, N, d = shape
+    rng = np.random.default_rng(N * 7 + d)
+    x = random_state(rng, B, N, d, max_value=6, dead_frac=0.3).astype(dtype)  # small range => many key ties
+    cm = rng.integers(0, 2 ** d, B)
+    for flags in (0, O.F_OBS_RESCALE, O.F_OBS_SORT_COORD0, O.F_OBS_SORT_LEX, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE,
+                  O.F_OBS_SORT_COORD0 | O.F_OBS_RESCALE):
+        for oc in (None, cm):
+            got = run_step(hb, x, None, None, 0, flags, want_obs=True, obs_coord=oc)[4]
+            exp = cport.features(x, flags, obs_coord=oc)
+            assert np.array_equal(got, exp), (flags, oc is None)
+    # fused: features of the state AFTER the step
+    ha, ax = rng.integers(0, 2 ** d, B), rng.integers(0, d, B)
+    ops_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    got = run_step(hb, x, ha, ax, ops_bits, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, want_obs=True)
+    exp_state = cport.step(x, ha, ax, ops_bits, 0)[0]
+    assert np.array_equal(got[0], exp_state)
+    assert np.array_equal(got[4], cport.features(exp_state, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE))
+
+
+def test_float_state_rescaled_rollout(hb, family):
+    """DQN path with scale_observation: float state divided by its max every step
+    (fused_game.py:160-162).  Values are non-integers; parity is exact because the kernel keeps
+    the reference's left-to-right summation and IEEE division."""
+    rng = np.random.default_rng(5)
+    B, N, d = 200, 20, 3
+    x = rng.integers(0, 21, size=(B, N, d)).astype(np.float32)
+    ops_bits = O.OP_SHIFT | O.OP_NEWTON | O.OP_RESCALE
+    flags = TORCH_FLAGS | O.F_ACT_DISCRETE
+    g = run_step(hb, x, None, None, O.OP_NEWTON | O.OP_RESCALE, 0)[0]
+    o = cport.step(x, None, None, O.OP_NEWTON | O.OP_RESCALE, 0)[0]
+    assert np.array_equal(g, o)
+    for t in range(6):
+        ha, ax = rng.integers(0, 4, B), rng.integers(0, 3, B)
+        g = run_step(hb, g, ha, ax, ops_bits, flags)[0]
+        o = cport.step(o, ha, ax, ops_bits, flags)[0]
+        assert np.array_equal(g, o), t
+
+
+def test_padding_value_and_inplace(hb, family):
+    from hironaka_b200 import ops
+    rng = np.random.default_rng(11)
+    x = random_state(rng, 70, 10, 3, 9).astype(np.float32)
+    x[x < 0] = -1e-8  # padding used by test/testTrainer.py:77
+    ha, ax = rng.integers(0, 8, 70), rng.integers(0, 3, 70)
+    got = run_step(hb, x, ha, ax, O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS, pad=-1e-8)[0]
+    exp = cport.step(x, ha, ax, O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS, padding_value=-1e-8)[0]
+    assert np.array_equal(got, exp)
+    t = dev(x)
+    r = ops.step(t, dev(ha.astype(np.int32)), dev(ax.astype(np.int32)), ops=O.OP_SHIFT | O.OP_NEWTON,
+                 flags=TORCH_FLAGS, padding_value=-1e-8, inplace=True)
+    assert r.state.data_ptr() == t.data_ptr() and np.array_equal(t.cpu().numpy(), exp)
+    # unaligned base pointer (4-byte aligned only): the non-TMA path must give the same answer
+    buf = torch.zeros(70 * 30 + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(70, 10, 3)
+    view.copy_(dev(x))
+    assert view.data_ptr() % 16 != 0
+    ops.step(view, dev(ha.astype(np.int32)), dev(ax.astype(np.int32)), ops=O.OP_SHIFT | O.OP_NEWTON,
+             flags=TORCH_FLAGS, padding_value=-1e-8, inplace=True)
+    assert np.array_equal(view.cpu().numpy(), exp)
+
+
+def test_exceed_flag_and_errors(hb):
+    from hironaka_b200 import ops
+    from hironaka_b200._lib import HironakaB200Error
+    x = dev(np.array([[[1, 2, 3], [5, 0, 70000]]], dtype=np.int32))
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.step(x, ops=0, write_state=False, exceed_flag=flag, value_threshold=1e5)
+    assert flag.item() == 0
+    ops.step(x, ops=0, write_state=False, exceed_flag=flag, value_threshold=7e4)
+    assert flag.item() == 1
+    with pytest.raises(HironakaB200Error):
+        ops.step(torch.zeros(2, 3, 3, dtype=torch.int32), ops=O.OP_NEWTON)  # CPU tensor: no fallback
+    with pytest.raises(HironakaB200Error):
+        ops.step(x, ops=O.OP_RESCALE)  # rescale is undefined on int32 state
+    with pytest.raises(HironakaB200Error):
+        ops.step(torch.zeros(1, 2, 11, dtype=torch.int32, device="cuda"), ops=O.OP_NEWTON)  # d > HK_MAX_DIM
+    with pytest.raises(ValueError):
+        ops.step(x, ops=O.OP_SHIFT)  # missing actions
+    e = torch.zeros(0, 20, 3, dtype=torch.int32, device="cuda")
+    assert ops.step(e, ops=O.OP_NEWTON, want_done=True).done.numel() == 0  # empty batch
+
+
+# ---------------------------------------------------------------- BASELINE sizes
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(name="C2", B=1 << 20, N=20, d=3, T=20, mv=20, ops=O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
+    dict(name="C1", B=1024, N=10, d=3, T=10, mv=21, ops=O.OP_SHIFT | O.OP_NEWTON, flags=TORCH_FLAGS | O.F_ACT_DISCRETE),
+    dict(name="C5", B=1 << 16, N=64, d=5, T=6, mv=20, ops=O.OP_SHIFT | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
+], ids=lambda c: c["name"])
+def test_baseline_sizes_bit_exact(hb, cfg):
+    """Full-size parity against the C port on identical seeded inputs."""
+    from hironaka_b200 import ops
+    B, N, d, T = cfg["B"], cfg["N"], cfg["d"], cfg["T"]
+    rng = np.random.default_rng(2024)
+    x = rng.integers(0, cfg["mv"], size=(B, N, d)).astype(np.int32)
+    ncls = 2 ** d - d - 1
+    ha = rng.integers(0, ncls, size=(T, B)).astype(np.int32)
+    ax = rng.integers(0, d, size=(T, B)).astype(np.int32)
+    init_ops = O.OP_NEWTON | (cfg["ops"] & O.OP_REPOSITION)
+    o = cport.step(x, None, None, init_ops, 0)[0]
+    g = dev(x)
+    ops.step(g, ops=init_ops, inplace=True)
+    assert np.array_equal(g.cpu().numpy(), o)
+    g_roll = g.clone()
+    odones = []
+    for t in range(T):
+        o, od, orw, _ = cport.step(o, ha[t], ax[t], cfg["ops"], cfg["flags"])
+        r = ops.step(g, dev(ha[t]), dev(ax[t]), ops=cfg["ops"], flags=cfg["flags"], inplace=True, want_done=True,
+                     want_reward=True)
+        odones.append(od.astype(bool))
+        assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)), t
+        assert np.array_equal(r.reward.cpu().numpy(), orw), t
+        if t in (0, 1, T - 1):
+            assert np.array_equal(g.cpu().numpy(), o), t
+    # one-launch rollout ends in the same state with the same per-step finished counts
+    _, _, _, dcount, _ = ops.rollout(g_roll, dev(ha), dev(ax), ops=cfg["ops"], flags=cfg["flags"], inplace=True)
+    assert np.array_equal(g_roll.cpu().numpy(), o)
+    assert np.array_equal(dcount.cpu().numpy(), np.stack(odones).sum(1))
+    # size-independent properties: the filter is idempotent; survivors are pairwise incomparable
+    g2 = g.clone()
+    ops.step(g2, ops=O.OP_NEWTON, inplace=True)
+    assert torch.equal(g2, g)

@@ -276,7 +276,7 @@ def run_gpu_arm(args):
     value = B * world * K / (total_ms_max * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
-    e2e = measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
+    e2e = None if args.no_e2e else measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -294,7 +294,7 @@ def run_gpu_arm(args):
         "int_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s,
     }
     cpu = None
-    if True:
+    if not args.no_cpu:
         try:
             rate, cores, dt = cpu_rate(1 << 18, 40, 5)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -356,6 +356,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

@@ -151,6 +151,7 @@ int check_shape(long long B, int N, int d, int dtype) {
 int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     int rc = check_shape(p.B, p.N, p.d, dtype);
     if (rc != HK_OK) return rc;
+    if (p.B == 0) return HK_OK;  // empty batch: nothing to do (an empty tensor has a null data pointer)
     if (p.in == nullptr) return HK_ERR_BAD_ARG;
     if ((((uintptr_t)p.in) & 3u) || (((uintptr_t)p.out) & 3u)) return HK_ERR_ALIGN;
     if ((p.ops & HK_OP_SHIFT) && (p.host_action == nullptr || p.axis == nullptr)) return HK_ERR_BAD_ARG;

@@ -274,6 +274,101 @@ __device__ __forceinline__ void game_features(const T (&x)[N * D], uint32_t lm, 
     }
 }
 
+// ---- compacted tiers ------------------------------------------------------------------------------
+// Under real play few of the N slots are live (mean 6 of 20 after the root filter, 3 after two
+// steps), and the O(K^2 d) filter only needs the live rows.  Each warp therefore picks a tier
+// K in {4, 8, 12, N} from the maximum live count over its 32 games (warp-uniform, no
+// divergence), gathers every lane's live rows into K register rows through the lane's own
+// shared-memory copy of the game (slot order is kept, so the lowest-index-wins dedupe rule is
+// unchanged), runs all T steps on the K rows and scatters the survivors back to their slots.
+struct LaneState {
+    long long g;
+    bool valid, shift;
+    int32_t ha, ax;
+    int cnt;
+    int32_t len;
+};
+
+template <typename T, int N, int D, int K>
+__device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, T (&x)[N * D],
+                                           uint32_t lm, bool write, bool& exceed) {
+    const long long B = p.B;
+    const T padv = Elem<T>::pad(p.pad);
+    T y[K * D];
+    int idx[K];
+    uint32_t clm = 0, cvalid = 0;
+    if constexpr (K == N) {
+#pragma unroll
+        for (int q = 0; q < N * D; ++q) y[q] = x[q];
+        clm = lm;
+        cvalid = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
+    } else {
+        uint32_t m = lm;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool v = m != 0;
+            const int i = v ? (__ffs((int)m) - 1) : 0;
+            m &= m - 1;
+            idx[k] = i;
+            clm |= v ? (1u << k) : 0u;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                T val = Elem<T>::from_bits(row[i * D + c]);
+                if constexpr (Elem<T>::is_float) val = val + 0.0f;
+                y[k * D + c] = val;
+            }
+        }
+        cvalid = clm;
+    }
+    // T consecutive steps on the compact rows (T == 1 for hk_step)
+    for (int st = 0; st < p.T; ++st) {
+        int32_t ha_n = 3, ax_n = 0;
+        if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
+            ha_n = __ldg(p.host_action + (long long)(st + 1) * B + ls.g);
+            ax_n = __ldg(p.axis + (long long)(st + 1) * B + ls.g);
+        }
+        const bool prev_done = ls.cnt < 2;
+        clm = game_step<T, K, D>(y, clm, p.ops, p.flags, ls.ha, ls.ax);
+        ls.cnt = __popc(clm);
+        const bool dn = ls.cnt < 2;
+        if (ls.valid) {
+            if (p.done) p.done[(long long)st * B + ls.g] = dn ? 1 : 0;
+            if (p.reward) {
+                float r = (dn && !prev_done) ? 1.0f : 0.0f;
+                p.reward[(long long)st * B + ls.g] = (p.flags & HK_F_ROLE_AGENT) ? -r : r;
+            }
+        }
+        if (p.done_count) {
+            const int c = __popc(__ballot_sync(0xffffffffu, ls.valid && dn));
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(p.done_count + st, c);
+        }
+        if (dn && !prev_done) ls.len = st + 1;
+        ls.ha = ha_n;
+        ls.ax = ax_n;
+    }
+    if (p.exceed_flag) exceed = exceeds<T, K, D>(y, clm, p.threshold);
+    if (write) {
+        if constexpr (K == N) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) y[i * D + c] = ((clm >> i) & 1u) ? y[i * D + c] : padv;
+            }
+            store_game<T, N * D>(row, y);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if ((cvalid >> k) & 1u) {
+                    const bool lv = (clm >> k) & 1u;
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        row[idx[k] * D + c] = (uint32_t)Elem<T>::bits(lv ? y[k * D + c] : padv);
+                }
+            }
+        }
+    }
+}
+
 // ---- tile movement -------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
@@ -299,6 +394,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
     const int OW = W + (p.obs_coord ? D : 0);
     const bool obs_tma = aligned16(p.obs);
     const T padv = Elem<T>::pad(p.pad);
+    const bool write = (gout != nullptr);
 
     if (lane == 0) {
 #pragma unroll
@@ -329,16 +425,18 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
     int s = 0;
     for (long long t = gw; t < ntiles; t += nw) {
         uint32_t* stage = ring + s * L::TILE_WORDS;
-        const long long g = (t << 5) + lane;
-        const bool valid = g < B;
+        uint32_t* row = stage + lane * W;
+        LaneState ls;
+        ls.g = (t << 5) + lane;
+        ls.valid = ls.g < B;
         const int words = tile_words(t);
         const bool tma = tile_tma(t);
-
-        const bool shift = (p.ops & HK_OP_SHIFT) && valid;
-        int32_t ha = 3, ax = 0;
-        if (shift) {
-            ha = __ldg(p.host_action + g);
-            ax = __ldg(p.axis + g);
+        ls.shift = (p.ops & HK_OP_SHIFT) && ls.valid;
+        ls.ha = 3;
+        ls.ax = 0;
+        if (ls.shift) {
+            ls.ha = __ldg(p.host_action + ls.g);
+            ls.ax = __ldg(p.axis + ls.g);
         }
 
         if (tma) {
@@ -350,59 +448,73 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
         }
 
         T x[W];
-        load_game<T, W>(stage + lane * W, x);
+        load_game<T, W>(row, x);
         if constexpr (Elem<T>::is_float) {
 #pragma unroll
             for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
         }
         uint32_t lm = live_mask<T, N, D>(x);
-        int cnt = __popc(lm);
-        int32_t len = (cnt < 2) ? 0 : p.T + 1;
-        // T consecutive steps with the state in registers (T == 1 for hk_step)
-        for (int st = 0; st < p.T; ++st) {
-            int32_t ha_n = 3, ax_n = 0;
-            if (shift && st + 1 < p.T) {  // prefetch the next step's actions
-                ha_n = __ldg(p.host_action + (long long)(st + 1) * B + g);
-                ax_n = __ldg(p.axis + (long long)(st + 1) * B + g);
-            }
-            const bool prev_done = cnt < 2;
-            lm = game_step<T, N, D>(x, lm, p.ops, p.flags, ha, ax);
-            cnt = __popc(lm);
-            const bool dn = cnt < 2;
-            if (valid) {
-                if (p.done) p.done[(long long)st * B + g] = dn ? 1 : 0;
-                if (p.reward) {
-                    float r = (dn && !prev_done) ? 1.0f : 0.0f;
-                    p.reward[(long long)st * B + g] = (p.flags & HK_F_ROLE_AGENT) ? -r : r;
+        ls.cnt = __popc(lm);
+        ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
+        bool exceed = false;
+        if (p.ops) {
+            const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
+            if (N > 4 && lmax <= 4) {
+                constexpr int K = N > 4 ? 4 : N;
+                if (write) {  // dead rows are rewritten with the padding value (every reference op does)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                    }
+                    store_game<T, W>(row, x);
                 }
+                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+            } else if (N > 8 && lmax <= 8) {
+                constexpr int K = N > 8 ? 8 : N;
+                if (write) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                    }
+                    store_game<T, W>(row, x);
+                }
+                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+            } else if (N > 12 && lmax <= 12) {
+                constexpr int K = N > 12 ? 12 : N;
+                if (write) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                    }
+                    store_game<T, W>(row, x);
+                }
+                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+            } else {
+                tier_steps<T, N, D, N>(p, ls, row, x, lm, write, exceed);
             }
-            if (p.done_count) {
-                const int c = __popc(__ballot_sync(0xffffffffu, valid && dn));
-                if (lane == 0 && c) atomicAdd(p.done_count + st, c);
+        } else {
+            // no op selected (hk_dones / hk_features / exceed check): outputs of the state as it is
+            if (ls.valid) {
+                const bool dn = ls.cnt < 2;
+                if (p.done) p.done[ls.g] = dn ? 1 : 0;
+                if (p.reward) p.reward[ls.g] = 0.0f;
             }
-            if (dn && !prev_done) len = st + 1;
-            ha = ha_n;
-            ax = ax_n;
+            if (p.exceed_flag) exceed = exceeds<T, N, D>(x, lm, p.threshold);
+            if (write) store_game<T, W>(row, x);
         }
-        if (valid) {
-            if (p.num_points) p.num_points[g] = cnt;
-            if (p.length) p.length[g] = len;
+        if (ls.valid) {
+            if (p.num_points) p.num_points[ls.g] = ls.cnt;
+            if (p.length) p.length[ls.g] = ls.len;
         }
         if (p.exceed_flag) {
-            const bool e = valid && exceeds<T, N, D>(x, lm, p.threshold);
-            if (__any_sync(0xffffffffu, e) && lane == 0) *p.exceed_flag = 1;
+            if (__any_sync(0xffffffffu, exceed && ls.valid) && lane == 0) *p.exceed_flag = 1;
         }
 
         bool stored = false;
-        if (gout) {
-            if (p.ops) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] : padv;
-                }
-            }
-            store_game<T, W>(stage + lane * W, x);
+        if (write) {
             if (tma) {
                 fence_async_smem();
                 __syncwarp();
@@ -416,12 +528,16 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
         }
         if constexpr (OBS) {
             if (p.obs) {
-                float* row = obs_tile + lane * OW;
-                game_features<T, N, D>(x, lm, p.flags, p.pad, row);
+                // features of the NEW state: re-read the lane's game (scattered survivors included)
+                T z[W];
+                load_game<T, W>(row, z);
+                const uint32_t zl = live_mask<T, N, D>(z);
+                float* orow = obs_tile + lane * OW;
+                game_features<T, N, D>(z, zl, p.flags, p.pad, orow);
                 if (p.obs_coord) {
-                    const uint32_t ocm = valid ? action_mask(__ldg(p.obs_coord + g), p.flags) : 0u;
+                    const uint32_t ocm = ls.valid ? action_mask(__ldg(p.obs_coord + ls.g), p.flags) : 0u;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) row[W + k] = (float)((ocm >> k) & 1u);
+                    for (int k = 0; k < D; ++k) orow[W + k] = (float)((ocm >> k) & 1u);
                 }
                 const int owords = (words / W) * OW;
                 float* gobs = p.obs + t * 32ll * OW;

@@ -63,17 +63,27 @@ int kernel_ctas_per_sm(K kernel, KernelFacts& facts, int dev, int threads, size_
 }
 
 // ---- small (thread-per-game) family -----------------------------------------------------------
+// ring geometry of the thread-per-game kernel per shape: (warps per CTA, stages per warp)
+// (tools/tune_small.cu on B200, C2 workload: 4x3 = 95.6 us/step, 4x2 = 96.5, 3x3 = 102, 2x4 = 103)
+template <int N, int D, bool OBS>
+struct SmallTune {
+    static constexpr int WARPS = 4;
+    static constexpr int STAGES = OBS ? 2 : 3;  // the obs tile takes the room of the third stage
+};
+
 template <typename T, int N, int D, bool OBS>
 int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
-    using L = hk::SmallLayout<N, D, OBS>;
+    constexpr int WARPS = SmallTune<N, D, OBS>::WARPS;
+    constexpr int STAGES = SmallTune<N, D, OBS>::STAGES;
+    using L = hk::SmallLayout<N, D, OBS, WARPS, STAGES>;
     static KernelFacts facts;
-    auto kernel = hk::hk_small_kernel<T, N, D, OBS>;
+    auto kernel = hk::hk_small_kernel<T, N, D, OBS, WARPS, STAGES>;
     cudaError_t err = cudaSuccess;
-    const int threads = hk::SMALL_WARPS * 32;
+    const int threads = WARPS * 32;
     const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
     if (err != cudaSuccess) return (int)err;
     const long long ntiles = (p.B + 31) / 32;
-    long long ctas = (ntiles + hk::SMALL_WARPS - 1) / hk::SMALL_WARPS;
+    long long ctas = (ntiles + WARPS - 1) / WARPS;
     const long long cap = (long long)device_sms(dev) * per_sm;  // persistent: one wave
     if (ctas > cap) ctas = cap;
     kernel<<<(unsigned)ctas, threads, L::SMEM_BYTES, stream>>>(p);
@@ -164,7 +174,8 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     const bool obs = p.obs != nullptr;
-    const bool small = is_small(p.N, p.d) && !force_generic;
+    // remove_repeated alone is not on the step path: it runs on the warp-per-game kernel for every shape
+    const bool small = is_small(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE);
     if (dtype == HK_DTYPE_I32) {
         if (small) return obs ? dispatch_small<int32_t, true>(p, dev, stream) : dispatch_small<int32_t, false>(p, dev, stream);
         return obs ? dispatch_generic<int32_t, true>(p, dev, stream) : dispatch_generic<int32_t, false>(p, dev, stream);

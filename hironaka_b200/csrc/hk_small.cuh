@@ -14,18 +14,21 @@
 
 namespace hk {
 
-constexpr int SMALL_WARPS = 4;   // warps per CTA
-constexpr int SMALL_STAGES = 2;  // ring depth per warp
-constexpr int SMALL_BAR_BYTES = 128;
+constexpr int SMALL_BAR_BYTES = 256;
 
-template <int N, int D, bool OBS>
+// WARPS warps per CTA, each with a private ring of STAGES tiles.  With STAGES >= 3 the refill of a
+// stage is issued one iteration after its store (cp.async.bulk.wait_group.read 1), so the issuing
+// lane never waits on the store it has just launched; with STAGES == 2 it has to wait for that
+// store to finish reading shared memory before the stage can be refilled.
+template <int N, int D, bool OBS, int WARPS, int STAGES>
 struct SmallLayout {
+    static_assert(WARPS * STAGES * 8 <= SMALL_BAR_BYTES, "mbarrier area too small");
     static constexpr int W = N * D;
     static constexpr int TILE_WORDS = 32 * W;
     static constexpr int OBS_W = W + D;
     static constexpr int OBS_WORDS = OBS ? 32 * OBS_W : 0;
-    static constexpr int WARP_WORDS = SMALL_STAGES * TILE_WORDS + OBS_WORDS;
-    static constexpr size_t SMEM_BYTES = SMALL_BAR_BYTES + (size_t)SMALL_WARPS * WARP_WORDS * 4;
+    static constexpr int WARP_WORDS = STAGES * TILE_WORDS + OBS_WORDS;
+    static constexpr size_t SMEM_BYTES = SMALL_BAR_BYTES + (size_t)WARPS * WARP_WORDS * 4;
 };
 
 // ---- game <-> shared memory -------------------------------------------------------------------
@@ -150,23 +153,55 @@ __device__ __forceinline__ uint32_t op_newton(T (&x)[N * D], uint32_t lm) {
     return lm & ~kill;
 }
 
-// remove_repeated alone (_fn.py:192-213): row i dies iff an identical row j < i exists.
-template <typename T, int N, int D>
-__device__ __forceinline__ uint32_t op_dedupe(const T (&x)[N * D], uint32_t lm) {
-    uint32_t kill = 0;
+// The same filter with the victim loop ROLLED (code size K times smaller: the fully unrolled
+// N = 20 body is 33 KB of SASS, more than the 32 KB instruction cache, and warps of one SM run
+// different tiers at the same time).  Victim i is re-read from the lane's shared-memory scratch
+// (a register array cannot be indexed dynamically); dominators j stay in registers with static
+// indices.  The tie-break needs j >= i at run time: t - (j >= i) also neutralises the self pair
+// (t_ii = 0 -> -1).  RS = scratch row stride in words (4 => one conflict-free LDS.128 per victim).
+template <typename T, int K, int D, int RS>
+__device__ __forceinline__ uint32_t op_newton_rolled(T (&y)[K * D], uint32_t clm, uint32_t* scratch) {
 #pragma unroll
-    for (int i = 1; i < N; ++i) {
-        bool rep = false;
+    for (int k = 0; k < K; ++k) {
 #pragma unroll
-        for (int j = 0; j < i; ++j) {
-            bool eq = ((lm >> j) & 1u) != 0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) eq = eq && (x[i * D + k] == x[j * D + k]);
-            rep = rep || eq;
-        }
-        kill |= rep ? (1u << i) : 0u;
+        for (int c = 0; c < D; ++c) y[k * D + c] = ((clm >> k) & 1u) ? y[k * D + c] : Elem<T>::big();
     }
-    return lm & ~kill;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if constexpr (RS == 4 && D == 3) {
+            *reinterpret_cast<uint4*>(scratch + k * 4) =
+                make_uint4((uint32_t)Elem<T>::bits(y[k * 3]), (uint32_t)Elem<T>::bits(y[k * 3 + 1]),
+                           (uint32_t)Elem<T>::bits(y[k * 3 + 2]), 0u);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) scratch[k * RS + c] = (uint32_t)Elem<T>::bits(y[k * D + c]);
+        }
+    }
+    uint32_t kill = 0;
+#pragma unroll 1
+    for (int i = 0; i < K; ++i) {
+        T v[D];
+        if constexpr (RS == 4 && D == 3) {
+            const uint4 q = *reinterpret_cast<const uint4*>(scratch + i * 4);
+            v[0] = Elem<T>::from_bits(q.x);
+            v[1] = Elem<T>::from_bits(q.y);
+            v[2] = Elem<T>::from_bits(q.z);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[c] = Elem<T>::from_bits(scratch[i * RS + c]);
+        }
+        int32_t acc = (int32_t)0x80000000;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            int32_t t = Elem<T>::bits(v[0] - y[j * D]);
+#pragma unroll
+            for (int c = 1; c < D; ++c) t |= Elem<T>::bits(v[c] - y[j * D + c]);
+            t -= (j >= i) ? 1 : 0;
+            acc &= t;
+        }
+        kill |= ((acc >= 0) ? 1u : 0u) << i;
+    }
+    return clm & ~kill;
 }
 
 // rescale (float state): live entries / game max, max == 0 -> 1 (rescale_torch _torch_ops.py:136-146)
@@ -197,9 +232,9 @@ __device__ __forceinline__ bool exceeds(const T (&x)[N * D], uint32_t lm, float 
 }
 
 // One full step of one game in registers.  Returns the new live mask; x holds garbage in dead rows.
-template <typename T, int N, int D>
+template <typename T, int N, int D, int RS = 0>
 __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
-                                              int32_t ax) {
+                                              int32_t ax, uint32_t* scratch = nullptr) {
     if (ops & HK_OP_SHIFT) {
         const uint32_t cm = action_mask(ha, flags);
         bool apply = (ax >= 0) && (ax < D);
@@ -208,8 +243,13 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
         op_shift<T, N, D>(x, lm, cm, ax, apply);
     }
     if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm);
-    if (ops & HK_OP_DEDUPE) lm = op_dedupe<T, N, D>(x, lm);
-    if (ops & HK_OP_NEWTON) lm = op_newton<T, N, D>(x, lm);
+    if (ops & HK_OP_NEWTON) {
+        if constexpr (RS > 0) {
+            lm = op_newton_rolled<T, N, D, RS>(x, lm, scratch);
+        } else {
+            lm = op_newton<T, N, D>(x, lm);
+        }
+    }
     if constexpr (Elem<T>::is_float) {
         if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm);
     }
@@ -294,6 +334,10 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
                                            uint32_t lm, bool write, bool& exceed) {
     const long long B = p.B;
     const T padv = Elem<T>::pad(p.pad);
+    // tiers of 12 rows and more run the filter with a rolled victim loop through the lane's own
+    // shared-memory game area (scratch); the area is rebuilt from registers at the end
+    constexpr bool ROLLED = (K >= 12) && (K < N) && ((N * D) % 4 == 0);  // the full tier (root filter) stays unrolled
+    constexpr int RS = !ROLLED ? 0 : ((D == 3 && 4 * K <= N * D) ? 4 : D);
     T y[K * D];
     int idx[K];
     uint32_t clm = 0, cvalid = 0;
@@ -328,7 +372,7 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
             ax_n = __ldg(p.axis + (long long)(st + 1) * B + ls.g);
         }
         const bool prev_done = ls.cnt < 2;
-        clm = game_step<T, K, D>(y, clm, p.ops, p.flags, ls.ha, ls.ax);
+        clm = game_step<T, K, D, RS>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
         ls.cnt = __popc(clm);
         const bool dn = ls.cnt < 2;
         if (ls.valid) {
@@ -356,6 +400,11 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
             }
             store_game<T, N * D>(row, y);
         } else {
+            if constexpr (ROLLED) {  // the scratch overwrote the game area: all padding, then the survivors
+                const uint32_t pw = (uint32_t)Elem<T>::bits(padv);
+#pragma unroll
+                for (int q = 0; q < (N * D) / 4; ++q) reinterpret_cast<uint4*>(row)[q] = make_uint4(pw, pw, pw, pw);
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if ((cvalid >> k) & 1u) {
@@ -374,9 +423,12 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* s
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
 }
 
-template <typename T, int N, int D, bool OBS>
-__global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepParams p) {
-    using L = SmallLayout<N, D, OBS>;
+template <typename T, int N, int D, bool OBS, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p) {
+    using L = SmallLayout<N, D, OBS, WARPS, STAGES>;
+    constexpr int SMALL_WARPS = WARPS;
+    constexpr int SMALL_STAGES = STAGES;
+    constexpr bool DELAYED_REFILL = (STAGES >= 3) && !OBS;  // the single obs tile needs its store drained first
     constexpr int W = L::W;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -459,39 +511,28 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
         bool exceed = false;
         if (p.ops) {
             const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
+            auto prestore = [&]() {  // dead rows are rewritten with the padding value (every reference op does)
+                if (write) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                    }
+                    store_game<T, W>(row, x);
+                }
+            };
             if (N > 4 && lmax <= 4) {
-                constexpr int K = N > 4 ? 4 : N;
-                if (write) {  // dead rows are rewritten with the padding value (every reference op does)
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-#pragma unroll
-                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
-                    }
-                    store_game<T, W>(row, x);
-                }
-                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+                prestore();
+                tier_steps<T, N, D, (N > 4 ? 4 : N)>(p, ls, row, x, lm, write, exceed);
             } else if (N > 8 && lmax <= 8) {
-                constexpr int K = N > 8 ? 8 : N;
-                if (write) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-#pragma unroll
-                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
-                    }
-                    store_game<T, W>(row, x);
-                }
-                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+                prestore();
+                tier_steps<T, N, D, (N > 8 ? 8 : N)>(p, ls, row, x, lm, write, exceed);
             } else if (N > 12 && lmax <= 12) {
-                constexpr int K = N > 12 ? 12 : N;
-                if (write) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-#pragma unroll
-                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
-                    }
-                    store_game<T, W>(row, x);
-                }
-                tier_steps<T, N, D, K>(p, ls, row, x, lm, write, exceed);
+                if (W % 4 != 0) prestore();
+                tier_steps<T, N, D, (N > 12 ? 12 : N)>(p, ls, row, x, lm, write, exceed);
+            } else if (N > 16 && lmax <= 16) {
+                if (W % 4 != 0) prestore();
+                tier_steps<T, N, D, (N > 16 ? 16 : N)>(p, ls, row, x, lm, write, exceed);
             } else {
                 tier_steps<T, N, D, N>(p, ls, row, x, lm, write, exceed);
             }
@@ -556,11 +597,19 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) hk_small_kernel(const StepPa
         }
         __syncwarp();
         if (lane == 0) {
-            if (stored) {
+            if constexpr (DELAYED_REFILL) {
+                // Every iteration commits a (possibly empty) bulk group, so "at most one group still
+                // reading" means the PREVIOUS iteration's store has drained its stage: refill that one.
                 bulk_commit();
-                bulk_wait_read<0>();  // the stage (and obs tile) may be overwritten from here on
+                bulk_wait_read<1>();
+                if (t != gw) issue_load(t + (SMALL_STAGES - 1) * nw, s == 0 ? SMALL_STAGES - 1 : s - 1);
+            } else {
+                if (stored) {
+                    bulk_commit();
+                    bulk_wait_read<0>();  // the stage (and obs tile) may be overwritten from here on
+                }
+                issue_load(t + SMALL_STAGES * nw, s);
             }
-            issue_load(t + SMALL_STAGES * nw, s);
         }
         __syncwarp();
         s = (s + 1 == SMALL_STAGES) ? 0 : s + 1;

@@ -36,6 +36,7 @@ SIGNATURES = {
     "hk_session_set_state": (ctypes.c_int, [_p, _p]),
     "hk_session_get_state": (ctypes.c_int, [_p, _p]),
     "hk_session_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _u32, _u32]),
+    "hk_session_rollout": (ctypes.c_int, [_p, _p, _p, _i32, _p, _u32, _u32]),
     "hk_session_state_ptr": (_p, [_p]),
     "hk_session_stream": (_p, [_p]),
 }

@@ -28,6 +28,7 @@ HK_F_ROLE_AGENT = 1 << 3
 HK_F_OBS_RESCALE = 1 << 4
 HK_F_OBS_SORT_COORD0 = 1 << 5
 HK_F_OBS_SORT_LEX = 1 << 6
+HK_F_ACT_U8 = 1 << 7
 
 # the two semantics of the reference
 TORCH_SEMANTICS = HK_F_NOOP_INVALID | HK_F_FREEZE_ENDED  # hironaka/src/_torch_ops.py:90-93

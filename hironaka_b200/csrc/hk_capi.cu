@@ -325,9 +325,14 @@ struct hk_session {
     int N, d, dtype;
     float pad;
     cudaStream_t stream;
+    cudaStream_t copy_stream;
+    cudaEvent_t ready[2], freed[2];
     void* state;
-    int32_t* host_action;
+    int32_t* host_action;  // two slots of B int32 each (double buffer for hk_session_rollout)
     int32_t* axis;
+    int32_t* counts;       // per-step finished-game counts of a rollout (device)
+    int32_t* counts_pinned; // pinned host mirror: a D2H copy into pageable memory would block the host every step
+    int counts_cap;
     uint8_t* done;
     float* reward;
     int32_t* done_count;
@@ -355,12 +360,22 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
     s->dtype = dtype;
     s->pad = padding_value;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&s->ready[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->freed[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&s->state, (size_t)B * N * d * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->host_action, (size_t)B * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->host_action, (size_t)B * 4 * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->reward, (size_t)B * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_count, 4);
+    // per-step count buffers of hk_session_rollout are sized here (allocating later would put a
+    // device-synchronising cudaMallocHost on the step path); they grow only for T > 1024
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->counts, 1024 * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->counts_pinned, 1024 * 4);
+    if (e == cudaSuccess) s->counts_cap = 1024;
     if (e != cudaSuccess) {
         hk_session_destroy(s);
         return (int)e;
@@ -379,6 +394,13 @@ int hk_session_destroy(hk_session* s) {
     cudaFree(s->done);
     cudaFree(s->reward);
     cudaFree(s->done_count);
+    cudaFree(s->counts);
+    if (s->counts_pinned) cudaFreeHost(s->counts_pinned);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ready[i]) cudaEventDestroy(s->ready[i]);
+        if (s->freed[i]) cudaEventDestroy(s->freed[i]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HK_OK;
@@ -405,9 +427,10 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
     if (!s) return HK_ERR_BAD_ARG;
     if ((ops & HK_OP_SHIFT) && (!host_action_host || !axis_host)) return HK_ERR_BAD_ARG;
     HK_CUDA(cudaSetDevice(s->device));
+    const size_t abytes = (size_t)s->B * ((flags & HK_F_ACT_U8) ? 1 : 4);
     if (ops & HK_OP_SHIFT) {
-        HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, (size_t)s->B * 4, cudaMemcpyHostToDevice, s->stream));
-        HK_CUDA(cudaMemcpyAsync(s->axis, axis_host, (size_t)s->B * 4, cudaMemcpyHostToDevice, s->stream));
+        HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, abytes, cudaMemcpyHostToDevice, s->stream));
+        HK_CUDA(cudaMemcpyAsync(s->axis, axis_host, abytes, cudaMemcpyHostToDevice, s->stream));
     }
     StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
     p.host_action = s->host_action;
@@ -426,6 +449,52 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
     if (reward_host) HK_CUDA(cudaMemcpyAsync(reward_host, s->reward, (size_t)s->B * 4, cudaMemcpyDeviceToHost, s->stream));
     if (done_count_host) HK_CUDA(cudaMemcpyAsync(done_count_host, s->done_count, 4, cudaMemcpyDeviceToHost, s->stream));
     HK_CUDA(cudaStreamSynchronize(s->stream));
+    return HK_OK;
+}
+
+int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                       int32_t* done_count_host, uint32_t ops, uint32_t flags) {
+    if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || !axis_host) return HK_ERR_BAD_ARG;
+    HK_CUDA(cudaSetDevice(s->device));
+    if (s->counts_cap < T) {
+        cudaFree(s->counts);
+        if (s->counts_pinned) cudaFreeHost(s->counts_pinned);
+        s->counts = nullptr;
+        s->counts_pinned = nullptr;
+        s->counts_cap = 0;
+        HK_CUDA(cudaMalloc((void**)&s->counts, (size_t)T * 4));
+        HK_CUDA(cudaMallocHost((void**)&s->counts_pinned, (size_t)T * 4));
+        s->counts_cap = T;
+    }
+    const size_t esz = (flags & HK_F_ACT_U8) ? 1 : 4;
+    const size_t abytes = (size_t)s->B * esz;
+    HK_CUDA(cudaMemsetAsync(s->counts, 0, (size_t)T * 4, s->stream));
+    for (int t = 0; t < T; ++t) {
+        const int slot = t & 1;
+        int32_t* ha = s->host_action + (size_t)slot * s->B;
+        int32_t* ax = s->axis + (size_t)slot * s->B;
+        // copy stream: wait until the step that last used this slot has run, then upload step t
+        if (t >= 2) HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[slot], 0));
+        HK_CUDA(cudaMemcpyAsync(ha, (const char*)host_action_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
+                                s->copy_stream));
+        HK_CUDA(cudaMemcpyAsync(ax, (const char*)axis_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
+                                s->copy_stream));
+        HK_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
+        HK_CUDA(cudaStreamWaitEvent(s->stream, s->ready[slot], 0));
+        StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
+        p.host_action = ha;
+        p.axis = ax;
+        p.done_count = s->counts + t;
+        p.ops = ops;
+        p.flags = flags;
+        int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
+        if (rc != HK_OK) return rc;
+        HK_CUDA(cudaEventRecord(s->freed[slot], s->stream));
+        if (done_count_host)  // the step's result goes back to the host right after the step
+            HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    HK_CUDA(cudaStreamSynchronize(s->stream));
+    if (done_count_host) memcpy(done_count_host, s->counts_pinned, (size_t)T * 4);
     return HK_OK;
 }
 

@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
         }
         int32_t ha = 3, ax = 0;
         if (p.ops & HK_OP_SHIFT) {
-            ha = __ldg(p.host_action + g);
-            ax = __ldg(p.axis + g);
+            ha = load_action(p.host_action, g, p.flags);
+            ax = load_action(p.axis, g, p.flags);
         }
         if (tma) {
             mbar_wait(bar, parity);
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
         for (int st = 0; st < p.T; ++st) {
             int32_t ha_n = 3, ax_n = 0;
             if ((p.ops & HK_OP_SHIFT) && st + 1 < p.T) {
-                ha_n = __ldg(p.host_action + (long long)(st + 1) * p.B + g);
-                ax_n = __ldg(p.axis + (long long)(st + 1) * p.B + g);
+                ha_n = load_action(p.host_action, (long long)(st + 1) * p.B + g, p.flags);
+                ax_n = load_action(p.axis, (long long)(st + 1) * p.B + g, p.flags);
             }
             const bool prev_done = cnt < 2;
 
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                     for (int k = 0; k < D; ++k) gobs[rank * D + k] = fi[k];
                 }
                 if (p.obs_coord && lane < D) {
-                    const uint32_t ocm = action_mask(__ldg(p.obs_coord + g), p.flags);
+                    const uint32_t ocm = action_mask(load_action(p.obs_coord, g, p.flags), p.flags);
                     gobs[W + lane] = (float)((ocm >> lane) & 1u);
                 }
             }

@@ -368,8 +368,8 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
     for (int st = 0; st < p.T; ++st) {
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
-            ha_n = __ldg(p.host_action + (long long)(st + 1) * B + ls.g);
-            ax_n = __ldg(p.axis + (long long)(st + 1) * B + ls.g);
+            ha_n = load_action(p.host_action, (long long)(st + 1) * B + ls.g, p.flags);
+            ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
         }
         const bool prev_done = ls.cnt < 2;
         clm = game_step<T, K, D, RS>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         ls.ha = 3;
         ls.ax = 0;
         if (ls.shift) {
-            ls.ha = __ldg(p.host_action + ls.g);
-            ls.ax = __ldg(p.axis + ls.g);
+            ls.ha = load_action(p.host_action, ls.g, p.flags);
+            ls.ax = load_action(p.axis, ls.g, p.flags);
         }
 
         if (tma) {
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                 float* orow = obs_tile + lane * OW;
                 game_features<T, N, D>(z, zl, p.flags, p.pad, orow);
                 if (p.obs_coord) {
-                    const uint32_t ocm = ls.valid ? action_mask(__ldg(p.obs_coord + ls.g), p.flags) : 0u;
+                    const uint32_t ocm = ls.valid ? action_mask(load_action(p.obs_coord, ls.g, p.flags), p.flags) : 0u;
 #pragma unroll
                     for (int k = 0; k < D; ++k) orow[W + k] = (float)((ocm >> k) & 1u);
                 }

@@ -55,6 +55,21 @@ class HostSession:
         check(rc, "hk_session_step")
         return cnt.value if want_done_count else None
 
+    def rollout(self, host_actions: np.ndarray, axes: np.ndarray, ops: int, flags: int) -> np.ndarray:
+        """T steps from host action streams [T, B] (int32, or uint8 with HK_F_ACT_U8): uploads are
+        double-buffered against the running step, the finished-game count of every step is read
+        back; returns int32 [T].  Pass pinned arrays (e.g. torch.empty(..., pin_memory=True).numpy())
+        for full PCIe speed."""
+        want = np.uint8 if flags & C.HK_F_ACT_U8 else np.int32
+        ha = np.ascontiguousarray(host_actions, dtype=want)
+        ax = np.ascontiguousarray(axes, dtype=want)
+        if ha.ndim != 2 or ha.shape[1] != self.B or ax.shape != ha.shape:
+            raise ValueError("host_actions and axes must be [T, B]")
+        counts = np.zeros(ha.shape[0], dtype=np.int32)
+        check(lib().hk_session_rollout(self._h, ha.ctypes.data, ax.ctypes.data, ha.shape[0], counts.ctypes.data,
+                                       ops, flags), "hk_session_rollout")
+        return counts
+
     def close(self) -> None:
         if self._h:
             lib().hk_session_destroy(self._h)

@@ -70,6 +70,8 @@ extern "C" {
 #define HK_F_OBS_RESCALE (1u << 4)    /* observation features are rescaled (scale_observation, util.py:183) */
 #define HK_F_OBS_SORT_COORD0 (1u << 5)/* rows sorted by coordinate 0, descending, stable (TensorPoints.get_features, tensor_points.py:72-74) */
 #define HK_F_OBS_SORT_LEX (1u << 6)   /* rows sorted descending lexicographically, LAST coordinate primary, stable (util.py:195) */
+#define HK_F_ACT_U8 (1u << 7)         /* host_action[] / axis[] / obs_coord[] are uint8 arrays instead of int32 (ids < 256, i.e.
+                                         discrete ids up to d = 8 or bitmasks up to d = 8): 2 instead of 8 action bytes per game-step */
 
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
@@ -151,6 +153,12 @@ int hk_session_get_state(hk_session* s, void* state_host);         /* D2H of [B,
 int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_t* axis_host,
                     uint8_t* done_host, float* reward_host, int32_t* done_count_host, uint32_t ops,
                     uint32_t flags);
+/* T steps driven from host action streams [T,B] (int32, or uint8 with HK_F_ACT_U8; pinned memory
+ * recommended): step t+1's actions are copied on a second stream while step t runs; after every
+ * step the number of finished games is copied to done_count_host[t] (the per-step read of
+ * compute_rho, hironaka/jax/jax_trainer.py:533-534).  One synchronisation at the end. */
+int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                       int32_t* done_count_host, uint32_t ops, uint32_t flags);
 void* hk_session_state_ptr(hk_session* s); /* device pointer of the resident state (zero-copy interop) */
 void* hk_session_stream(hk_session* s);
 

@@ -254,6 +254,40 @@ def test_host_session_numpy_only():
     s.close()
 
 
+def test_uint8_actions_and_session_rollout():
+    """HK_F_ACT_U8 (2 action bytes per game-step) and the pipelined host-buffer rollout."""
+    from hironaka_b200 import HostSession, constants as C, ops
+    rng = np.random.default_rng(17)
+    for (B, N, d) in [(3000, 20, 3), (500, 64, 5)]:
+        ncls = 2 ** d - d - 1
+        Tn = 7
+        x = rng.integers(0, 20, (B, N, d)).astype(np.int32)
+        ha = rng.integers(0, ncls, (Tn, B)).astype(np.int32)
+        ax = rng.integers(0, d, (Tn, B)).astype(np.int32)
+        op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+        o, counts = x, []
+        for t in range(Tn):
+            o, od, _, _ = cport.step(o, ha[t], ax[t], op_bits, O.F_ACT_DISCRETE)
+            counts.append(int(od.sum()))
+        # device path with uint8 action tensors
+        st = T(x)
+        for t in range(Tn):
+            hu, au = T(ha[t].astype(np.uint8)), T(ax[t].astype(np.uint8))
+            rc_flags = C.HK_F_ACT_DISCRETE | C.HK_F_ACT_U8
+            from hironaka_b200._lib import check, lib
+            check(lib().hk_step(st.data_ptr(), st.data_ptr(), hu.data_ptr(), au.data_ptr(), None, None, None, None, None,
+                                None, B, N, d, C.HK_DTYPE_I32, op_bits, rc_flags, -1.0, 1e8,
+                                torch.cuda.current_stream().cuda_stream))
+        assert eq(st, o)
+        # host-buffer session, int32 and uint8 streams
+        for u8 in (False, True):
+            s = HostSession(x)
+            dt = np.uint8 if u8 else np.int32
+            got = s.rollout(ha.astype(dt), ax.astype(dt), op_bits, C.HK_F_ACT_DISCRETE | (C.HK_F_ACT_U8 if u8 else 0))
+            assert got.tolist() == counts and np.array_equal(s.get_state(), o)
+            s.close()
+
+
 def test_cuda_graph_capture_of_step():
     """The device entry points neither allocate nor synchronise: a step can be captured in a
     CUDA graph and replayed (MCTS node expansion)."""

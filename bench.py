@@ -36,6 +36,7 @@ METRIC = "game_steps_per_sec"
 UNIT = "game-steps/s"
 N_POINTS, DIM, T_ROLLOUT, MAX_VALUE = 20, 3, 20, 20
 GAMES_PER_GPU = 1 << 20
+CPU_SAMPLE_GAMES = 1 << 19   # bounded sample of the C2 workload for the CPU arm (state 126 MB, ~1 s per 40 steps)
 MAX_RESIDENT_ROLLOUTS = 10  # distinct pre-generated batches; beyond K = 200 they are restored from pristine copies
 BYTES_PER_GAME_STEP = 8 * N_POINTS * DIM + 13  # int32 state r+w, 2 x int32 action, u8 done, f32 reward
 OPS_PER_GAME_STEP = N_POINTS * (N_POINTS - 1) * (DIM + 1) + 3 * N_POINTS * DIM + N_POINTS
@@ -165,7 +166,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 1 << 18
+    sample = CPU_SAMPLE_GAMES
     rate, cores, dt = cpu_rate(sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -276,6 +277,12 @@ def run_gpu_arm(args):
     value = B * world * K / (total_ms_max * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            secondary = measure_secondary(torch, lib, C, dev)
+        except Exception as e:  # context numbers must never take the headline down
+            secondary = {"error": repr(e)}
     e2e = None if args.no_e2e else measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
 
     if rank != 0:
@@ -299,9 +306,9 @@ def run_gpu_arm(args):
     cpu = None
     if not args.no_cpu:
         try:
-            rate, cores, dt = cpu_rate(1 << 18, 40, 5)
+            rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, 40, 5)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{1 << 18} games x 40 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
+                   "sample": f"{CPU_SAMPLE_GAMES} games x 40 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
                              f"(C port of the reference step) over {cores} pthreads"}
         except Exception as e:  # the CPU baseline must never take the GPU line down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -310,12 +317,168 @@ def run_gpu_arm(args):
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
-        "library": os.path.relpath(hb.LIB_PATH, ROOT),
+        "library": os.path.relpath(hb.LIB_PATH, ROOT), "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def int32_peak():
+    try:
+        with open(os.path.join(ROOT, "profiles", "int32_peak.json")) as f:
+            return float(json.load(f)["int32_peak_ops"]), "measured (profiles/int32_peak.json, tools/int32_peak.cu)"
+    except Exception:
+        return 148 * 128 * 1.965e9, "nominal 148 SM x 128 lanes x 1.965 GHz"
+
+
+def measure_secondary(torch, lib, C, dev):
+    """The other BASELINE.json configs, device-timed with CUDA events (rank 0, N = 1 only).
+    They are parity-test cases first (tests/test_gpu_parity.py::test_baseline_sizes_bit_exact);
+    the numbers here are context for DESIGN.md, not the headline."""
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    peak_hbm, _ = measured_peak()
+    peak_int, int_src = int32_peak()
+    out = {}
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n  # ms per call
+
+    def make(B, N, d, T, mv, seed, reposition):
+        rng = np.random.default_rng(seed)
+        ncls = 2 ** d - d - 1
+        x = torch.from_numpy(rng.integers(0, mv, size=(B, N, d), dtype=np.int32)).to(dev)
+        ha = torch.from_numpy(rng.integers(0, ncls, size=(T, B), dtype=np.int32)).to(dev)
+        ax = torch.from_numpy(rng.integers(0, d, size=(T, B), dtype=np.int32)).to(dev)
+        init = C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0)
+        rc = lib.hk_step(x.data_ptr(), x.data_ptr(), None, None, None, None, None, None, None, None, B, N, d,
+                         C.HK_DTYPE_I32, init, 0, -1.0, 1e8, stream)
+        assert rc == 0, rc
+        return x, ha, ax
+
+    def step_fn(x, ha, ax, B, N, d, T, ops_bits, flags, done, reward, pristine=None):
+        def fn(i):
+            t = i % T
+            if t == 0 and pristine is not None and i > 0:
+                x.copy_(pristine)
+            rc = lib.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(),
+                             reward.data_ptr(), None, None, None, None, B, N, d, C.HK_DTYPE_I32, ops_bits, flags, -1.0,
+                             1e8, stream)
+            if rc != 0:
+                raise RuntimeError(rc)
+        return fn
+
+    # C1: TensorPoints batch=1024, dim=3, max_num_points=10, torch semantics, T=10 (launch-latency bound)
+    B, N, d, T = 1024, 10, 3, 10
+    x, ha, ax = make(B, N, d, T, 21, 1, False)
+    done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+    ms = timed(step_fn(x, ha, ax, B, N, d, T, C.HK_OP_SHIFT | C.HK_OP_NEWTON, C.TORCH_SEMANTICS | C.HK_F_ACT_DISCRETE,
+                       done, rew, x.clone()), 200)
+    out["C1"] = {"workload": "B=1024, N=10, d=3, torch semantics, T=10", "us_per_launch": ms * 1e3,
+                 "game_steps_per_s": B / (ms * 1e-3), "bound": "launch latency (1024 games = 123 KB per launch)",
+                 "hbm_frac": B * (8 * N * d + 13) / (ms * 1e-3) / 1e9 / peak_hbm}
+
+    # C5: dim=5, max_num_points=64, batch 256K, T=20 — the warp-per-game kernel, ALU-bound shape
+    B, N, d, T = 1 << 18, 64, 5, 20
+    x, ha, ax = make(B, N, d, T, 20, 5, True)
+    done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+    pristine = x.clone()
+    fn = step_fn(x, ha, ax, B, N, d, T, C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, C.HK_F_ACT_DISCRETE, done,
+                 rew, None)
+    per = []
+    for rep in range(3):
+        x.copy_(pristine)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+        ev[0].record()
+        for t in range(T):
+            fn(t)
+            ev[t + 1].record()
+        torch.cuda.synchronize()
+        if rep:
+            per.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
+    per = np.mean(np.array(per), axis=0)
+    ms = float(per.mean())
+    ops5 = N * (N - 1) * (d + 1) + 3 * N * d + N
+    bytes5 = 8 * N * d + 13
+    # the same kernel on the ROOT filter (64 random live points per game = the dense worst case)
+    xr = torch.from_numpy(np.random.default_rng(6).integers(0, 20, size=(B, N, d), dtype=np.int32)).to(dev)
+    work = xr.clone()
+
+    def root(i):
+        work.copy_(xr)
+        rc = lib.hk_step(work.data_ptr(), work.data_ptr(), None, None, None, None, None, None, None, None, B, N, d,
+                         C.HK_DTYPE_I32, C.HK_OP_NEWTON, 0, -1.0, 1e8, stream)
+        assert rc == 0
+
+    def copy_only(i):
+        work.copy_(xr)
+    ms_root = timed(root, 10) - timed(copy_only, 10)
+    out["C5"] = {"workload": "B=262144, N=64, d=5, random play T=20, JAX semantics with reposition",
+                 "kernel": "hk::hk_generic_kernel<int,5,false>", "ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
+                 "ms_by_rollout_step": [round(float(v), 4) for v in per],
+                 "hbm_frac": B * bytes5 / (ms * 1e-3) / 1e9 / peak_hbm,
+                 "int_ops_per_game_step_dense": ops5, "int32_peak": peak_int, "int32_peak_source": int_src,
+                 "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
+                 "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
+                         "dense count; the dense count is what the root filter (64 live points) executes"}
+
+    # C3: MCTS node expansion — latency per call at eval_batch_size 10/100/512 (N=20, d=3)
+    lat = {}
+    for B in (10, 100, 512):
+        N, d, T = 20, 3, 20
+        x, ha, ax = make(B, N, d, T, 20, 3, True)
+        done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+        obs = torch.empty((B, N * d), dtype=torch.float32, device=dev)
+        flags = C.HK_F_ACT_DISCRETE | C.HK_F_OBS_SORT_LEX | C.HK_F_OBS_RESCALE
+
+        def one(i):
+            rc = lib.hk_step(x.data_ptr(), x.data_ptr(), ha[i % T].data_ptr(), ax[i % T].data_ptr(), done.data_ptr(),
+                             rew.data_ptr(), None, obs.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32,
+                             C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, flags, -1.0, 1e8, stream)
+            assert rc == 0
+        stream_us = timed(one, 2000) * 1e3
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gs = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.hk_step(x.data_ptr(), x.data_ptr(), ha[0].data_ptr(), ax[0].data_ptr(), done.data_ptr(),
+                             rew.data_ptr(), None, obs.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32,
+                             C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, flags, -1.0, 1e8, gs)
+            assert rc == 0
+        graph_us = timed(lambda i: g.replay(), 2000) * 1e3
+        lat[str(B)] = {"stream_launch_us": stream_us, "graph_replay_us": graph_us}
+    out["C3_step_with_features_us_per_call"] = lat
+
+    # one-launch rollout (hk_rollout, T=20): the state is read and written once per 20 steps
+    B, N, d, T = GAMES_PER_GPU, N_POINTS, DIM, T_ROLLOUT
+    x, ha, ax = make(B, N, d, T, MAX_VALUE, 9, True)
+    pristine = x.clone()
+    dcount = torch.zeros(T, dtype=torch.int32, device=dev)
+
+    def roll(i):
+        x.copy_(pristine)
+        rc = lib.hk_rollout(x.data_ptr(), x.data_ptr(), ha.data_ptr(), ax.data_ptr(), None, None, dcount.data_ptr(), None,
+                            B, N, d, T, C.HK_DTYPE_I32, C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON,
+                            C.HK_F_ACT_DISCRETE, -1.0, stream)
+        assert rc == 0
+
+    def copy2(i):
+        x.copy_(pristine)
+    ms = timed(roll, 10) - timed(copy2, 10)
+    out["rollout_fused_T20"] = {"workload": "C2, 1 Mi games, hk_rollout: 20 steps in one launch", "ms_per_rollout": ms,
+                                "game_steps_per_s": B * T / (ms * 1e-3),
+                                "bytes_per_game_step": (8 * N * d) / T + 8 + 0.0}
+    return out
 
 
 def measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist):
@@ -372,6 +535,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (profiling runs)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

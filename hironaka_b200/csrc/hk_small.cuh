@@ -256,71 +256,83 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
     return lm;
 }
 
-// Observation features of one game: optional rescale, stable descending rank sort, scatter into
-// the lane's row of the obs tile.  (TensorPoints.get_features tensor_points.py:72-74;
-// order_and_rescale util.py:186-196.)
-template <typename T, int N, int D>
-__device__ __forceinline__ void game_features(const T (&x)[N * D], uint32_t lm, uint32_t flags, float padf,
-                                              float* row) {
-    float f[N * D];
+// one element of the lane's shared-memory game area (float: -0.0 canonicalised to +0.0)
+template <typename T>
+__device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
+    T v = Elem<T>::from_bits(row[w]);
+    if constexpr (Elem<T>::is_float) v = v + 0.0f;
+    return v;
+}
+
+// Observation features from the compact rows: optional rescale, stable descending rank sort
+// among the LIVE rows only (dead rows all equal the padding value, which is below every live key,
+// so they fill the tail of the observation in any stable order), scattered into the lane's row of
+// the obs tile.  (TensorPoints.get_features tensor_points.py:72-74; order_and_rescale
+// util.py:186-196.)  Compact order is slot order, so ties resolve to the lowest slot first.
+template <typename T, int K, int D>
+__device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm, const int (&slot)[K], uint32_t flags,
+                                              float padf, float* orow, int W) {
+    // all padding first
+    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+        const float4 pv = make_float4(padf, padf, padf, padf);
+        for (int q = 0; q < W / 4; ++q) reinterpret_cast<float4*>(orow)[q] = pv;
+    } else {
+        for (int q = 0; q < W; ++q) orow[q] = padf;
+    }
+    float f[K * D];
     float mx = -1.0f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
+    for (int k = 0; k < K; ++k) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            float v = Elem<T>::to_float(x[i * D + k]);
-            f[i * D + k] = v;
-            mx = ((lm >> i) & 1u) ? fmaxf(mx, v) : mx;
+        for (int c = 0; c < D; ++c) {
+            const float v = Elem<T>::to_float(y[k * D + c]);
+            f[k * D + c] = v;
+            mx = ((clm >> k) & 1u) ? fmaxf(mx, v) : mx;
         }
     }
     if (mx == 0.0f) mx = 1.0f;
-    const bool resc = (flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+    if ((flags & HK_F_OBS_RESCALE) && mx > 0.0f) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            float v = f[i * D + k];
-            v = resc ? __fdiv_rn(v, mx) : v;
-            f[i * D + k] = ((lm >> i) & 1u) ? v : padf;
-        }
+        for (int q = 0; q < K * D; ++q) f[q] = __fdiv_rn(f[q], mx);
     }
-    int rank[N];
+    int rank[K];
+    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX);
+    const bool lex = flags & HK_F_OBS_SORT_LEX;
 #pragma unroll
-    for (int i = 0; i < N; ++i) rank[i] = i;
-    if (flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX)) {
-        const bool lex = flags & HK_F_OBS_SORT_LEX;
+    for (int k = 0; k < K; ++k) rank[k] = sorted ? 0 : slot[k];  // unsorted: every row stays in its slot
 #pragma unroll
-        for (int i = 0; i < N; ++i) rank[i] = 0;
+    for (int i = 0; i < K; ++i) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
+        for (int j = i + 1; j < K; ++j) {
+            const bool both = sorted && (((clm >> i) & (clm >> j) & 1u) != 0);
+            // does row j sort strictly before row i?  (ties: lower slot first)
+            bool gt = f[j * D] > f[i * D];
+            if (lex) {
 #pragma unroll
-            for (int j = i + 1; j < N; ++j) {
-                // does row j sort strictly before row i?  (ties: lower index first)
-                bool gt = f[j * D] > f[i * D];
-                if (lex) {
-#pragma unroll
-                    for (int k = 1; k < D; ++k)
-                        gt = (f[j * D + k] > f[i * D + k]) || ((f[j * D + k] == f[i * D + k]) && gt);
-                }
-                rank[i] += gt ? 1 : 0;
-                rank[j] += gt ? 0 : 1;
+                for (int c = 1; c < D; ++c)
+                    gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
             }
+            rank[i] += (both && gt) ? 1 : 0;
+            rank[j] += (both && !gt) ? 1 : 0;
         }
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
+    for (int k = 0; k < K; ++k) {
+        if ((clm >> k) & 1u) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) row[rank[i] * D + k] = f[i * D + k];
+            for (int c = 0; c < D; ++c) orow[rank[k] * D + c] = f[k * D + c];
+        }
     }
 }
 
 // ---- compacted tiers ------------------------------------------------------------------------------
 // Under real play few of the N slots are live (mean 6 of 20 after the root filter, 3 after two
 // steps), and the O(K^2 d) filter only needs the live rows.  Each warp therefore picks a tier
-// K in {4, 8, 12, N} from the maximum live count over its 32 games (warp-uniform, no
+// K in {4, 8, 12, 16, N} from the maximum live count over its 32 games (warp-uniform, no
 // divergence), gathers every lane's live rows into K register rows through the lane's own
 // shared-memory copy of the game (slot order is kept, so the lowest-index-wins dedupe rule is
-// unchanged), runs all T steps on the K rows and scatters the survivors back to their slots.
+// unchanged), runs the steps on the K rows and scatters the survivors back to their slots.  In a
+// multi-step rollout the warp drops to a smaller tier as soon as its live counts allow it.
 struct LaneState {
     long long g;
     bool valid, shift;
@@ -329,15 +341,22 @@ struct LaneState {
     int32_t len;
 };
 
-template <typename T, int N, int D, int K>
-__device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, T (&x)[N * D],
-                                           uint32_t lm, bool write, bool& exceed) {
+__host__ __device__ constexpr int next_lower_tier(int K) { return K > 16 ? 16 : (K > 12 ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0))); }
+
+// Runs steps [st, T) of one tile on K compact rows; returns the step index at which it stopped
+// (T, or earlier when every game of the warp fits the next lower tier).  The lane's game area in
+// shared memory (`row`) holds the current state on entry and on exit.
+template <typename T, int N, int D, int K, bool OBS>
+__device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, const T (&x)[N * D],
+                                          uint32_t lm, int st, bool& exceed, float* orow, int OW) {
     const long long B = p.B;
     const T padv = Elem<T>::pad(p.pad);
-    // tiers of 12 rows and more run the filter with a rolled victim loop through the lane's own
+    const bool mutate = p.ops != 0;
+    // tiers of 12 and 16 rows run the filter with a rolled victim loop through the lane's own
     // shared-memory game area (scratch); the area is rebuilt from registers at the end
-    constexpr bool ROLLED = (K >= 12) && (K < N) && ((N * D) % 4 == 0);  // the full tier (root filter) stays unrolled
+    constexpr bool ROLLED = (K >= 12) && (K < N) && ((N * D) % 4 == 0);
     constexpr int RS = !ROLLED ? 0 : ((D == 3 && 4 * K <= N * D) ? 4 : D);
+    constexpr int LOWER = next_lower_tier(K);
     T y[K * D];
     int idx[K];
     uint32_t clm = 0, cvalid = 0;
@@ -356,16 +375,11 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
             idx[k] = i;
             clm |= v ? (1u << k) : 0u;
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                T val = Elem<T>::from_bits(row[i * D + c]);
-                if constexpr (Elem<T>::is_float) val = val + 0.0f;
-                y[k * D + c] = val;
-            }
+            for (int c = 0; c < D; ++c) y[k * D + c] = x_row_value<T>(row, i * D + c);
         }
         cvalid = clm;
     }
-    // T consecutive steps on the compact rows (T == 1 for hk_step)
-    for (int st = 0; st < p.T; ++st) {
+    for (; st < p.T;) {
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
             ha_n = load_action(p.host_action, (long long)(st + 1) * B + ls.g, p.flags);
@@ -389,9 +403,14 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
         if (dn && !prev_done) ls.len = st + 1;
         ls.ha = ha_n;
         ls.ax = ax_n;
+        ++st;
+        if constexpr (LOWER > 0) {
+            if (st < p.T && __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0) <= LOWER) break;  // re-tier
+        }
     }
-    if (p.exceed_flag) exceed = exceeds<T, K, D>(y, clm, p.threshold);
-    if (write) {
+    const bool last = st >= p.T;
+    if (last && p.exceed_flag) exceed = exceeds<T, K, D>(y, clm, p.threshold);
+    if (mutate) {
         if constexpr (K == N) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -416,6 +435,17 @@ __device__ __forceinline__ void tier_steps(const StepParams& p, LaneState& ls, u
             }
         }
     }
+    if constexpr (OBS) {
+        if (last && p.obs) {
+            if constexpr (K == N) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) idx[k] = k;
+            }
+            tier_features<T, K, D>(y, clm, idx, p.flags, p.pad, orow, N * D);
+        }
+    }
+    (void)OW;
+    return st;
 }
 
 // ---- tile movement -------------------------------------------------------------------------------
@@ -447,6 +477,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
     const bool obs_tma = aligned16(p.obs);
     const T padv = Elem<T>::pad(p.pad);
     const bool write = (gout != nullptr);
+    const bool mutate = p.ops != 0;
 
     if (lane == 0) {
 #pragma unroll
@@ -478,6 +509,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
     for (long long t = gw; t < ntiles; t += nw) {
         uint32_t* stage = ring + s * L::TILE_WORDS;
         uint32_t* row = stage + lane * W;
+        float* orow = obs_tile + lane * OW;
         LaneState ls;
         ls.g = (t << 5) + lane;
         ls.valid = ls.g < B;
@@ -499,53 +531,54 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
             __syncwarp();
         }
 
-        T x[W];
-        load_game<T, W>(row, x);
-        if constexpr (Elem<T>::is_float) {
-#pragma unroll
-            for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
-        }
-        uint32_t lm = live_mask<T, N, D>(x);
-        ls.cnt = __popc(lm);
-        ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
         bool exceed = false;
-        if (p.ops) {
+        bool normalised = false;
+        ls.len = -1;
+        int st = 0;
+        do {
+            T x[W];
+            load_game<T, W>(row, x);
+            if constexpr (Elem<T>::is_float) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
+            }
+            const uint32_t lm = live_mask<T, N, D>(x);
+            ls.cnt = __popc(lm);
+            if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
             const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
-            auto prestore = [&]() {  // dead rows are rewritten with the padding value (every reference op does)
-                if (write) {
+            // the gathered tiers scatter only live rows, so dead rows are rewritten with the padding
+            // value first (every reference op does that); once per tile is enough
+            auto prestore = [&]() {
+                if (mutate && !normalised) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
 #pragma unroll
                         for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
                     }
                     store_game<T, W>(row, x);
+                    normalised = true;
                 }
             };
             if (N > 4 && lmax <= 4) {
                 prestore();
-                tier_steps<T, N, D, (N > 4 ? 4 : N)>(p, ls, row, x, lm, write, exceed);
+                st = tier_steps<T, N, D, (N > 4 ? 4 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
             } else if (N > 8 && lmax <= 8) {
                 prestore();
-                tier_steps<T, N, D, (N > 8 ? 8 : N)>(p, ls, row, x, lm, write, exceed);
+                st = tier_steps<T, N, D, (N > 8 ? 8 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
             } else if (N > 12 && lmax <= 12) {
                 if (W % 4 != 0) prestore();
-                tier_steps<T, N, D, (N > 12 ? 12 : N)>(p, ls, row, x, lm, write, exceed);
+                st = tier_steps<T, N, D, (N > 12 ? 12 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                normalised = normalised || (W % 4 == 0);
             } else if (N > 16 && lmax <= 16) {
                 if (W % 4 != 0) prestore();
-                tier_steps<T, N, D, (N > 16 ? 16 : N)>(p, ls, row, x, lm, write, exceed);
+                st = tier_steps<T, N, D, (N > 16 ? 16 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                normalised = normalised || (W % 4 == 0);
             } else {
-                tier_steps<T, N, D, N>(p, ls, row, x, lm, write, exceed);
+                st = tier_steps<T, N, D, N, OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                normalised = true;
             }
-        } else {
-            // no op selected (hk_dones / hk_features / exceed check): outputs of the state as it is
-            if (ls.valid) {
-                const bool dn = ls.cnt < 2;
-                if (p.done) p.done[ls.g] = dn ? 1 : 0;
-                if (p.reward) p.reward[ls.g] = 0.0f;
-            }
-            if (p.exceed_flag) exceed = exceeds<T, N, D>(x, lm, p.threshold);
-            if (write) store_game<T, W>(row, x);
-        }
+        } while (st < p.T);
+
         if (ls.valid) {
             if (p.num_points) p.num_points[ls.g] = ls.cnt;
             if (p.length) p.length[ls.g] = ls.len;
@@ -569,12 +602,6 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         }
         if constexpr (OBS) {
             if (p.obs) {
-                // features of the NEW state: re-read the lane's game (scattered survivors included)
-                T z[W];
-                load_game<T, W>(row, z);
-                const uint32_t zl = live_mask<T, N, D>(z);
-                float* orow = obs_tile + lane * OW;
-                game_features<T, N, D>(z, zl, p.flags, p.pad, orow);
                 if (p.obs_coord) {
                     const uint32_t ocm = ls.valid ? action_mask(load_action(p.obs_coord, ls.g, p.flags), p.flags) : 0u;
 #pragma unroll

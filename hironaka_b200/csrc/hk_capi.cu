@@ -105,28 +105,37 @@ bool is_small(int N, int d) { return d == 3 && (N == 20 || N == 10 || N == 5); }
 // ---- generic (warp-per-game) family -------------------------------------------------------------
 template <typename T, int D, bool OBS>
 int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
-    static KernelFacts facts[9];  // indexed by warps per CTA (1..8)
     auto kernel = hk::hk_generic_kernel<T, D, OBS>;
     const int W = p.N * D;
     const int Wpad = (W + 3) & ~3;
     const int R = (p.N + 31) / 32;
-    const int slot_words = Wpad * (OBS ? 2 : 1) + ((R + 3) & ~3);
+    const int slot_words = Wpad * (OBS ? 3 : 2) + ((R + 3) & ~3);  // two state buffers (+ features) + live-mask words
     int warps = 8;
-    while (warps > 1 && 128 + (size_t)warps * slot_words * 4 > 160 * 1024) warps >>= 1;
-    const size_t smem = 128 + (size_t)warps * slot_words * 4;
+    while (warps > 1 && (size_t)warps * slot_words * 4 > 160 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * slot_words * 4;
+    // launch facts depend on N through the shared-memory size: cache the last one per device
+    struct Facts {
+        std::atomic<size_t> smem_set{0};
+        std::atomic<long long> key{-1};
+        std::atomic<int> per_sm{0};
+    };
+    static Facts facts[kMaxDevices];
+    Facts& fc = facts[dev];
     cudaError_t err = cudaSuccess;
-    // the smem opt-in depends on N; always (re)apply the max so that a later larger N works
-    static std::atomic<size_t> smem_set[kMaxDevices];
-    if (smem > smem_set[dev].load(std::memory_order_acquire)) {
+    if (smem > fc.smem_set.load(std::memory_order_acquire)) {
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        smem_set[dev].store(smem, std::memory_order_release);
+        fc.smem_set.store(smem, std::memory_order_release);
     }
-    int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
-    if (err != cudaSuccess) return (int)err;
-    if (per_sm < 1) per_sm = 1;
-    (void)facts;
+    const long long key = ((long long)smem << 8) | warps;
+    int per_sm = fc.per_sm.load(std::memory_order_acquire);
+    if (fc.key.load(std::memory_order_acquire) != key || per_sm <= 0) {
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
+        if (err != cudaSuccess) return (int)err;
+        if (per_sm < 1) per_sm = 1;
+        fc.per_sm.store(per_sm, std::memory_order_release);
+        fc.key.store(key, std::memory_order_release);
+    }
     long long ctas = (p.B + warps - 1) / warps;
     const long long cap = (long long)device_sms(dev) * per_sm;
     if (ctas > cap) ctas = cap;

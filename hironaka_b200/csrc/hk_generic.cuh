@@ -1,17 +1,18 @@
 // hk_generic.cuh — warp-per-game step kernel for any (N <= 1024, d <= 10).
 //
-// Mapping (DESIGN.md "K-warp"): one warp owns one game at a time; the game's N*d words live
-// in the warp's private shared-memory slot (TMA bulk load when the game is 16-byte sized and
-// aligned, cooperative LDG otherwise); lane l owns rows l, l+32, ...  The dominance filter
+// Mapping (DESIGN.md "K-warp"): one warp owns one game at a time; lane l owns rows l, l+32, ...
+// The game's N*d words are double-buffered in the warp's private shared-memory slots with
+// cp.async (LDGSTS): while game g is processed, game g + (number of warps) streams in, so every
+// warp always has one game in flight (games of this class are 1-16 KB, too small for an efficient
+// TMA transaction each).  Results leave through coalesced 16-byte stores.  The dominance filter
 // broadcasts candidate dominators j from shared memory (uniform address => one wavefront) and
-// iterates ONLY over live j (warp-uniform loop over the ballot words), so cost tracks the
-// number of live points rather than N.  This is the kernel for BASELINE config 5 (N=64, d=5).
+// iterates ONLY over live j (warp-uniform loop over the ballot words), so cost tracks the number
+// of live points rather than N.  This is the kernel for BASELINE config 5 (N=64, d=5) and for
+// remove_repeated alone.
 #pragma once
 #include "hk_common.cuh"
 
 namespace hk {
-
-constexpr int GEN_MAX_ROWS_PER_LANE = HK_MAX_POINTS / 32;
 
 template <typename T>
 __device__ __forceinline__ T warp_min(T v) {
@@ -29,63 +30,76 @@ __device__ __forceinline__ float warp_maxf(float v) {
     return v;
 }
 
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// smem per warp: x[N*D] words, then (OBS) f[N*D] floats, then live-mask words lmw[ceil(N/32)]
+// One dominance word for victim row xi against dominator row j of the shared game:
+// sign 0 <=> row j kills the victim (see op_newton in hk_small.cuh for the derivation).
+template <typename T, int D>
+__device__ __forceinline__ int32_t dominance_word(const T (&xi)[D], const T* x, int i, int j) {
+    int32_t t = Elem<T>::bits(xi[0] - x[j * D]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) t |= Elem<T>::bits(xi[k] - x[j * D + k]);
+    t -= (j >= i) ? 1 : 0;  // ties only kill from a lower slot; also neutralises the self pair
+    return t;
+}
+
+// smem per warp: two state buffers x[2][Wpad], then (OBS) f[Wpad] floats, then lmw[ceil(N/32)]
 template <typename T, int D, bool OBS>
-__global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
+__global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N;
     const int W = N * D;
     const int R = (N + 31) >> 5;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
-    uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 128) + (size_t)warp * slot_words;
-    T* x = reinterpret_cast<T*>(slot);
     const int Wpad = (W + 3) & ~3;
-    float* f = reinterpret_cast<float*>(slot + Wpad);
-    uint32_t* lmw = slot + Wpad + (OBS ? Wpad : 0);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * slot_words;
+    float* f = reinterpret_cast<float*>(slot + 2 * Wpad);
+    uint32_t* lmw = slot + 2 * Wpad + (OBS ? Wpad : 0);
 
     const uint32_t* gin = reinterpret_cast<const uint32_t*>(p.in);
     uint32_t* gout = reinterpret_cast<uint32_t*>(p.out);
-    const bool tma = aligned16(p.in) && aligned16(p.out) && ((W & 3) == 0);
+    const bool vec_in = aligned16(p.in) && ((W & 3) == 0);
+    const bool vec_out = aligned16(p.out) && ((W & 3) == 0);
     const T padv = Elem<T>::pad(p.pad);
     const int OW = W + (p.obs_coord ? D : 0);
 
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    uint32_t parity = 0;
-
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long nw = (long long)gridDim.x * warps_per_cta;
-    for (long long g = gw; g < p.B; g += nw) {
-        // ---- load the game ----
-        if (tma) {
-            if (lane == 0) {
-                mbar_expect_tx(bar, (uint32_t)W * 4u);
-                bulk_load(slot, gin + g * W, (uint32_t)W * 4u, bar);
-            }
+
+    auto prefetch = [&](long long g, int b) {
+        uint32_t* dst = slot + b * Wpad;
+        const uint32_t* src = gin + g * W;
+        if (vec_in) {
+            for (int c = lane; c < (W >> 2); c += 32) cp_async_16(dst + 4 * c, src + 4 * c);
         } else {
-            for (int w = lane; w < W; w += 32) slot[w] = gin[g * W + w];
+            for (int w = lane; w < W; w += 32) cp_async_4(dst + w, src + w);
         }
+    };
+
+    int b = 0;
+    if (gw < p.B) prefetch(gw, 0);
+    cp_async_commit();
+    for (long long g = gw; g < p.B; g += nw, b ^= 1) {
+        if (g + nw < p.B) prefetch(g + nw, b ^ 1);
+        cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
         int32_t ha = 3, ax = 0;
         if (p.ops & HK_OP_SHIFT) {
             ha = load_action(p.host_action, g, p.flags);
             ax = load_action(p.axis, g, p.flags);
         }
-        if (tma) {
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-        } else {
-            __syncwarp();
-        }
+        cp_async_wait<1>();  // everything but the newest group has landed: game g is in buffer b
+        __syncwarp();
+        T* x = reinterpret_cast<T*>(slot + b * Wpad);
 
         // ---- liveness ----
         uint32_t mylive = 0;  // bit r <=> row lane + 32 r is live
@@ -95,12 +109,12 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
             bool lv = false;
             if (i < N) {
                 if constexpr (Elem<T>::is_float) {
-                    for (int k = 0; k < D; ++k) x[i * D + k] = x[i * D + k] + 0.0f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[i * D + k] = x[i * D + k] + 0.0f;  // canonicalise -0.0
                 }
                 lv = x[i * D] >= Elem<T>::zero();
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, lv);
-            cnt += __popc(bal);
+            cnt += __popc(__ballot_sync(0xffffffffu, lv));
             mylive |= lv ? (1u << r) : 0u;
         }
         int32_t len = (cnt < 2) ? 0 : p.T + 1;
@@ -113,7 +127,7 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
             const bool prev_done = cnt < 2;
 
             // ---- shift ----
-            if (p.ops & HK_OP_SHIFT) {
+            if ((p.ops & HK_OP_SHIFT) && cnt > 0) {
                 const uint32_t cm = action_mask(ha, p.flags);
                 bool apply = (ax >= 0) && (ax < D);
                 if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
@@ -123,31 +137,37 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                         if (!((mylive >> r) & 1u)) continue;
                         const int i = lane + 32 * r;
                         T s = Elem<T>::zero();
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + x[i * D + k] : s;
                         x[i * D + ax] = s;
                     }
                 }
             }
             // ---- reposition ----
-            if (p.ops & HK_OP_REPOSITION) {
-    #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    T mn = Elem<T>::big();
-                    for (int r = 0; r < R; ++r) {
-                        if (!((mylive >> r) & 1u)) continue;
-                        T v = x[(lane + 32 * r) * D + k];
-                        mn = v < mn ? v : mn;
+            if ((p.ops & HK_OP_REPOSITION) && cnt > 0) {
+                T mn[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) mn[k] = Elem<T>::big();
+                for (int r = 0; r < R; ++r) {
+                    if (!((mylive >> r) & 1u)) continue;
+                    const int i = lane + 32 * r;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const T v = x[i * D + k];
+                        mn[k] = v < mn[k] ? v : mn[k];
                     }
-                    mn = warp_min<T>(mn);
-                    for (int r = 0; r < R; ++r) {
-                        if (!((mylive >> r) & 1u)) continue;
-                        x[(lane + 32 * r) * D + k] -= mn;
-                    }
+                }
+#pragma unroll
+                for (int k = 0; k < D; ++k) mn[k] = warp_min<T>(mn[k]);
+                for (int r = 0; r < R; ++r) {
+                    if (!((mylive >> r) & 1u)) continue;
+                    const int i = lane + 32 * r;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[i * D + k] -= mn[k];
                 }
             }
             // ---- dedupe alone (remove_repeated _fn.py:192-213) ----
-            if (p.ops & HK_OP_DEDUPE) {
+            if ((p.ops & HK_OP_DEDUPE) && cnt >= 2) {
                 __syncwarp();
                 uint32_t kill = 0;
                 for (int r = 0; r < R; ++r) {
@@ -166,34 +186,61 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                 mylive &= ~kill;
             }
             // ---- newton: dedupe + dominance, reading the pre-removal state ----
-            if (p.ops & HK_OP_NEWTON) {
+            if ((p.ops & HK_OP_NEWTON) && cnt >= 2) {
                 for (int r = 0; r < R; ++r) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, (mylive >> r) & 1u);
                     if (lane == 0) lmw[r] = bal;
                 }
                 __syncwarp();
                 uint32_t kill = 0;
-                for (int r = 0; r < R; ++r) {
-                    const int i = lane + 32 * r;
-                    const bool lv = (mylive >> r) & 1u;
-                    T xi[D];
-    #pragma unroll
-                    for (int k = 0; k < D; ++k) xi[k] = lv ? x[i * D + k] : Elem<T>::big();
-                    int32_t acc = (int32_t)0x80000000;
+                if (R <= 2) {
+                    // both rows of the lane ride on the same broadcast of dominator j
+                    const int i0 = lane, i1 = lane + 32;
+                    const bool l0 = mylive & 1u, l1 = (mylive >> 1) & 1u;
+                    T a0[D], a1[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        a0[k] = l0 ? x[i0 * D + k] : Elem<T>::big();
+                        a1[k] = l1 ? x[i1 * D + k] : Elem<T>::big();
+                    }
+                    int32_t acc0 = (int32_t)0x80000000, acc1 = (int32_t)0x80000000;
                     for (int r2 = 0; r2 < R; ++r2) {
                         uint32_t m = lmw[r2];
                         while (m) {
                             const int j = 32 * r2 + __ffs((int)m) - 1;
                             m &= m - 1;
-                            int32_t t = Elem<T>::bits(xi[0] - x[j * D]);
-    #pragma unroll
-                            for (int k = 1; k < D; ++k) t |= Elem<T>::bits(xi[k] - x[j * D + k]);
-                            t -= (j > i) ? 1 : 0;
-                            t = (j == i) ? (int32_t)0x80000000 : t;
-                            acc &= t;
+                            T xj[D];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) xj[k] = x[j * D + k];
+                            int32_t t0 = Elem<T>::bits(a0[0] - xj[0]), t1 = Elem<T>::bits(a1[0] - xj[0]);
+#pragma unroll
+                            for (int k = 1; k < D; ++k) {
+                                t0 |= Elem<T>::bits(a0[k] - xj[k]);
+                                t1 |= Elem<T>::bits(a1[k] - xj[k]);
+                            }
+                            acc0 &= t0 - ((j >= i0) ? 1 : 0);
+                            acc1 &= t1 - ((j >= i1) ? 1 : 0);
                         }
                     }
-                    kill |= (acc >= 0) ? (1u << r) : 0u;
+                    kill = ((acc0 >= 0) ? 1u : 0u) | ((acc1 >= 0) ? 2u : 0u);
+                } else {
+                    for (int r = 0; r < R; ++r) {
+                        const int i = lane + 32 * r;
+                        const bool lv = (mylive >> r) & 1u;
+                        T xi[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) xi[k] = lv ? x[i * D + k] : Elem<T>::big();
+                        int32_t acc = (int32_t)0x80000000;
+                        for (int r2 = 0; r2 < R; ++r2) {
+                            uint32_t m = lmw[r2];
+                            while (m) {
+                                const int j = 32 * r2 + __ffs((int)m) - 1;
+                                m &= m - 1;
+                                acc &= dominance_word<T, D>(xi, x, i, j);
+                            }
+                        }
+                        kill |= (acc >= 0) ? (1u << r) : 0u;
+                    }
                 }
                 __syncwarp();
                 mylive &= ~kill;
@@ -205,7 +252,7 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                     for (int r = 0; r < R; ++r) {
                         if (!((mylive >> r) & 1u)) continue;
                         const int i = lane + 32 * r;
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < D; ++k) mx = fmaxf(mx, x[i * D + k]);
                     }
                     mx = warp_maxf(mx);
@@ -214,7 +261,7 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                         for (int r = 0; r < R; ++r) {
                             if (!((mylive >> r) & 1u)) continue;
                             const int i = lane + 32 * r;
-    #pragma unroll
+#pragma unroll
                             for (int k = 0; k < D; ++k) x[i * D + k] = __fdiv_rn(x[i * D + k], mx);
                         }
                     }
@@ -261,25 +308,20 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
         if (p.exceed_flag) {
             if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
         }
-        bool stored = false;
+        __syncwarp();
         if (gout) {
-            if (tma) {
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    bulk_store(gout + g * W, slot, (uint32_t)W * 4u);
-                    bulk_commit();
-                }
-                stored = true;
+            const uint32_t* src = slot + b * Wpad;
+            uint32_t* dst = gout + g * W;
+            if (vec_out) {
+                for (int c = lane; c < (W >> 2); c += 32)
+                    reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
             } else {
-                __syncwarp();
-                for (int w = lane; w < W; w += 32) gout[g * W + w] = slot[w];
+                for (int w = lane; w < W; w += 32) dst[w] = src[w];
             }
         }
         // ---- observation features ----
         if constexpr (OBS) {
             if (p.obs) {
-                __syncwarp();
                 float mx = -1.0f;
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
@@ -337,11 +379,9 @@ __global__ void __launch_bounds__(256) hk_generic_kernel(const StepParams p, int
                 }
             }
         }
-        __syncwarp();
-        if (stored && lane == 0) bulk_wait_read<0>();
-        __syncwarp();
+        __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
     }
-    if (lane == 0) bulk_wait_all<0>();
+    cp_async_wait<0>();
 }
 
 }  // namespace hk

@@ -5,6 +5,7 @@ Layers (bottom up):
   _lib, ops        ctypes loader and tensor-level launch wrappers (no fallback path)
   src              drop-in for hironaka.src torch ops (shift_torch, get_newton_polytope_torch, ...)
   TensorPoints     drop-in for hironaka.core.TensorPoints (the `point_cls=` seam)
+  FusedGame        drop-in for hironaka.trainer.fused_game.FusedGame (one launch per move)
   functional       drop-in for hironaka/jax/util.py (take_actions, get_dones, reward_fn, feature_fn, ...)
   GameBatch        resident int32 batches, fused T-step rollouts, sharding + rollout all-gather
   HostSession      NumPy host-buffer sessions over hk_session_*
@@ -29,10 +30,13 @@ def __getattr__(name):  # lazy: importing the package must not require torch or 
     if name == "HostSession":
         from .session import HostSession
         return HostSession
+    if name == "FusedGame":
+        from .fused_game import FusedGame
+        return FusedGame
     if name == "HostActionEncoder":
         from .host_action import HostActionEncoder
         return HostActionEncoder
-    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build"):
+    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build", "fused_game", "players"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

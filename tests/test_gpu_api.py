@@ -138,6 +138,63 @@ def test_tensor_points_features_and_fused_game_flow():
         assert eq(rew, O.default_reward("host", O.ended_batch(ref))[~done.cpu().numpy()])
 
 
+def test_fused_game_step_experiences():
+    """hironaka_b200.FusedGame.step against the reference composition (fused_game.py:54-102):
+    experiences of the games not already over, in order, with the pinned dtypes
+    (test/testTrainer.py:105-118).  Deterministic players: a scripted host and ChooseFirst."""
+    from hironaka_b200 import FusedGame, TensorPoints
+    from hironaka_b200.players import AllCoordHostModule, ChooseFirstAgentModule, ChooseLastAgentModule
+
+    class ScriptedHost(torch.nn.Module):
+        def __init__(self, ids):
+            super().__init__()
+            self.ids, self.k = ids, 0
+
+        def forward(self, x):
+            out = torch.nn.functional.one_hot(self.ids[self.k % len(self.ids)].long(), num_classes=4).float()
+            return out
+
+    rng = np.random.default_rng(12)
+    B, N, d = 300, 20, 3
+    dev = torch.device("cuda")
+    for sample_for, scale in (("host", True), ("agent", False)):
+        x = rng.integers(0, 21, (B, N, d)).astype(np.float32)
+        ids = [T(rng.integers(0, 4, B)) for _ in range(6)]
+        host = ScriptedHost(ids)
+        game = FusedGame(host, ChooseFirstAgentModule(d, N, dev), device=dev)
+        pts = TensorPoints(T(x))
+        pts.get_newton_polytope()
+        ref = O.get_newton_polytope_torch(x)
+        if scale:
+            pts.rescale()
+            ref = O.rescale_torch(ref)
+        for t in range(5):
+            host.k = t
+            obs, act, rew, done, nobs = game.step(pts, sample_for, scale_observation=scale, exploration_rate=0.0)
+            hid = ids[t].cpu().numpy()
+            coords = O.decode_table(3)[hid].astype(np.float32)
+            axis = coords.argmax(1)
+            keep = ~O.ended_batch(ref)
+            new = O.fused_game_point_ops(ref, coords, axis, scale)
+            nd = O.ended_batch(new)
+            assert rew.dtype == torch.float32 and done.dtype == torch.bool
+            assert eq(done, nd[keep][:, None]) and eq(rew, O.default_reward(sample_for, nd[keep])[:, None])
+            if sample_for == "host":
+                assert act.dtype == torch.int32 and eq(act, hid[keep][:, None])
+                assert eq(obs, O.get_features_torch(ref)[keep]) and eq(nobs, O.get_features_torch(new)[keep])
+            else:
+                assert eq(act, axis[keep][:, None]) and eq(obs["coords"], coords[keep])
+                assert eq(obs["points"], O.get_features_torch(ref)[keep])
+                assert eq(nobs["points"], O.get_features_torch(new)[keep])
+            assert eq(pts.points, new)
+            ref = new
+    # the parameter-free players (test/testTrainer.py:36-46)
+    ao = {"points": T(np.array([[[1, 0, 0]]], np.float32)), "coords": T(np.array([[1, 1, 0]], np.float32))}
+    assert eq(ChooseFirstAgentModule(3, 20, dev)(ao), [[1.0, 0.0, 0.0]])
+    assert eq(ChooseLastAgentModule(3, 20, dev)(ao), [[0.0, 1.0, 0.0]])
+    assert eq(AllCoordHostModule(3, 20, dev)(ao["points"]), [[0.0, 0.0, 0.0, 1.0]])
+
+
 # ---- functional JAX-style API (test/testJAX.py:80-153,205-219,461-488) ------------------------
 def test_functional_api():
     from hironaka_b200 import functional as F

@@ -103,9 +103,9 @@ int dispatch_small(const StepParams& p, int dev, cudaStream_t stream) {
 bool is_small(int N, int d) { return d == 3 && (N == 20 || N == 10 || N == 5); }
 
 // ---- generic (warp-per-game) family -------------------------------------------------------------
-template <typename T, int D, bool OBS>
-int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
-    auto kernel = hk::hk_generic_kernel<T, D, OBS>;
+template <typename T, int D, bool OBS, int RT>
+int launch_generic_rt(const StepParams& p, int dev, cudaStream_t stream) {
+    auto kernel = hk::hk_generic_kernel<T, D, OBS, RT>;
     const int W = p.N * D;
     const int Wpad = (W + 3) & ~3;
     const int R = (p.N + 31) / 32;
@@ -141,6 +141,16 @@ int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
     if (ctas > cap) ctas = cap;
     kernel<<<(unsigned)ctas, warps * 32, smem, stream>>>(p, warps, slot_words);
     return (int)cudaGetLastError();
+}
+
+// rows-per-lane specialisations exist for the common dimensions; everything else takes run-time loops
+template <typename T, int D, bool OBS>
+int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
+    if constexpr (D >= 2 && D <= 5) {
+        if (p.N <= 32) return launch_generic_rt<T, D, OBS, 1>(p, dev, stream);
+        if (p.N <= 64) return launch_generic_rt<T, D, OBS, 2>(p, dev, stream);
+    }
+    return launch_generic_rt<T, D, OBS, 0>(p, dev, stream);
 }
 
 template <typename T, bool OBS>

@@ -54,13 +54,16 @@ __device__ __forceinline__ int32_t dominance_word(const T (&xi)[D], const T* x, 
 }
 
 // smem per warp: two state buffers x[2][Wpad], then (OBS) f[Wpad] floats, then lmw[ceil(N/32)]
-template <typename T, int D, bool OBS>
+// RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
+// guards become predication) or 0 for any N (run-time loops).
+template <typename T, int D, bool OBS, int RT>
 __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
+    constexpr int UNR = RT > 0 ? RT : 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N;
     const int W = N * D;
-    const int R = (N + 31) >> 5;
+    const int R = RT > 0 ? RT : ((N + 31) >> 5);
     const int Wpad = (W + 3) & ~3;
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * slot_words;
     float* f = reinterpret_cast<float*>(slot + 2 * Wpad);
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         // ---- liveness ----
         uint32_t mylive = 0;  // bit r <=> row lane + 32 r is live
         int cnt = 0;
+        _Pragma("unroll UNR")
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
             bool lv = false;
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
                 if (p.flags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
                 if (apply) {
+                    _Pragma("unroll UNR")
                     for (int r = 0; r < R; ++r) {
                         if (!((mylive >> r) & 1u)) continue;
                         const int i = lane + 32 * r;
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 T mn[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) mn[k] = Elem<T>::big();
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
                     const int i = lane + 32 * r;
@@ -159,6 +165,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 }
 #pragma unroll
                 for (int k = 0; k < D; ++k) mn[k] = warp_min<T>(mn[k]);
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
                     const int i = lane + 32 * r;
@@ -170,6 +177,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             if ((p.ops & HK_OP_DEDUPE) && cnt >= 2) {
                 __syncwarp();
                 uint32_t kill = 0;
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
                     const int i = lane + 32 * r;
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             }
             // ---- newton: dedupe + dominance, reading the pre-removal state ----
             if ((p.ops & HK_OP_NEWTON) && cnt >= 2) {
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const uint32_t bal = __ballot_sync(0xffffffffu, (mylive >> r) & 1u);
                     if (lane == 0) lmw[r] = bal;
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                         a1[k] = l1 ? x[i1 * D + k] : Elem<T>::big();
                     }
                     int32_t acc0 = (int32_t)0x80000000, acc1 = (int32_t)0x80000000;
+                    _Pragma("unroll UNR")
                     for (int r2 = 0; r2 < R; ++r2) {
                         uint32_t m = lmw[r2];
                         while (m) {
@@ -224,6 +234,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     }
                     kill = ((acc0 >= 0) ? 1u : 0u) | ((acc1 >= 0) ? 2u : 0u);
                 } else {
+                    _Pragma("unroll UNR")
                     for (int r = 0; r < R; ++r) {
                         const int i = lane + 32 * r;
                         const bool lv = (mylive >> r) & 1u;
@@ -231,6 +242,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
 #pragma unroll
                         for (int k = 0; k < D; ++k) xi[k] = lv ? x[i * D + k] : Elem<T>::big();
                         int32_t acc = (int32_t)0x80000000;
+                        _Pragma("unroll UNR")
                         for (int r2 = 0; r2 < R; ++r2) {
                             uint32_t m = lmw[r2];
                             while (m) {
@@ -249,6 +261,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             if constexpr (Elem<T>::is_float) {
                 if (p.ops & HK_OP_RESCALE) {
                     float mx = -1.0f;
+                    _Pragma("unroll UNR")
                     for (int r = 0; r < R; ++r) {
                         if (!((mylive >> r) & 1u)) continue;
                         const int i = lane + 32 * r;
@@ -258,6 +271,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     mx = warp_maxf(mx);
                     if (mx == 0.0f) mx = 1.0f;
                     if (mx > 0.0f) {
+                        _Pragma("unroll UNR")
                         for (int r = 0; r < R; ++r) {
                             if (!((mylive >> r) & 1u)) continue;
                             const int i = lane + 32 * r;
@@ -269,6 +283,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             }
             // ---- per-step outputs ----
             cnt = 0;
+            _Pragma("unroll UNR")
             for (int r = 0; r < R; ++r) cnt += __popc(__ballot_sync(0xffffffffu, (mylive >> r) & 1u));
             const bool dn = cnt < 2;
             if (lane == 0) {
@@ -286,6 +301,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         }
         // ---- outputs ----
         bool exceed = false;
+        _Pragma("unroll UNR")
         for (int r = 0; r < R; ++r) {
             const int i = lane + 32 * r;
             const bool lv = (mylive >> r) & 1u;
@@ -323,6 +339,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         if constexpr (OBS) {
             if (p.obs) {
                 float mx = -1.0f;
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
                     const int i = lane + 32 * r;
@@ -332,6 +349,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 mx = warp_maxf(mx);
                 if (mx == 0.0f) mx = 1.0f;
                 const bool resc = (p.flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
                     if (i >= N) continue;
@@ -347,6 +365,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 float* gobs = p.obs + g * (long long)OW;
                 const bool sorted = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX);
                 const bool lex = p.flags & HK_F_OBS_SORT_LEX;
+                _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
                     if (i >= N) continue;

@@ -29,6 +29,10 @@ HK_F_OBS_RESCALE = 1 << 4
 HK_F_OBS_SORT_COORD0 = 1 << 5
 HK_F_OBS_SORT_LEX = 1 << 6
 HK_F_ACT_U8 = 1 << 7
+HK_F_HOST_ALL_COORD = 1 << 8
+HK_F_HOST_ZEILLINGER = 1 << 9
+HK_F_AGENT_FIRST = 1 << 10
+HK_F_AGENT_LAST = 1 << 11
 
 # the two semantics of the reference
 TORCH_SEMANTICS = HK_F_NOOP_INVALID | HK_F_FREEZE_ENDED  # hironaka/src/_torch_ops.py:90-93

@@ -183,7 +183,16 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     if (p.B == 0) return HK_OK;  // empty batch: nothing to do (an empty tensor has a null data pointer)
     if (p.in == nullptr) return HK_ERR_BAD_ARG;
     if ((((uintptr_t)p.in) & 3u) || (((uintptr_t)p.out) & 3u)) return HK_ERR_ALIGN;
-    if ((p.ops & HK_OP_SHIFT) && (p.host_action == nullptr || p.axis == nullptr)) return HK_ERR_BAD_ARG;
+    {
+        const bool host_fixed = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER);
+        const bool agent_fixed = p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
+        if ((p.flags & HK_F_HOST_ALL_COORD) && (p.flags & HK_F_HOST_ZEILLINGER)) return HK_ERR_BAD_ARG;
+        if ((p.flags & HK_F_AGENT_FIRST) && (p.flags & HK_F_AGENT_LAST)) return HK_ERR_BAD_ARG;
+        if (host_fixed) p.host_action = nullptr;
+        if (agent_fixed) p.axis = nullptr;
+        if ((p.ops & HK_OP_SHIFT) && ((!host_fixed && p.host_action == nullptr) || (!agent_fixed && p.axis == nullptr)))
+            return HK_ERR_BAD_ARG;
+    }
     if ((p.ops & HK_OP_RESCALE) && dtype != HK_DTYPE_F32) return HK_ERR_UNSUPPORTED;
     if (p.ops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON | HK_OP_RESCALE | HK_OP_DEDUPE)) return HK_ERR_BAD_ARG;
     if ((p.flags & HK_F_OBS_SORT_COORD0) && (p.flags & HK_F_OBS_SORT_LEX)) return HK_ERR_BAD_ARG;
@@ -444,16 +453,15 @@ int hk_session_get_state(hk_session* s, void* state_host) {
 int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_t* axis_host, uint8_t* done_host,
                     float* reward_host, int32_t* done_count_host, uint32_t ops, uint32_t flags) {
     if (!s) return HK_ERR_BAD_ARG;
-    if ((ops & HK_OP_SHIFT) && (!host_action_host || !axis_host)) return HK_ERR_BAD_ARG;
     HK_CUDA(cudaSetDevice(s->device));
     const size_t abytes = (size_t)s->B * ((flags & HK_F_ACT_U8) ? 1 : 4);
-    if (ops & HK_OP_SHIFT) {
+    if ((ops & HK_OP_SHIFT) && host_action_host)
         HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, abytes, cudaMemcpyHostToDevice, s->stream));
+    if ((ops & HK_OP_SHIFT) && axis_host)
         HK_CUDA(cudaMemcpyAsync(s->axis, axis_host, abytes, cudaMemcpyHostToDevice, s->stream));
-    }
     StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
-    p.host_action = s->host_action;
-    p.axis = s->axis;
+    p.host_action = host_action_host ? s->host_action : nullptr;
+    p.axis = axis_host ? s->axis : nullptr;
     p.done = done_host ? s->done : nullptr;
     p.reward = reward_host ? s->reward : nullptr;
     p.ops = ops;

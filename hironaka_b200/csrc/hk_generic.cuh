@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
         int32_t ha = 3, ax = 0;
         if (p.ops & HK_OP_SHIFT) {
-            ha = load_action(p.host_action, g, p.flags);
-            ax = load_action(p.axis, g, p.flags);
+            if (p.host_action) ha = load_action(p.host_action, g, p.flags);
+            if (p.axis) ax = load_action(p.axis, g, p.flags);
         }
         cp_async_wait<1>();  // everything but the newest group has landed: game g is in buffer b
         __syncwarp();
@@ -125,14 +125,75 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         for (int st = 0; st < p.T; ++st) {
             int32_t ha_n = 3, ax_n = 0;
             if ((p.ops & HK_OP_SHIFT) && st + 1 < p.T) {
-                ha_n = load_action(p.host_action, (long long)(st + 1) * p.B + g, p.flags);
-                ax_n = load_action(p.axis, (long long)(st + 1) * p.B + g, p.flags);
+                if (p.host_action) ha_n = load_action(p.host_action, (long long)(st + 1) * p.B + g, p.flags);
+                if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * p.B + g, p.flags);
             }
             const bool prev_done = cnt < 2;
 
             // ---- shift ----
             if ((p.ops & HK_OP_SHIFT) && cnt > 0) {
-                const uint32_t cm = action_mask(ha, p.flags);
+                uint32_t cm;
+                if (p.flags & HK_F_HOST_ALL_COORD) {
+                    cm = (1u << D) - 1u;
+                } else if (p.flags & HK_F_HOST_ZEILLINGER) {
+                    // Zeillinger's host, lane-parallel: every lane scans the pairs (i, j) of its own rows i,
+                    // then a lexicographic (L, S, flat index) minimum is reduced over the warp
+                    _Pragma("unroll UNR")
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t bal = __ballot_sync(0xffffffffu, (mylive >> r) & 1u);
+                        if (lane == 0) lmw[r] = bal;
+                    }
+                    __syncwarp();
+                    ZeilBest zb;
+                    zb.L = __int_as_float(0x7f800000);
+                    zb.S = zb.L;
+                    zb.i = -1;
+                    zb.j = -1;
+                    _Pragma("unroll UNR")
+                    for (int r = 0; r < R; ++r) {
+                        if (!((mylive >> r) & 1u)) continue;
+                        const int i = lane + 32 * r;
+                        float vi[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) vi[k] = Elem<T>::to_float(x[i * D + k]);
+                        for (int r2 = 0; r2 < R; ++r2) {
+                            uint32_t m = lmw[r2];
+                            while (m) {
+                                const int j = 32 * r2 + __ffs((int)m) - 1;
+                                m &= m - 1;
+                                float vj[D];
+#pragma unroll
+                                for (int k = 0; k < D; ++k) vj[k] = Elem<T>::to_float(x[j * D + k]);
+                                zeillinger_consider<D>(zb, vi, vj, i, j);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float L2 = __shfl_xor_sync(0xffffffffu, zb.L, o);
+                        const float S2 = __shfl_xor_sync(0xffffffffu, zb.S, o);
+                        const int i2 = __shfl_xor_sync(0xffffffffu, zb.i, o);
+                        const int j2 = __shfl_xor_sync(0xffffffffu, zb.j, o);
+                        const long long f1 = (long long)zb.i * N + zb.j, f2 = (long long)i2 * N + j2;
+                        const bool take = (i2 >= 0) && ((zb.i < 0) || (L2 < zb.L) || (L2 == zb.L && (S2 < zb.S || (S2 == zb.S && f2 < f1))));
+                        zb.L = take ? L2 : zb.L;
+                        zb.S = take ? S2 : zb.S;
+                        zb.i = take ? i2 : zb.i;
+                        zb.j = take ? j2 : zb.j;
+                    }
+                    const bool found = zb.i >= 0;
+                    float vi[D], vj[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        vi[k] = found ? Elem<T>::to_float(x[zb.i * D + k]) : 0.0f;
+                        vj[k] = found ? Elem<T>::to_float(x[zb.j * D + k]) : 0.0f;
+                    }
+                    cm = zeillinger_mask_from_diff<D>(vi, vj, found);
+                    __syncwarp();
+                } else {
+                    cm = action_mask(ha, p.flags);
+                }
+                ax = agent_policy_axis(cm, ax, p.flags, D);
                 bool apply = (ax >= 0) && (ax < D);
                 if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
                 if (p.flags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;

@@ -232,11 +232,58 @@ __device__ __forceinline__ bool exceeds(const T (&x)[N * D], uint32_t lm, float 
 }
 
 // One full step of one game in registers.  Returns the new live mask; x holds garbage in dead rows.
+// Zeillinger's host on K register rows, thread-per-game: the rows go to the lane's shared-memory
+// scratch (stride ZS words) and an (i, j) double loop walks them in flat order.
+template <typename T, int K, int D, int ZS>
+__device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_t clm, uint32_t* scratch) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) scratch[k * ZS + c] = __float_as_uint(Elem<T>::to_float(y[k * D + c]));
+    }
+    ZeilBest b;
+    b.L = __int_as_float(0x7f800000);
+    b.S = b.L;
+    b.i = -1;
+    b.j = -1;
+#pragma unroll 1
+    for (int i = 0; i < K; ++i) {
+        if (!((clm >> i) & 1u)) continue;
+        float vi[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) vi[c] = __uint_as_float(scratch[i * ZS + c]);
+#pragma unroll 1
+        for (int j = 0; j < K; ++j) {
+            if (!((clm >> j) & 1u)) continue;
+            float vj[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) vj[c] = __uint_as_float(scratch[j * ZS + c]);
+            zeillinger_consider<D>(b, vi, vj, i, j);
+        }
+    }
+    const bool found = b.i >= 0;
+    float vi[D], vj[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        vi[c] = found ? __uint_as_float(scratch[b.i * ZS + c]) : 0.0f;
+        vj[c] = found ? __uint_as_float(scratch[b.j * ZS + c]) : 0.0f;
+    }
+    return zeillinger_mask_from_diff<D>(vi, vj, found);
+}
+
 template <typename T, int N, int D, int RS = 0>
 __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
-                                              int32_t ax, uint32_t* scratch = nullptr) {
+                                              int32_t ax_in, uint32_t* scratch = nullptr) {
     if (ops & HK_OP_SHIFT) {
-        const uint32_t cm = action_mask(ha, flags);
+        uint32_t cm;
+        if (flags & HK_F_HOST_ALL_COORD) {
+            cm = (1u << D) - 1u;
+        } else if (flags & HK_F_HOST_ZEILLINGER) {
+            cm = zeillinger_rows<T, N, D, D>(x, lm, scratch);
+        } else {
+            cm = action_mask(ha, flags);
+        }
+        const int ax = agent_policy_axis(cm, ax_in, flags, D);
         bool apply = (ax >= 0) && (ax < D);
         if (flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
         if (flags & HK_F_FREEZE_ENDED) apply = apply && (__popc(lm) >= 2);
@@ -382,8 +429,8 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
     for (; st < p.T;) {
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
-            ha_n = load_action(p.host_action, (long long)(st + 1) * B + ls.g, p.flags);
-            ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
+            if (p.host_action) ha_n = load_action(p.host_action, (long long)(st + 1) * B + ls.g, p.flags);
+            if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
         }
         const bool prev_done = ls.cnt < 2;
         clm = game_step<T, K, D, RS>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
@@ -419,10 +466,15 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             }
             store_game<T, N * D>(row, y);
         } else {
-            if constexpr (ROLLED) {  // the scratch overwrote the game area: all padding, then the survivors
+            if (ROLLED || (p.flags & HK_F_HOST_ZEILLINGER)) {  // the scratch overwrote the game area: all padding, then the survivors
                 const uint32_t pw = (uint32_t)Elem<T>::bits(padv);
+                if constexpr ((N * D) % 4 == 0) {
 #pragma unroll
-                for (int q = 0; q < (N * D) / 4; ++q) reinterpret_cast<uint4*>(row)[q] = make_uint4(pw, pw, pw, pw);
+                    for (int q = 0; q < (N * D) / 4; ++q) reinterpret_cast<uint4*>(row)[q] = make_uint4(pw, pw, pw, pw);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < N * D; ++q) row[q] = pw;
+                }
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -519,8 +571,8 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         ls.ha = 3;
         ls.ax = 0;
         if (ls.shift) {
-            ls.ha = load_action(p.host_action, ls.g, p.flags);
-            ls.ax = load_action(p.axis, ls.g, p.flags);
+            if (p.host_action) ls.ha = load_action(p.host_action, ls.g, p.flags);
+            if (p.axis) ls.ax = load_action(p.axis, ls.g, p.flags);
         }
 
         if (tma) {

@@ -57,8 +57,12 @@ class GameBatch:
                      (FusedGame.agent_move, hironaka/trainer/fused_game.py:150-162)
     """
 
+    HOST_POLICIES = {None: 0, "stream": 0, "all_coord": C.HK_F_HOST_ALL_COORD, "zeillinger": C.HK_F_HOST_ZEILLINGER}
+    AGENT_POLICIES = {None: 0, "stream": 0, "choose_first": C.HK_F_AGENT_FIRST, "choose_last": C.HK_F_AGENT_LAST}
+
     def __init__(self, points: torch.Tensor, *, semantics: str = "jax", reposition: bool = True,
-                 discrete_host_action: bool = True, role: str = "host", initial_filter: bool = False):
+                 discrete_host_action: bool = True, role: str = "host", initial_filter: bool = False,
+                 host_policy: Optional[str] = None, agent_policy: Optional[str] = None):
         if semantics not in ("jax", "torch"):
             raise ValueError("semantics must be 'jax' or 'torch'")
         if not points.is_cuda:
@@ -68,8 +72,10 @@ class GameBatch:
         self.points = points.contiguous()
         self.B, self.N, self.d = self.points.shape
         self.ops = C.HK_OP_SHIFT | C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0)
+        # fixed players evaluated in the kernel (hironaka/jax/players.py): their action array is not needed
         self.flags = (C.TORCH_SEMANTICS if semantics == "torch" else C.JAX_SEMANTICS) | \
-            (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0)
+            (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
+            self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]
         self.reposition = reposition
         if initial_filter:  # generate_pts: newton -> (reposition) on the root states (util.py:385-392)
             _ops.step(self.points, ops=C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0), inplace=True)
@@ -78,19 +84,21 @@ class GameBatch:
     def device(self):
         return self.points.device
 
-    def step(self, host_action: torch.Tensor, axis: torch.Tensor, want_reward: bool = True):
+    def step(self, host_action: Optional[torch.Tensor] = None, axis: Optional[torch.Tensor] = None,
+             want_reward: bool = True):
         """One game-step in place; returns (done [B] bool, reward [B] f32 | None)."""
         r = _ops.step(self.points, host_action, axis, ops=self.ops, flags=self.flags, inplace=True, want_done=True,
                       want_reward=want_reward)
         return r.done, r.reward
 
-    def rollout(self, host_actions: torch.Tensor, axes: torch.Tensor, want_done: bool = False,
-                want_reward: bool = False, want_length: bool = True):
+    def rollout(self, host_actions: Optional[torch.Tensor] = None, axes: Optional[torch.Tensor] = None,
+                want_done: bool = False, want_reward: bool = False, want_length: bool = True,
+                steps: Optional[int] = None):
         """T game-steps in ONE launch, state on chip in between.  Returns
         (done [T,B] | None, reward [T,B] | None, done_count [T] int32, length [B] int32 | None)."""
         _, done, reward, dcount, length = _ops.rollout(self.points, host_actions, axes, ops=self.ops, flags=self.flags,
                                                        inplace=True, want_done=want_done, want_reward=want_reward,
-                                                       want_done_count=True, want_length=want_length)
+                                                       want_done_count=True, want_length=want_length, steps=steps)
         return done, reward, dcount, length
 
     def step_host(self, host_action_host: torch.Tensor, axis_host: torch.Tensor) -> int:

@@ -101,10 +101,12 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
         dst = None
     ha = ax = None
     if ops & C.HK_OP_SHIFT:
-        if host_action is None or axis is None:
-            raise ValueError("shift needs host_action and axis")
-        ha = _as_i32(host_action, B, dev, "host_action")
-        ax = _as_i32(axis, B, dev, "axis")
+        host_fixed = flags & (C.HK_F_HOST_ALL_COORD | C.HK_F_HOST_ZEILLINGER)
+        agent_fixed = flags & (C.HK_F_AGENT_FIRST | C.HK_F_AGENT_LAST)
+        if (host_action is None and not host_fixed) or (axis is None and not agent_fixed):
+            raise ValueError("shift needs host_action and axis (or a fixed-player flag for the missing one)")
+        ha = None if host_fixed else _as_i32(host_action, B, dev, "host_action")
+        ax = None if agent_fixed else _as_i32(axis, B, dev, "axis")
     done = torch.empty(B, dtype=torch.uint8, device=dev) if want_done else None
     reward = torch.empty(B, dtype=torch.float32, device=dev) if want_reward else None
     npts = torch.empty(B, dtype=torch.int32, device=dev) if want_num_points else None
@@ -125,18 +127,31 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
     return StepResult(dst, None if done is None else done.view(torch.bool), reward, npts, obs)
 
 
-def rollout(state: torch.Tensor, host_actions: torch.Tensor, axes: torch.Tensor, *, ops: int, flags: int = 0,
-            padding_value: float = -1.0, inplace: bool = True, want_done: bool = False, want_reward: bool = False,
-            want_done_count: bool = True, want_length: bool = False):
-    """T fused steps in one launch (hk_rollout): host_actions / axes are int32 [T, B]."""
+def rollout(state: torch.Tensor, host_actions: Optional[torch.Tensor], axes: Optional[torch.Tensor], *, ops: int,
+            flags: int = 0, padding_value: float = -1.0, inplace: bool = True, want_done: bool = False,
+            want_reward: bool = False, want_done_count: bool = True, want_length: bool = False,
+            steps: Optional[int] = None):
+    """T fused steps in one launch (hk_rollout): host_actions / axes are int32 [T, B]; either may be
+    None when the matching fixed-player flag (HK_F_HOST_* / HK_F_AGENT_*) is set, in which case
+    `steps` gives T if both are None."""
     dt = _require_state(state)
     B, N, d = state.shape
     dev = state.device
-    if host_actions.dim() != 2 or host_actions.shape[1] != B or axes.shape != host_actions.shape:
-        raise ValueError("host_actions and axes must be [T, B]")
-    T = host_actions.shape[0]
-    ha = host_actions.to(device=dev, dtype=torch.int32).contiguous()
-    ax = axes.to(device=dev, dtype=torch.int32).contiguous()
+    host_fixed = flags & (C.HK_F_HOST_ALL_COORD | C.HK_F_HOST_ZEILLINGER)
+    agent_fixed = flags & (C.HK_F_AGENT_FIRST | C.HK_F_AGENT_LAST)
+    if (host_actions is None and not host_fixed) or (axes is None and not agent_fixed):
+        raise ValueError("rollout needs host_actions and axes (or a fixed-player flag for the missing one)")
+    shapes = [t.shape for t in (None if host_fixed else host_actions, None if agent_fixed else axes) if t is not None]
+    if shapes:
+        if any(len(sh) != 2 or sh[1] != B for sh in shapes) or len(set(shapes)) != 1:
+            raise ValueError("host_actions and axes must be [T, B]")
+        T = shapes[0][0]
+    else:
+        if not steps:
+            raise ValueError("steps is required when both players are fixed")
+        T = int(steps)
+    ha = None if host_fixed else host_actions.to(device=dev, dtype=torch.int32).contiguous()
+    ax = None if agent_fixed else axes.to(device=dev, dtype=torch.int32).contiguous()
     dst = state if inplace else torch.empty_like(state)
     done = torch.empty((T, B), dtype=torch.uint8, device=dev) if want_done else None
     reward = torch.empty((T, B), dtype=torch.float32, device=dev) if want_reward else None

@@ -73,6 +73,14 @@ extern "C" {
 #define HK_F_ACT_U8 (1u << 7)         /* host_action[] / axis[] / obs_coord[] are uint8 arrays instead of int32 (ids < 256, i.e.
                                          discrete ids up to d = 8 or bitmasks up to d = 8): 2 instead of 8 action bytes per game-step */
 
+/* Fixed players evaluated inside the kernel (zero host round-trips in validation rollouts).  With a
+ * host flag set host_action may be NULL, with an agent flag set axis may be NULL. */
+#define HK_F_HOST_ALL_COORD (1u << 8)  /* host picks every coordinate (all_coord_host_fn, hironaka/jax/players.py:42-52;
+                                          AllCoordHostModule, trainer/player_modules/modules.py:68-79) */
+#define HK_F_HOST_ZEILLINGER (1u << 9) /* Zeillinger's host (zeillinger_fn, players.py:55-105) on the state before the step */
+#define HK_F_AGENT_FIRST (1u << 10)    /* agent picks the first chosen coordinate (choose_first_agent_fn, players.py:156-183) */
+#define HK_F_AGENT_LAST (1u << 11)     /* agent picks the last chosen coordinate (choose_last_agent_fn, players.py:186-212) */
+
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
 const char* hk_error_string(int code);

@@ -88,6 +88,48 @@ static void parallel_for(int64_t B, range_fn fn, void* ctx) {
         if (th[t]) pthread_join(th[t], 0);
 }
 
+#include <math.h>
+/* Zeillinger's host (zeillinger_fn_slice hironaka/jax/players.py:55-105) on one game, float32 */
+static uint32_t oracle_zeillinger(const float* pts, int N, int d) {
+    float bestL = INFINITY, bestS = INFINITY;
+    int bi = -1, bj = -1;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            int neg = 0;
+            for (int k = 0; k < d; ++k) neg |= (pts[i * d + k] < 0) || (pts[j * d + k] < 0);
+            if (neg) continue;
+            float mx = pts[i * d] - pts[j * d], mn = mx;
+            for (int k = 1; k < d; ++k) {
+                float df = pts[i * d + k] - pts[j * d + k];
+                if (df > mx) mx = df;
+                if (df < mn) mn = df;
+            }
+            if (fabsf(mx - mn) <= 1e-8f + 1e-5f * fabsf(mn)) continue; /* jnp.isclose(maximal, minimal) */
+            int cmax = 0, cmin = 0;
+            for (int k = 0; k < d; ++k) {
+                float df = pts[i * d + k] - pts[j * d + k];
+                cmax += df == mx;
+                cmin += df == mn;
+            }
+            float L = mx - mn, S = (float)(mx == mn ? cmax : cmax + cmin);
+            if (L < bestL || (L == bestL && S < bestS)) { /* lexsort is stable: first in flat order wins ties */
+                bestL = L;
+                bestS = S;
+                bi = i;
+                bj = j;
+            }
+        }
+    if (bi < 0) return 3u; /* every pair is (inf, inf): index 0 = pair (0,0), constant difference -> action 0 = {0,1} */
+    int amin = 0, amax = 0;
+    float mn = pts[bi * d] - pts[bj * d], mx = mn;
+    for (int k = 1; k < d; ++k) {
+        float df = pts[bi * d + k] - pts[bj * d + k];
+        if (df < mn) { mn = df; amin = k; }
+        if (df > mx) { mx = df; amax = k; }
+    }
+    return amin == amax ? 3u : ((1u << amin) | (1u << amax));
+}
+
 #define NO_RESCALE(x, N, d, pad) (void)0
 #define F32_RESCALE(x, N, d, pad)                                                                       \
     do { /* rescale_torch hironaka/src/_torch_ops.py:136-146 */                                         \
@@ -110,6 +152,16 @@ static void parallel_for(int64_t B, range_fn fn, void* ctx) {
         }                                                                                               \
         int prev_done = live_before < 2; /* get_dones, hironaka/jax/util.py:34-35 */                   \
         if (ops & HK_OP_SHIFT) {                                                                        \
+            /* fixed players: all_coord_host_fn / zeillinger_fn / choose_first|last_agent_fn            \
+               (hironaka/jax/players.py:42-52,55-105,156-212) */                                        \
+            if (flags & HK_F_HOST_ALL_COORD) cmask = (1u << d) - 1u;                                    \
+            else if (flags & HK_F_HOST_ZEILLINGER) {                                                    \
+                float zf[ORACLE_MAX_WORDS];                                                             \
+                for (int t = 0; t < N * d; ++t) zf[t] = (float)x[t];                                    \
+                cmask = oracle_zeillinger(zf, N, d);                                                    \
+            }                                                                                           \
+            if (flags & HK_F_AGENT_FIRST) { a = 0; while (a < d - 1 && !((cmask >> a) & 1u)) ++a; if (!cmask) a = 0; } \
+            else if (flags & HK_F_AGENT_LAST) { a = d - 1; while (a > 0 && !((cmask >> a) & 1u)) --a; if (!cmask) a = d - 1; } \
             /* shift_torch hironaka/src/_torch_ops.py:46-110; shift_jax _jax_ops.py:76-90 */           \
             int apply = 1;                                                                              \
             if ((flags & HK_F_NOOP_INVALID) && !((cmask >> a) & 1u)) apply = 0;   /* :90-91 */          \
@@ -227,9 +279,10 @@ static void parallel_for(int64_t B, range_fn fn, void* ctx) {
             uint32_t cm = 0;                                                                            \
             int32_t a = 0;                                                                              \
             if (c->ops & HK_OP_SHIFT) {                                                                 \
-                cm = (c->flags & HK_F_ACT_DISCRETE) ? oracle_decode(c->host_action[b])                  \
-                                                    : (uint32_t)c->host_action[b];                      \
-                a = c->axis[b];                                                                         \
+                if (c->host_action)                                                                     \
+                    cm = (c->flags & HK_F_ACT_DISCRETE) ? oracle_decode(c->host_action[b])              \
+                                                        : (uint32_t)c->host_action[b];                  \
+                if (c->axis) a = c->axis[b];                                                            \
             }                                                                                           \
             NAME##_one(c->state_in + b * N * d, x, cm, a, N, d, c->ops, c->flags, c->pad,               \
                        c->done ? c->done + b : 0, c->reward ? c->reward + b : 0,                        \

@@ -244,6 +244,62 @@ def test_random_features(hb, family, shape, dtype):
     assert np.array_equal(got[4], cport.features(exp_state, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE))
 
 
+F_ALL, F_ZEIL, F_FIRST, F_LAST = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+
+
+@pytest.mark.parametrize("shape", [(300, 20, 3), (200, 10, 3), (100, 5, 3), (64, 16, 4), (40, 64, 5), (30, 40, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_fixed_players(hb, family, shape, dtype):
+    """Hosts all_coord / Zeillinger and agents choose_first / choose_last evaluated in the kernel
+    (hironaka/jax/players.py:42-105,156-212) against the C port, step by step and as one launch."""
+    from hironaka_b200 import ops
+    B, N, d = shape
+    rng = np.random.default_rng(N + d)
+    x0 = random_state(rng, B, N, d, 12, dead_frac=0.3, dup_frac=0.1).astype(dtype)
+    ncls = 2 ** d - d - 1
+    op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    for pol in (F_ALL | F_FIRST, F_ALL | F_LAST, F_ZEIL | F_FIRST, F_ZEIL | F_LAST, F_ZEIL, F_FIRST, F_LAST):
+        Tn = 5
+        ha = rng.integers(0, ncls, (Tn, B)).astype(np.int32)
+        ax = rng.integers(0, d, (Tn, B)).astype(np.int32)
+        host_fixed, agent_fixed = pol & (F_ALL | F_ZEIL), pol & (F_FIRST | F_LAST)
+        flags = pol | O.F_ACT_DISCRETE
+        o, g = x0, dev(x0)
+        counts = []
+        for t in range(Tn):
+            o, od, orw, onp = cport.step(o, None if host_fixed else ha[t], None if agent_fixed else ax[t], op_bits, flags)
+            r = ops.step(g, None if host_fixed else dev(ha[t]), None if agent_fixed else dev(ax[t]), ops=op_bits,
+                         flags=flags, inplace=True, want_done=True, want_reward=True)
+            assert np.array_equal(g.cpu().numpy(), o), (pol, t)
+            assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)) and np.array_equal(r.reward.cpu().numpy(), orw)
+            counts.append(int(od.sum()))
+        out, _, _, dcount, _ = ops.rollout(dev(x0), None if host_fixed else dev(ha), None if agent_fixed else dev(ax),
+                                           ops=op_bits, flags=flags, inplace=False, steps=Tn)
+        assert np.array_equal(out.cpu().numpy(), o) and dcount.tolist() == counts, pol
+
+
+def test_zeillinger_kat(hb, family):
+    """Zeillinger known answers of test/testJAX.py:232-268 through a kernel step: the chosen
+    coordinates are read off the shifted point (x_a <- sum over the chosen set, agent = first)."""
+    from hironaka_b200 import ops
+    def chosen_mask(pts):
+        p = pts.astype(np.float32)[None]
+        got = ops.step(dev(p), ops=O.OP_SHIFT, flags=F_ZEIL | F_FIRST, inplace=False).state.cpu().numpy()[0]
+        exp_oh = O.zeillinger_fn_slice(pts.astype(np.float32))
+        mb = O.decode_table(pts.shape[1])[int(exp_oh.argmax())]
+        a = int(np.argmax(mb))
+        ref = pts.astype(np.float32).copy()
+        live = ref[:, 0] >= 0
+        ref[live, a] = (ref[live] * mb[None]).sum(1)
+        assert np.array_equal(got, ref)
+        return mb
+    assert chosen_mask(K.ZEIL_PTS).tolist() == [1, 0, 1]                      # one-hot [0,1,0,0] = id 1 = {0,2}
+    for pts, mb in zip(K.ZEIL_OBS2, K.ZEIL_OBS2_MB):
+        assert chosen_mask(pts).tolist() == mb.tolist()
+    assert chosen_mask(K.ZEIL_PTS3[0]).tolist() == [1, 0, 1]
+
+
 def test_float_state_rescaled_rollout(hb, family):
     """DQN path with scale_observation: float state divided by its max every step
     (fused_game.py:160-162).  Values are non-integers; parity is exact because the kernel keeps

@@ -30,13 +30,16 @@ def __getattr__(name):  # lazy: importing the package must not require torch or 
     if name == "HostSession":
         from .session import HostSession
         return HostSession
+    if name == "ReplayBuffer":
+        from .replay_buffer import ReplayBuffer
+        return ReplayBuffer
     if name == "FusedGame":
         from .fused_game import FusedGame
         return FusedGame
     if name == "HostActionEncoder":
         from .host_action import HostActionEncoder
         return HostActionEncoder
-    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build", "fused_game", "players"):
+    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build", "fused_game", "players", "replay_buffer"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 
+#include "hk_experience.cuh"
 #include "hk_generic.cuh"
 #include "hk_small.cuh"
 
@@ -344,6 +345,56 @@ int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action
     p.ops = ops;
     p.flags = flags;
     return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int64_t hk_experience_scratch_words(int64_t B) {
+    if (B < 0) return 0;
+    return (B + hk::EXP_ROWS_PER_BLOCK - 1) / hk::EXP_ROWS_PER_BLOCK + 4;
+}
+
+int hk_experience_append(const uint8_t* skip, const float* obs, const float* next_obs, int32_t obs_width,
+                         const float* coords, const float* next_coords, int32_t coord_width, const int32_t* action,
+                         const float* reward, const uint8_t* done, float* buf_obs, float* buf_next_obs,
+                         float* buf_coords, float* buf_next_coords, int32_t* buf_action, float* buf_reward,
+                         uint8_t* buf_done, int64_t capacity, int64_t* pos, int32_t* full, int32_t* appended,
+                         int32_t* scratch, int64_t B, void* stream) {
+    if (B < 0 || capacity < 1 || !skip || !pos || !full || !scratch) return HK_ERR_BAD_ARG;
+    if ((buf_obs && (!obs || obs_width < 1)) || (buf_next_obs && (!next_obs || obs_width < 1))) return HK_ERR_BAD_ARG;
+    if ((buf_coords && (!coords || coord_width < 1)) || (buf_next_coords && (!next_coords || coord_width < 1)))
+        return HK_ERR_BAD_ARG;
+    if ((buf_action && !action) || (buf_reward && !reward) || (buf_done && !done)) return HK_ERR_BAD_ARG;
+    if (B == 0) return HK_OK;
+    hk::ExpParams p;
+    memset(&p, 0, sizeof(p));
+    p.skip = skip;
+    p.obs = obs;
+    p.next_obs = next_obs;
+    p.coords = coords;
+    p.next_coords = next_coords;
+    p.action = action;
+    p.reward = reward;
+    p.done = done;
+    p.buf_obs = buf_obs;
+    p.buf_next_obs = buf_next_obs;
+    p.buf_coords = buf_coords;
+    p.buf_next_coords = buf_next_coords;
+    p.buf_action = buf_action;
+    p.buf_reward = buf_reward;
+    p.buf_done = buf_done;
+    p.capacity = capacity;
+    p.pos = (long long*)pos;
+    p.full = full;
+    p.appended = appended;
+    p.scratch = scratch;
+    p.B = B;
+    p.ow = obs_width;
+    p.cw = coord_width;
+    p.nblocks = (int)((B + hk::EXP_ROWS_PER_BLOCK - 1) / hk::EXP_ROWS_PER_BLOCK);
+    cudaStream_t st = (cudaStream_t)stream;
+    hk::hk_exp_count_kernel<<<p.nblocks, hk::EXP_THREADS, 0, st>>>(p);
+    hk::hk_exp_scan_kernel<<<1, 1024, 0, st>>>(p);
+    hk::hk_exp_scatter_kernel<<<p.nblocks, hk::EXP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
 }
 
 // ---- host-buffer sessions ----------------------------------------------------------------------

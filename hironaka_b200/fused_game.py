@@ -72,6 +72,30 @@ class FusedGame:
                 self._rewards(sample_for, output_obs, next_observations, next_done).reshape(-1, 1),
                 next_done.reshape(-1, 1), next_observations)
 
+    def step_into(self, buffer, points: TensorPoints, sample_for: str, masked=True, scale_observation=True,
+                  exploration_rate=0.2) -> None:
+        """``step`` followed by ``ReplayBuffer.add`` with NO host round-trip: the `[~done]` filter of
+        the reference (a sync per masked tensor, fused_game.py:82-94) becomes an order-preserving
+        device-side compaction straight into the circular buffer (ReplayBuffer.add_masked)."""
+        assert sample_for in ["host", "agent"]
+        if points.dtype != self.dtype:
+            points.type(self.dtype)
+        observations = points.get_features()
+        done = points.ended_batch_in_tensor
+        host_move, chosen_actions = self.host_move(points, exploration_rate=exploration_rate if sample_for == "host" else 0.0)
+        agent_move = self.agent_move(points, host_move, masked=masked, scale_observation=scale_observation, inplace=True,
+                                     exploration_rate=exploration_rate if sample_for == "agent" else 0.0)
+        next_done = points.ended_batch_in_tensor
+        next_observations = points.get_features()
+        sign = 1.0 if sample_for == "host" else -1.0
+        reward = next_done.to(torch.float32) * sign  # _default_reward (fused_game.py:175-182)
+        if sample_for == "host":
+            buffer.add_masked(done, observations, chosen_actions, reward, next_done, next_observations)
+        else:
+            next_host_move, _ = self.host_move(points, exploration_rate=exploration_rate)
+            buffer.add_masked(done, {"points": observations, "coords": host_move}, agent_move, reward, next_done,
+                              {"points": next_observations, "coords": next_host_move})
+
     def host_move(self, points: TensorPoints, masked=True, exploration_rate=0.0) -> Tuple[torch.Tensor, torch.Tensor]:
         """Host net -> argmax (or noise) -> multi-binary host move (fused_game.py:104-122)."""
         with torch.inference_mode():

@@ -145,6 +145,23 @@ int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action
                int32_t N, int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags,
                float padding_value, void* stream);
 
+/* ---- experience writer --------------------------------------------------------
+ * Appends the rows with skip[b] == 0, IN BATCH ORDER, to circular replay buffers at
+ * (pos + rank) mod capacity and advances the DEVICE-resident pos / full — the no-sync form of
+ * FusedGame.step's `[~done]` filtering (hironaka/trainer/fused_game.py:82-99) followed by
+ * ReplayBuffer.add (hironaka/trainer/replay_buffer.py:63-127).  Any source/buffer pair may be NULL.
+ *   obs/next_obs [B, obs_width] float, coords/next_coords [B, coord_width] float (agent dict obs),
+ *   action [B] int32, reward [B] float, done [B] uint8; buffers have `capacity` rows of the same widths;
+ *   pos [1] int64 and full [1] int32 live on the device; appended [1] int32 (nullable) gets the count;
+ *   scratch: hk_experience_scratch_words(B) int32 words of device memory owned by the caller. */
+int64_t hk_experience_scratch_words(int64_t B);
+int hk_experience_append(const uint8_t* skip, const float* obs, const float* next_obs, int32_t obs_width,
+                         const float* coords, const float* next_coords, int32_t coord_width,
+                         const int32_t* action, const float* reward, const uint8_t* done, float* buf_obs,
+                         float* buf_next_obs, float* buf_coords, float* buf_next_coords, int32_t* buf_action,
+                         float* buf_reward, uint8_t* buf_done, int64_t capacity, int64_t* pos, int32_t* full,
+                         int32_t* appended, int32_t* scratch, int64_t B, void* stream);
+
 /* ---- host-buffer sessions (numpy / ctypes callers; the _np_ops.py calling style) -------
  * A session owns the device state of one shard of B games on one GPU plus staging buffers
  * and a stream.  All pointers below are HOST pointers (pinned or pageable). */

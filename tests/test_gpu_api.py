@@ -195,6 +195,78 @@ def test_fused_game_step_experiences():
     assert eq(AllCoordHostModule(3, 20, dev)(ao["points"]), [[0.0, 0.0, 0.0, 1.0]])
 
 
+def test_replay_buffer_masked_append_and_wraparound():
+    """hk_experience_append: order-preserving compaction of the rows with skip == 0 into circular
+    buffers with a device-resident position, against the reference procedure (boolean-mask filter
+    then ReplayBuffer.add with wrap-around, replay_buffer.py:63-127) replayed in NumPy."""
+    from hironaka_b200 import ReplayBuffer
+    rng = np.random.default_rng(33)
+    cap, N, d = 5000, 20, 3
+    buf = ReplayBuffer({"points": (N, d), "coords": (d,)}, d, cap, torch.device("cuda"))
+    ref = {k: np.zeros((cap,) + sh, np.float32) for k, sh in
+           {"op": (N, d), "oc": (d,), "nop": (N, d), "noc": (d,)}.items()}
+    ref_a, ref_r, ref_d = np.zeros((cap, 1), np.int32), np.zeros((cap, 1), np.float32), np.zeros((cap, 1), bool)
+    pos, full = 0, False
+    for it, B in enumerate([1, 31, 2048, 2049, 4999, 700, 3000]):
+        skip = rng.random(B) < (0.5 if it % 2 else 0.1)
+        op, nop = rng.random((B, N, d), dtype=np.float32), rng.random((B, N, d), dtype=np.float32)
+        oc, noc = rng.integers(0, 2, (B, d)).astype(np.float32), rng.integers(0, 2, (B, d)).astype(np.float32)
+        a, r, dn = rng.integers(0, 3, B).astype(np.int32), rng.random(B, dtype=np.float32), rng.random(B) < 0.3
+        buf.add_masked(T(skip), {"points": T(op), "coords": T(oc)}, T(a), T(r), T(dn), {"points": T(nop), "coords": T(noc)})
+        keep = ~skip
+        L = int(keep.sum())
+        for store, src in ((ref["op"], op), (ref["oc"], oc), (ref["nop"], nop), (ref["noc"], noc), (ref_a, a[:, None]),
+                           (ref_r, r[:, None]), (ref_d, dn[:, None])):
+            idx = (pos + np.arange(L)) % cap
+            store[idx] = src[keep]
+        full = full or (pos + L) >= cap
+        pos = (pos + L) % cap
+        assert buf.pos == pos and buf.full == full, it
+    assert eq(buf.observations["points"], ref["op"]) and eq(buf.observations["coords"], ref["oc"])
+    assert eq(buf.next_observations["points"], ref["nop"]) and eq(buf.next_observations["coords"], ref["noc"])
+    assert eq(buf.actions, ref_a) and eq(buf.rewards, ref_r) and eq(buf.dones, ref_d)
+    assert buf.actions.dtype == torch.int32 and buf.rewards.dtype == torch.float32 and buf.dones.dtype == torch.bool
+    # the reference signature (already-filtered rows) and sampling
+    buf2 = ReplayBuffer((N, d), 4, 100, torch.device("cuda"))
+    o = torch.rand(7, N, d, device="cuda")
+    buf2.add(o, torch.arange(7, device="cuda", dtype=torch.int32)[:, None], torch.ones(7, 1, device="cuda"),
+             torch.zeros(7, 1, device="cuda", dtype=torch.bool), o + 1)
+    assert buf2.pos == 7 and not buf2.full and torch.equal(buf2.observations[:7], o)
+    so, sa, sr, sd, sn = buf2.sample(64)
+    assert so.shape == (64, N, d) and int(sa.max()) <= 6 and torch.equal(sn, so + 1)
+
+
+def test_fused_game_step_into_buffer_matches_step():
+    """FusedGame.step_into (no host sync) fills the buffer with exactly what
+    FusedGame.step + ReplayBuffer.add would."""
+    from hironaka_b200 import FusedGame, ReplayBuffer, TensorPoints
+    from hironaka_b200.players import AllCoordHostModule, ChooseLastAgentModule
+    dev_ = torch.device("cuda")
+    rng = np.random.default_rng(5)
+    B, N, d = 500, 20, 3
+    x = rng.integers(0, 21, (B, N, d)).astype(np.float32)
+    for sample_for in ("host", "agent"):
+        game = FusedGame(AllCoordHostModule(d, N, dev_), ChooseLastAgentModule(d, N, dev_), device=dev_)
+        shape = (N, d) if sample_for == "host" else {"points": (N, d), "coords": (d,)}
+        b1 = ReplayBuffer(shape, 4, 4096, dev_)
+        b2 = ReplayBuffer(shape, 4, 4096, dev_)
+        p1, p2 = TensorPoints(T(x)), TensorPoints(T(x))
+        for p in (p1, p2):
+            p.get_newton_polytope()
+        for _ in range(4):
+            b1.add(*game.step(p1, sample_for, scale_observation=False, exploration_rate=0.0))
+            game.step_into(b2, p2, sample_for, scale_observation=False, exploration_rate=0.0)
+        assert b1.pos == b2.pos and b1.pos > 0
+        for a, b in ((b1.actions, b2.actions), (b1.rewards, b2.rewards), (b1.dones, b2.dones)):
+            assert torch.equal(a, b)
+        if sample_for == "host":
+            assert torch.equal(b1.observations, b2.observations) and torch.equal(b1.next_observations, b2.next_observations)
+        else:
+            for k in ("points", "coords"):
+                assert torch.equal(b1.observations[k], b2.observations[k])
+                assert torch.equal(b1.next_observations[k], b2.next_observations[k])
+
+
 # ---- functional JAX-style API (test/testJAX.py:80-153,205-219,461-488) ------------------------
 def test_functional_api():
     from hironaka_b200 import functional as F

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libhironaka_b200.so")
 SOURCES = ["hk_capi.cu"]
-DEPS = ["hk_capi.cu", "hk_common.cuh", "hk_small.cuh", "hk_generic.cuh", "hk_experience.cuh", os.path.join("..", "..", "include", "hironaka_b200.h")]
+DEPS = ["hk_capi.cu", "hk_common.cuh", "hk_small.cuh", "hk_generic.cuh", "hk_experience.cuh", "hk_value.cuh", os.path.join("..", "..", "include", "hironaka_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,7 @@
 #include "hk_experience.cuh"
 #include "hk_generic.cuh"
 #include "hk_small.cuh"
+#include "hk_value.cuh"
 
 using hk::StepParams;
 
@@ -394,6 +395,35 @@ int hk_experience_append(const uint8_t* skip, const float* obs, const float* nex
     hk::hk_exp_count_kernel<<<p.nblocks, hk::EXP_THREADS, 0, st>>>(p);
     hk::hk_exp_scan_kernel<<<1, 1024, 0, st>>>(p);
     hk::hk_exp_scatter_kernel<<<p.nblocks, hk::EXP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_points_out, float* value, int64_t B,
+                     int32_t T, int32_t W, int32_t dimension, int32_t offset, float discount, int32_t est_sign,
+                     int32_t reward_sign, int32_t unified, void* stream) {
+    if (B < 0 || T < 1 || T > hk::VALUE_MAX_T || !value || (!obs && !num_points)) return HK_ERR_BAD_ARG;
+    if (obs && !num_points && (W < 1 || dimension < 1)) return HK_ERR_BAD_ARG;
+    if (B == 0) return HK_OK;
+    hk::ValueParams p;
+    memset(&p, 0, sizeof(p));
+    p.obs = obs;
+    p.num_points = num_points;
+    p.num_points_out = num_points_out;
+    p.value = value;
+    p.B = B;
+    p.T = T;
+    p.W = W;
+    p.dimension = dimension;
+    p.offset = offset;
+    p.discount = discount;
+    p.est_sign = est_sign;
+    p.reward_sign = reward_sign;
+    p.unified = unified;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * T * sizeof(int32_t);
+    long long ctas = (B + warps - 1) / warps;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    hk::hk_value_targets_kernel<<<(unsigned)ctas, warps * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 

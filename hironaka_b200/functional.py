@@ -162,3 +162,39 @@ def get_env_step(role: str, spec: Tuple[int, int], rescale_points: bool = False,
         return r.state, r.done, r.reward, r.obs
 
     return env_step
+
+
+def calculate_value_using_reward_fn(value_prior: torch.Tensor, num_points: torch.Tensor, discount: float,
+                                    reward_role: str, est_role: str, use_unified_tree: bool) -> torch.Tensor:
+    """Value targets from per-step point counts (util.py:261-284).  The reference takes the reward and
+    estimate functions as callables; here they are named by role ("host"/"agent"), which is all the
+    reference ever passes (jax_trainer.py:579-580).  value_prior only provides shape and dtype."""
+    from ._lib import check, lib
+    B, T = value_prior.shape
+    npts = num_points.to(torch.int32).contiguous()
+    out = torch.empty((B, T), dtype=torch.float32, device=npts.device)
+    with torch.cuda.device(npts.device):
+        rc = lib().hk_value_targets(None, npts.data_ptr(), None, out.data_ptr(), B, T, 0, 1, 0, float(discount),
+                                    1 if est_role == "host" else -1, 1 if reward_role == "host" else -1,
+                                    1 if use_unified_tree else 0, torch.cuda.current_stream(npts.device).cuda_stream)
+    check(rc, "hk_value_targets")
+    return out.to(value_prior.dtype)
+
+
+def rollout_postprocess(rollouts, role: str, dimension: int, discount: float, use_unified_tree: bool = True):
+    """(obs[b,T,input_dim], policy[b,T,A], value[b,T]) -> flattened rollouts with the value prior
+    replaced by the ground-truth discounted value (JAXTrainer.rollout_postprocess,
+    jax_trainer.py:558-592); point counts are recovered from the observations in the kernel."""
+    from ._lib import check, lib
+    obs, policy, value = rollouts
+    B, T, W = obs.shape
+    o = obs.to(torch.float32).contiguous()
+    out = torch.empty((B, T), dtype=torch.float32, device=o.device)
+    offset = 1 if use_unified_tree or role == "agent" else 0
+    reward_role = "agent" if use_unified_tree else role
+    with torch.cuda.device(o.device):
+        rc = lib().hk_value_targets(o.data_ptr(), None, None, out.data_ptr(), B, T, W, dimension, offset, float(discount),
+                                    1 if role == "host" else -1, 1 if reward_role == "host" else -1,
+                                    1 if use_unified_tree else 0, torch.cuda.current_stream(o.device).cuda_stream)
+    check(rc, "hk_value_targets")
+    return obs.reshape(-1, W), policy.reshape(-1, policy.shape[2]), out.reshape(-1).to(value.dtype)

@@ -162,6 +162,16 @@ int hk_experience_append(const uint8_t* skip, const float* obs, const float* nex
                          float* buf_reward, uint8_t* buf_done, int64_t capacity, int64_t* pos, int32_t* full,
                          int32_t* appended, int32_t* scratch, int64_t B, void* stream);
 
+/* ---- rollout value targets --------------------------------------------------
+ * calculate_value_using_reward_fn (hironaka/jax/util.py:261-284) behind JAXTrainer.rollout_postprocess
+ * (hironaka/jax/jax_trainer.py:558-592).  Give either obs [B,T,W] (points per step are recovered as
+ * #(entries >= 0) / dimension - offset, :584) or num_points [B,T].  value [B,T] out; num_points_out
+ * nullable.  est_sign: +1 host / -1 agent (get_value_est_fn util.py:152-169); reward_sign: +1 host /
+ * -1 agent reward function; unified != 0 flips the discount sign every step (unified MC tree). */
+int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_points_out, float* value, int64_t B,
+                     int32_t T, int32_t W, int32_t dimension, int32_t offset, float discount, int32_t est_sign,
+                     int32_t reward_sign, int32_t unified, void* stream);
+
 /* ---- host-buffer sessions (numpy / ctypes callers; the _np_ops.py calling style) -------
  * A session owns the device state of one shard of B games on one GPU plus staging buffers
  * and a stream.  All pointers below are HOST pointers (pinned or pageable). */

@@ -328,6 +328,37 @@ def generate_pts(rng: np.random.Generator, shape, max_value: int, dtype=np.float
     return pts
 
 
+def calculate_value_using_reward_fn(num_points: np.ndarray, discount: float, reward_sign: int, est_sign: int,
+                                    use_unified_tree: bool) -> np.ndarray:
+    """hironaka/jax/util.py:261-284 with reward_fn = +-(dones & ~prev_dones) (:128-149) and
+    est_fn = sign / clip(num_points, 1) (:152-169).  float32 like the reference."""
+    num_points = np.asarray(num_points)
+    B, T = num_points.shape
+    done = num_points <= 1
+    next_done = np.concatenate([done[:, 1:], np.zeros((B, 1), dtype=bool)], axis=1)
+    reward = (next_done & ~done).astype(np.float32) * np.float32(reward_sign)
+    diff = np.arange(T).reshape(1, -1) - np.arange(T).reshape(-1, 1)
+    g = np.float32(-discount if use_unified_tree else discount)
+    with np.errstate(over="ignore"):
+        table = np.clip(np.power(g, diff.astype(np.float32)), -1, 1).astype(np.float32)
+    discounted = reward @ table.T  # vmap(matmul)(table, reward[b])
+    sign = (-1) ** (T + 1) if use_unified_tree else 1
+    est = (np.float32(1) / np.clip(num_points[:, -1], 1, None).astype(np.float32)) * np.float32(est_sign) * np.float32(sign)
+    unfinished = ((~done[:, -1:]) * est[:, None]) * np.power(g, np.arange(T)[::-1].astype(np.float32))[None, :]
+    return (discounted + unfinished).astype(np.float32)
+
+
+def rollout_postprocess(obs: np.ndarray, policy: np.ndarray, value: np.ndarray, role: str, dimension: int,
+                        discount: float, use_unified_tree: bool = True):
+    """hironaka/jax/jax_trainer.py:558-592."""
+    offset = 1 if use_unified_tree or role == "agent" else 0
+    num_points = (obs >= 0).sum(-1) // dimension - offset
+    reward_sign = -1 if (use_unified_tree or role == "agent") else 1
+    est_sign = 1 if role == "host" else -1
+    v = calculate_value_using_reward_fn(num_points, discount, reward_sign, est_sign, use_unified_tree)
+    return obs.reshape(-1, obs.shape[2]), policy.reshape(-1, policy.shape[2]), v.ravel().astype(value.dtype)
+
+
 # ---- fixed players (hironaka/jax/players.py) ------------------------------------------
 
 

@@ -92,3 +92,24 @@ ZEIL_PTS3[0, 9] = [147, 3, 12]
 AGENT_COORDS = np.array([[1, 1, 0], [0, 1, 1]], dtype=f32)
 CHOOSE_FIRST_OUT = np.array([[1, 0, 0], [0, 1, 0]], dtype=f32)
 CHOOSE_LAST_OUT = np.array([[0, 1, 0], [0, 0, 1]], dtype=f32)
+
+# rollout value targets: test/testJAXTrainer.py:91-389 (discount 0.99, dimension 3, N 5).  Point counts per
+# step are what rollout_postprocess recovers from the observations (jax_trainer.py:584).
+VALUE_KATS = [
+    # (num_points [B,T], role, use_unified_tree, expected values)
+    (np.array([[2, 2, 2, 2, 1], [2, 2, 2, 2, 2]]), "agent", False,
+     np.array([[-0.970299, -0.9801, -0.98999995, -1.0, -1.0], [-0.480298, -0.4851495, -0.49005002, -0.495, -0.5]], f32)),
+    (np.array([[3, 3, 3, 3, 2]]), "agent", True, np.array([[-0.480298, 0.4851495, -0.49005002, 0.495, -0.5]], f32)),
+    (np.array([[3, 3, 3, 2]]), "host", True, np.array([[0.4851495, -0.49005002, 0.495, -0.5]], f32)),
+    (np.array([[2, 1, 1, 1]]), "agent", True, np.array([[-1, 1, -1, 1]], f32)),
+    (np.array([[2, 2, 1, 1]]), "host", True, np.array([[0.99, -1, 1, -1]], f32)),
+]
+# the observation form of the last two (unified tree: host rows are zero-padded with d entries)
+VALUE_OBS_AGENT = np.array([[[-1, -1, -1, -1, -1, -1, 1, 1, 14, -1, -1, -1, 4, 1, 3, 1, 1, 0],
+                             [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 0, 0, 0],
+                             [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 1, 0, 1],
+                             [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 0, 0, 0]]], dtype=f32)
+VALUE_OBS_HOST = np.array([[[-1, -1, -1, -1, -1, -1, 1, 1, 14, -1, -1, -1, 4, 1, 3, 0, 0, 0],
+                            [-1, -1, -1, -1, -1, -1, 1, 1, 14, -1, -1, -1, 4, 5, 3, 1, 1, 1],
+                            [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 0, 0, 0],
+                            [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 1, 1, 1]]], dtype=f32)

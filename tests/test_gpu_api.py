@@ -310,6 +310,39 @@ def test_functional_api():
     assert torch.equal(again, pts)
 
 
+def test_value_targets_and_rollout_postprocess():
+    """hk_value_targets vs the reference's vectors (test/testJAXTrainer.py:330-389) and vs the NumPy
+    restatement on random rollouts.  Floating point: tolerance rtol 1e-5 / atol 1e-6 (the reference's
+    own test uses jnp.isclose)."""
+    from hironaka_b200 import functional as F
+    for npts, role, unified, expect in K.VALUE_KATS:
+        reward_role = "agent" if unified else role
+        v = F.calculate_value_using_reward_fn(torch.zeros(npts.shape, device="cuda"), T(npts), 0.99, reward_role, role, unified)
+        assert np.allclose(v.cpu().numpy(), expect, rtol=1e-5, atol=1e-6), (role, unified)
+    pol, val = torch.zeros((1, 4, 3), device="cuda"), torch.zeros((1, 4), device="cuda")
+    o, p_, v = F.rollout_postprocess((T(K.VALUE_OBS_AGENT), pol, val), "agent", 3, 0.99, True)
+    assert np.allclose(v.cpu().numpy(), [-1, 1, -1, 1]) and o.shape == (4, 18) and p_.shape == (4, 3)
+    v = F.rollout_postprocess((T(K.VALUE_OBS_HOST), pol, val), "host", 3, 0.99, True)[2]
+    assert np.allclose(v.cpu().numpy(), [0.99, -1, 1, -1])
+    rng = np.random.default_rng(2)
+    for (B, Tn, N, d) in [(300, 20, 20, 3), (65, 7, 5, 3), (10, 40, 8, 4)]:
+        # monotone point counts like a real game, then observations with that many live rows
+        npts = np.sort(rng.integers(1, N + 1, (B, Tn)), axis=1)[:, ::-1].copy()
+        for role in ("host", "agent"):
+            for unified in (False, True):
+                extra = d if (unified or role == "agent") else 0
+                obs = -np.ones((B, Tn, N * d + extra), np.float32)
+                for b in range(B):
+                    for t in range(Tn):
+                        obs[b, t, : npts[b, t] * d] = rng.random(npts[b, t] * d, dtype=np.float32)
+                if extra:
+                    obs[:, :, N * d:] = rng.integers(0, 2, (B, Tn, d))
+                pol, val = np.zeros((B, Tn, 4), np.float32), np.zeros((B, Tn), np.float32)
+                exp = O.rollout_postprocess(obs, pol, val, role, d, 0.97, unified)[2]
+                got = F.rollout_postprocess((T(obs), T(pol), T(val)), role, d, 0.97, unified)[2].cpu().numpy()
+                assert np.allclose(got, exp, rtol=1e-5, atol=1e-6), (B, Tn, role, unified)
+
+
 def test_fused_env_step_matches_composition():
     """get_env_step (one launch) == take_actions + get_dones + reward_fn + feature_fn."""
     from hironaka_b200 import functional as F

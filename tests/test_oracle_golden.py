@@ -106,6 +106,18 @@ def test_kat_dones_rewards():
     assert O.get_done_from_flatten(K.AGENT_FEAT_IN, "agent", 3).tolist() == [False, False]
 
 
+def test_kat_value_targets():
+    """calculate_value_using_reward_fn / rollout_postprocess vs test/testJAXTrainer.py:330-389."""
+    for npts, role, unified, expect in K.VALUE_KATS:
+        reward_sign = -1 if (unified or role == "agent") else 1
+        v = O.calculate_value_using_reward_fn(npts, 0.99, reward_sign, 1 if role == "host" else -1, unified)
+        assert np.allclose(v, expect, rtol=1e-5, atol=1e-8)
+    pol, val = np.zeros((1, 4, 3), np.float32), np.zeros((1, 4), np.float32)
+    assert np.allclose(O.rollout_postprocess(K.VALUE_OBS_AGENT, pol, val, "agent", 3, 0.99, True)[2], [-1, 1, -1, 1])
+    o, p_, v = O.rollout_postprocess(K.VALUE_OBS_HOST, pol, val, "host", 3, 0.99, True)
+    assert np.allclose(v, [0.99, -1, 1, -1]) and o.shape == (4, 18) and p_.shape == (4, 3)
+
+
 # ---------------------------------------------------------------- KATs through the C port
 
 

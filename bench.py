@@ -299,6 +299,10 @@ def run_gpu_arm(args):
         "algorithmic_bytes_per_launch": B * BYTES_PER_GAME_STEP, "avg_launch_ms": avg_launch_s * 1e3,
         "min_launch_ms": float(np.min(per_launch_ms)), "max_launch_ms": float(np.max(per_launch_ms)),
         "int_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s,
+        # the same launch against the INT32 issue peak (dense algorithmic op count of SURVEY 8d; the tiered
+        # kernel executes fewer because it only visits live points)
+        "int32": {"achieved_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s, "peak_ops_per_s": int32_peak()[0],
+                  "frac": B * OPS_PER_GAME_STEP / avg_launch_s / int32_peak()[0], "peak_source": int32_peak()[1]},
         # mean launch time by position in the 20-step rollout (live points thin out as play goes on)
         "launch_ms_by_rollout_step": [round(float(np.mean(per_launch_ms[t::T_ROLLOUT])), 5)
                                       for t in range(min(T_ROLLOUT, K))],

@@ -197,7 +197,10 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     }
     if ((p.ops & HK_OP_RESCALE) && dtype != HK_DTYPE_F32) return HK_ERR_UNSUPPORTED;
     if (p.ops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON | HK_OP_RESCALE | HK_OP_DEDUPE)) return HK_ERR_BAD_ARG;
-    if ((p.flags & HK_F_OBS_SORT_COORD0) && (p.flags & HK_F_OBS_SORT_LEX)) return HK_ERR_BAD_ARG;
+    {
+        const uint32_t sm = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
+        if (sm & (sm - 1)) return HK_ERR_BAD_ARG;  // at most one sort mode
+    }
     if (p.T < 1) return HK_ERR_BAD_ARG;
     if (p.B == 0) return HK_OK;
     int dev = 0;

@@ -424,8 +424,9 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 }
                 __syncwarp();
                 float* gobs = p.obs + g * (long long)OW;
-                const bool sorted = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX);
+                const bool sorted = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
                 const bool lex = p.flags & HK_F_OBS_SORT_LEX;
+                const bool lexf = p.flags & HK_F_OBS_SORT_LEX_FIRST;
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
@@ -442,6 +443,15 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                             if (lex) {
 #pragma unroll
                                 for (int k = 1; k < D; ++k) {
+                                    const float fj = f[j * D + k];
+                                    gt = (fj > fi[k]) || ((fj == fi[k]) && gt);
+                                    eq = eq && (fj == fi[k]);
+                                }
+                            } else if (lexf) {
+                                gt = f[j * D + D - 1] > fi[D - 1];
+                                eq = f[j * D + D - 1] == fi[D - 1];
+#pragma unroll
+                                for (int k = D - 2; k >= 0; --k) {
                                     const float fj = f[j * D + k];
                                     gt = (fj > fi[k]) || ((fj == fi[k]) && gt);
                                     eq = eq && (fj == fi[k]);

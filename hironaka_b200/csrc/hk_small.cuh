@@ -343,8 +343,9 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
         for (int q = 0; q < K * D; ++q) f[q] = __fdiv_rn(f[q], mx);
     }
     int rank[K];
-    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX);
+    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
     const bool lex = flags & HK_F_OBS_SORT_LEX;
+    const bool lexf = flags & HK_F_OBS_SORT_LEX_FIRST;
 #pragma unroll
     for (int k = 0; k < K; ++k) rank[k] = sorted ? 0 : slot[k];  // unsorted: every row stays in its slot
 #pragma unroll
@@ -354,9 +355,14 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
             const bool both = sorted && (((clm >> i) & (clm >> j) & 1u) != 0);
             // does row j sort strictly before row i?  (ties: lower slot first)
             bool gt = f[j * D] > f[i * D];
-            if (lex) {
+            if (lex) {  // last coordinate primary
 #pragma unroll
                 for (int c = 1; c < D; ++c)
+                    gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
+            } else if (lexf) {  // coordinate 0 primary
+                gt = f[j * D + D - 1] > f[i * D + D - 1];
+#pragma unroll
+                for (int c = D - 2; c >= 0; --c)
                     gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
             }
             rank[i] += (both && gt) ? 1 : 0;

@@ -85,6 +85,16 @@ class TensorPoints(PointsBase):
         f = f.view(self.batch_size, self.max_num_points, self.dimension)
         return f if self.points.dtype == torch.float32 else f.to(self.points.dtype)
 
+    def to_list_points(self) -> List[List[List[float]]]:
+        """The state in ``ListPoints`` form (hironaka/core/list_points.py): per game the live points
+        only, sorted descending lexicographically with coordinate 0 primary — the order
+        ``get_newton_polytope_approx_lst`` leaves them in (hironaka/src/_list_ops.py:9-45).  One
+        features launch, then one device->host copy."""
+        f = _ops.features(self.points, flags=C.HK_F_OBS_SORT_LEX_FIRST, padding_value=self.padding_value)
+        f = f.view(self.batch_size, self.max_num_points, self.dimension).cpu()
+        n = _ops.dones(self.points, want_num_points=True)[1].cpu().tolist()
+        return [f[b, : n[b]].tolist() for b in range(self.batch_size)]
+
     def type(self, t: Union[Type, torch.dtype]):
         self.dtype = t
         self.points = self.points.type(t)

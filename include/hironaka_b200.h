@@ -81,6 +81,9 @@ extern "C" {
 #define HK_F_AGENT_FIRST (1u << 10)    /* agent picks the first chosen coordinate (choose_first_agent_fn, players.py:156-183) */
 #define HK_F_AGENT_LAST (1u << 11)     /* agent picks the last chosen coordinate (choose_last_agent_fn, players.py:186-212) */
 
+#define HK_F_OBS_SORT_LEX_FIRST (1u << 12) /* rows sorted descending lexicographically, coordinate 0 primary: the order of
+                                              ListPoints (Python sorted(points, reverse=True), hironaka/src/_list_ops.py:25) */
+
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
 const char* hk_error_string(int code);

@@ -98,6 +98,25 @@ def per_op(ref, seed, B, N, d, max_value, pad=-1.0):
     return out
 
 
+def list_points_goldens(ref, seed, B, N, d, max_value):
+    """ListPoints order: get_newton_polytope_approx_lst (hironaka/src/_list_ops.py:9-45) on ragged lists."""
+    from hironaka.src import get_newton_polytope_approx_lst
+    rng = np.random.default_rng(seed)
+    games, padded = [], -np.ones((B, N, d), np.float32)
+    for b in range(B):
+        n = int(rng.integers(1, N + 1))
+        pts = rng.integers(0, max_value, (n, d)).astype(float).tolist()
+        games.append(pts)
+        padded[b, :n] = np.array(pts, np.float32)
+    out = get_newton_polytope_approx_lst([[list(p) for p in g] for g in games], inplace=False)
+    res = -np.ones((B, N, d), np.float32)
+    counts = np.zeros(B, np.int32)
+    for b in range(B):
+        counts[b] = len(out[b])
+        res[b, : counts[b]] = np.array(out[b], np.float32)
+    return dict(points=padded, newton_list_order=res, counts=counts)
+
+
 def tables(ref):
     out = {}
     for d in range(2, 8):
@@ -128,6 +147,8 @@ def main():
                                     ("64x5", 13, 6, 64, 5, 6), ("33x3", 14, 8, 33, 3, 6)]:
         np.savez_compressed(os.path.join(OUT, f"ref_ops_{name}.npz"), **per_op(ref, seed, B, N, d, mv))
     np.savez_compressed(os.path.join(OUT, "ref_tables.npz"), **tables(ref))
+    for name, seed, B, N, d, mv in [("20x3", 21, 64, 20, 3, 6), ("10x4", 22, 32, 10, 4, 4), ("40x2", 23, 16, 40, 2, 9)]:
+        np.savez_compressed(os.path.join(OUT, f"ref_list_{name}.npz"), **list_points_goldens(ref, seed, B, N, d, mv))
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -325,9 +325,15 @@ int hk_oracle_rescale_f32(const float* in, float* out, int64_t B, int32_t N, int
  * by coordinate 0 (tensor_points.py:72-74) or lexicographic with the last coordinate primary
  * (util.py:195), then optional coordinate set appended (make_agent_obs util.py:22-31). */
 static int lex_before(const float* a, int ia, const float* b, int ib, int d, int lex) {
-    /* 1 if row a sorts strictly before row b (descending keys, stable on index) */
-    if (lex) {
+    /* 1 if row a sorts strictly before row b (descending keys, stable on index);
+       lex: 1 = last coordinate primary (util.py:195), 2 = coordinate 0 primary (_list_ops.py:25) */
+    if (lex == 1) {
         for (int k = d - 1; k >= 0; --k) {
+            if (a[k] > b[k]) return 1;
+            if (a[k] < b[k]) return 0;
+        }
+    } else if (lex == 2) {
+        for (int k = 0; k < d; ++k) {
             if (a[k] > b[k]) return 1;
             if (a[k] < b[k]) return 0;
         }
@@ -339,8 +345,8 @@ static int lex_before(const float* a, int ia, const float* b, int ib, int d, int
 }
 
 static void features_one(const float* f, float* o, int N, int d, uint32_t flags) {
-    int sorted = (flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX)) != 0;
-    int lex = (flags & HK_F_OBS_SORT_LEX) != 0;
+    int sorted = (flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST)) != 0;
+    int lex = (flags & HK_F_OBS_SORT_LEX) ? 1 : ((flags & HK_F_OBS_SORT_LEX_FIRST) ? 2 : 0);
     for (int i = 0; i < N; ++i) {
         int r = i;
         if (sorted) {

@@ -138,6 +138,29 @@ def test_tensor_points_features_and_fused_game_flow():
         assert eq(rew, O.default_reward("host", O.ended_batch(ref))[~done.cpu().numpy()])
 
 
+def test_list_points_order(golden_dir):
+    """HK_F_OBS_SORT_LEX_FIRST and TensorPoints.to_list_points against the reference's ListPoints
+    filter (tests/golden/ref_list_*.npz from get_newton_polytope_approx_lst)."""
+    import glob, os
+    from hironaka_b200 import TensorPoints, constants as C, ops
+    for gen in (False, True):
+        ops.force_generic(gen)
+        for path in sorted(glob.glob(os.path.join(golden_dir, "ref_list_*.npz"))):
+            g = np.load(path)
+            for dt in (np.float32, np.int32):
+                st = T(g["points"].astype(dt))
+                r = ops.step(st, ops=C.HK_OP_NEWTON, flags=C.HK_F_OBS_SORT_LEX_FIRST, inplace=True, want_obs=True,
+                             want_num_points=True)
+                assert eq(r.obs.reshape(g["points"].shape), g["newton_list_order"]), (path, gen)
+                assert eq(r.num_points, g["counts"])
+            tp = TensorPoints(T(g["points"]))
+            tp.get_newton_polytope()
+            lst = tp.to_list_points()
+            for b in range(len(lst)):
+                assert lst[b] == g["newton_list_order"][b, : g["counts"][b]].tolist()
+    ops.force_generic(False)
+
+
 def test_fused_game_step_experiences():
     """hironaka_b200.FusedGame.step against the reference composition (fused_game.py:54-102):
     experiences of the games not already over, in order, with the pinned dtypes

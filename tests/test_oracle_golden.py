@@ -263,6 +263,19 @@ def test_golden_ops(golden_dir, impl):
                 assert np.array_equal(cport.features(n, O.F_OBS_RESCALE).reshape(B, N, d), g["rescale_after_newton"])
 
 
+def test_golden_list_points_order(golden_dir):
+    """ListPoints order (get_newton_polytope_approx_lst, _list_ops.py:9-45): survivors sorted
+    descending with coordinate 0 primary and compacted."""
+    files = sorted(glob.glob(os.path.join(golden_dir, "ref_list_*.npz")))
+    assert len(files) >= 3
+    for path in files:
+        g = np.load(path)
+        for x in (g["points"], g["points"].astype(np.int32)):
+            n, _, _, npts = cport.step(x, None, None, O.OP_NEWTON, 0)
+            assert np.array_equal(npts, g["counts"]), path
+            assert np.array_equal(cport.features(n, 1 << 12).reshape(x.shape), g["newton_list_order"]), path
+
+
 def test_golden_tables(golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_tables.npz"))
     for d in range(2, 8):

@@ -308,11 +308,11 @@ def run_gpu_arm(args):
                                       for t in range(min(T_ROLLOUT, K))],
     }
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         try:
-            rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, 40, 5)
+            rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, 80, 5)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{CPU_SAMPLE_GAMES} games x 40 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
+                   "sample": f"{CPU_SAMPLE_GAMES} games x 80 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
                              f"(C port of the reference step) over {cores} pthreads"}
         except Exception as e:  # the CPU baseline must never take the GPU line down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}

@@ -73,10 +73,8 @@ struct SmallTune {
     static constexpr int STAGES = OBS ? 2 : 3;  // the obs tile takes the room of the third stage
 };
 
-template <typename T, int N, int D, bool OBS>
-int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
-    constexpr int WARPS = SmallTune<N, D, OBS>::WARPS;
-    constexpr int STAGES = SmallTune<N, D, OBS>::STAGES;
+template <typename T, int N, int D, bool OBS, int WARPS, int STAGES>
+int launch_small_geom(const StepParams& p, int dev, cudaStream_t stream) {
     using L = hk::SmallLayout<N, D, OBS, WARPS, STAGES>;
     static KernelFacts facts;
     auto kernel = hk::hk_small_kernel<T, N, D, OBS, WARPS, STAGES>;
@@ -90,6 +88,17 @@ int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
     if (ctas > cap) ctas = cap;
     kernel<<<(unsigned)ctas, threads, L::SMEM_BYTES, stream>>>(p);
     return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int D, bool OBS>
+int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
+    // A one-launch rollout (T > 1) reads and writes the state once per T steps, so it is bound by
+    // issue rate, not by bytes in flight: one stage per warp and twice the warps
+    // (tools/tune_small.cu: 8x1 = 0.648 ms, 4x1 = 0.661, 4x2 = 0.733, 4x3 = 0.808 per 20-step rollout).
+    if constexpr (!OBS) {
+        if (p.T > 1) return launch_small_geom<T, N, D, false, 8, 1>(p, dev, stream);
+    }
+    return launch_small_geom<T, N, D, OBS, SmallTune<N, D, OBS>::WARPS, SmallTune<N, D, OBS>::STAGES>(p, dev, stream);
 }
 
 template <typename T, bool OBS>
@@ -450,6 +459,19 @@ struct hk_session {
     int32_t* done_count;
 };
 
+// sessions switch to their device for the duration of a call and restore the caller's device
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 #define HK_CUDA(x)                       \
     do {                                 \
         cudaError_t e_ = (x);            \
@@ -461,7 +483,7 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
     if (out == nullptr || B < 1) return HK_ERR_BAD_ARG;
     int rc = check_shape(B, N, d, dtype);
     if (rc != HK_OK) return rc;
-    HK_CUDA(cudaSetDevice(device));
+    DeviceGuard guard_(device);
     hk_session* s = new (std::nothrow) hk_session();
     if (!s) return HK_ERR_BAD_ARG;
     memset(s, 0, sizeof(*s));
@@ -498,7 +520,7 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
 
 int hk_session_destroy(hk_session* s) {
     if (!s) return HK_OK;
-    cudaSetDevice(s->device);
+    DeviceGuard guard_(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->state);
     cudaFree(s->host_action);
@@ -520,7 +542,7 @@ int hk_session_destroy(hk_session* s) {
 
 int hk_session_set_state(hk_session* s, const void* state_host) {
     if (!s || !state_host) return HK_ERR_BAD_ARG;
-    HK_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard_(s->device);
     HK_CUDA(cudaMemcpyAsync(s->state, state_host, (size_t)s->B * s->N * s->d * 4, cudaMemcpyHostToDevice, s->stream));
     HK_CUDA(cudaStreamSynchronize(s->stream));
     return HK_OK;
@@ -528,7 +550,7 @@ int hk_session_set_state(hk_session* s, const void* state_host) {
 
 int hk_session_get_state(hk_session* s, void* state_host) {
     if (!s || !state_host) return HK_ERR_BAD_ARG;
-    HK_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard_(s->device);
     HK_CUDA(cudaMemcpyAsync(state_host, s->state, (size_t)s->B * s->N * s->d * 4, cudaMemcpyDeviceToHost, s->stream));
     HK_CUDA(cudaStreamSynchronize(s->stream));
     return HK_OK;
@@ -537,7 +559,7 @@ int hk_session_get_state(hk_session* s, void* state_host) {
 int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_t* axis_host, uint8_t* done_host,
                     float* reward_host, int32_t* done_count_host, uint32_t ops, uint32_t flags) {
     if (!s) return HK_ERR_BAD_ARG;
-    HK_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard_(s->device);
     const size_t abytes = (size_t)s->B * ((flags & HK_F_ACT_U8) ? 1 : 4);
     if ((ops & HK_OP_SHIFT) && host_action_host)
         HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, abytes, cudaMemcpyHostToDevice, s->stream));
@@ -566,7 +588,7 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
 int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                        int32_t* done_count_host, uint32_t ops, uint32_t flags) {
     if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || !axis_host) return HK_ERR_BAD_ARG;
-    HK_CUDA(cudaSetDevice(s->device));
+    DeviceGuard guard_(s->device);
     if (s->counts_cap < T) {
         cudaFree(s->counts);
         if (s->counts_pinned) cudaFreeHost(s->counts_pinned);

@@ -15,6 +15,9 @@
 namespace hk {
 
 constexpr int SMALL_BAR_BYTES = 256;
+#ifndef HK_ROLLED_MIN
+#define HK_ROLLED_MIN 12  // smallest tier whose victim loop is rolled (tools/tune_small.cu)
+#endif
 
 // WARPS warps per CTA, each with a private ring of STAGES tiles.  With STAGES >= 3 the refill of a
 // stage is issued one iteration after its store (cp.async.bulk.wait_group.read 1), so the issuing

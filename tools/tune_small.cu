@@ -93,6 +93,42 @@ void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vecto
     cudaFree(d_state); cudaFree(d_ha); cudaFree(d_ax); cudaFree(d_done); cudaFree(d_rew);
 }
 
+// one-launch T-step rollouts (hk_rollout): state read and written once per T steps
+template <int WARPS, int STAGES>
+void run_rollout(int B, int R, const std::vector<int32_t>& pts, const std::vector<int32_t>& ha, const std::vector<int32_t>& ax) {
+    int sms = 148;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    int32_t *d_state, *d_ha, *d_ax, *d_cnt;
+    size_t sbytes = (size_t)B * N * D * 4;
+    CK(cudaMalloc(&d_state, sbytes * R)); CK(cudaMalloc(&d_ha, (size_t)R * T * B * 4)); CK(cudaMalloc(&d_ax, (size_t)R * T * B * 4));
+    CK(cudaMalloc(&d_cnt, T * 4)); CK(cudaMemset(d_cnt, 0, T * 4));
+    CK(cudaMemcpy(d_state, pts.data(), sbytes * R, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ha, ha.data(), (size_t)R * T * B * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ax, ax.data(), (size_t)R * T * B * 4, cudaMemcpyHostToDevice));
+    cudaStream_t st; CK(cudaStreamCreate(&st));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    hk::StepParams p; memset(&p, 0, sizeof(p));
+    p.B = B; p.N = N; p.d = D; p.pad = -1.f; p.threshold = 1e8f;
+    double tot = 0;
+    for (int r = 0; r < R; ++r) {
+        int32_t* s = d_state + (size_t)r * B * N * D;
+        p.in = s; p.out = s; p.T = 1; p.ops = HK_OP_NEWTON | HK_OP_REPOSITION; p.flags = 0; p.host_action = nullptr; p.axis = nullptr; p.done_count = nullptr;
+        launch<WARPS, STAGES>(p, st, sms, false, e0, e1);
+        p.T = T; p.ops = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON; p.flags = HK_F_ACT_DISCRETE; p.done_count = d_cnt;
+        p.host_action = d_ha + (size_t)r * T * B; p.axis = d_ax + (size_t)r * T * B;
+        launch<WARPS, STAGES>(p, st, sms, true, e0, e1);
+        CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) tot += ms;
+    }
+    std::vector<int32_t> out((size_t)B * N * D);
+    CK(cudaMemcpy(out.data(), d_state, sbytes, cudaMemcpyDeviceToHost));
+    unsigned long long cs = 1469598103934665603ull;
+    for (size_t i = 0; i < out.size(); ++i) cs = (cs ^ (unsigned)out[i]) * 1099511628211ull;
+    printf("ROLLOUT W=%d S=%d: %.3f ms per %d-step rollout = %.3e game-steps/s | checksum %016llx\n", WARPS, STAGES, tot / (R - 1), T,
+           (double)B * T / (tot / (R - 1) * 1e-3), cs);
+    cudaFree(d_state); cudaFree(d_ha); cudaFree(d_ax); cudaFree(d_cnt);
+}
+
 int main(int argc, char** argv) {
     int B = 1 << 20, R = 4;
     std::mt19937 rng(7);

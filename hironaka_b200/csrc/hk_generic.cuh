@@ -210,7 +210,16 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 }
             }
             // ---- reposition ----
-            if ((p.ops & HK_OP_REPOSITION) && cnt > 0) {
+            if ((p.ops & HK_OP_REPOSITION) && cnt == 1) {
+                // a lone point minus its own coordinates: the origin (most games of a long rollout are here)
+                _Pragma("unroll UNR")
+                for (int r = 0; r < R; ++r) {
+                    if (!((mylive >> r) & 1u)) continue;
+                    const int i = lane + 32 * r;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[i * D + k] = Elem<T>::zero();
+                }
+            } else if ((p.ops & HK_OP_REPOSITION) && cnt > 1) {
                 T mn[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) mn[k] = Elem<T>::big();
@@ -278,19 +287,29 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     for (int r2 = 0; r2 < R; ++r2) {
                         uint32_t m = lmw[r2];
                         while (m) {
-                            const int j = 32 * r2 + __ffs((int)m) - 1;
+                            // two dominators per trip (the second repeats the first when the count is odd:
+                            // AND-accumulation is idempotent), so ten broadcast loads are in flight together
+                            const int ja = 32 * r2 + __ffs((int)m) - 1;
                             m &= m - 1;
-                            T xj[D];
+                            const int jb = m ? (32 * r2 + __ffs((int)m) - 1) : ja;
+                            m &= m - 1;
+                            T xa[D], xb[D];
 #pragma unroll
-                            for (int k = 0; k < D; ++k) xj[k] = x[j * D + k];
-                            int32_t t0 = Elem<T>::bits(a0[0] - xj[0]), t1 = Elem<T>::bits(a1[0] - xj[0]);
+                            for (int k = 0; k < D; ++k) {
+                                xa[k] = x[ja * D + k];
+                                xb[k] = x[jb * D + k];
+                            }
+                            int32_t t0a = Elem<T>::bits(a0[0] - xa[0]), t1a = Elem<T>::bits(a1[0] - xa[0]);
+                            int32_t t0b = Elem<T>::bits(a0[0] - xb[0]), t1b = Elem<T>::bits(a1[0] - xb[0]);
 #pragma unroll
                             for (int k = 1; k < D; ++k) {
-                                t0 |= Elem<T>::bits(a0[k] - xj[k]);
-                                t1 |= Elem<T>::bits(a1[k] - xj[k]);
+                                t0a |= Elem<T>::bits(a0[k] - xa[k]);
+                                t1a |= Elem<T>::bits(a1[k] - xa[k]);
+                                t0b |= Elem<T>::bits(a0[k] - xb[k]);
+                                t1b |= Elem<T>::bits(a1[k] - xb[k]);
                             }
-                            acc0 &= t0 - ((j >= i0) ? 1 : 0);
-                            acc1 &= t1 - ((j >= i1) ? 1 : 0);
+                            acc0 &= (t0a - ((ja >= i0) ? 1 : 0)) & (t0b - ((jb >= i0) ? 1 : 0));
+                            acc1 &= (t1a - ((ja >= i1) ? 1 : 0)) & (t1b - ((jb >= i1) ? 1 : 0));
                         }
                     }
                     kill = ((acc0 >= 0) ? 1u : 0u) | ((acc1 >= 0) ? 2u : 0u);

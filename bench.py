@@ -220,6 +220,8 @@ def run_gpu_arm(args):
     done = torch.empty(B, dtype=torch.uint8, device=dev)
     reward = torch.empty(B, dtype=torch.float32, device=dev)
     lib = hb._lib.lib()
+    if args.no_pdl:
+        lib.hk_debug_set_pdl(0)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def launch_step(r, t):
@@ -540,6 +542,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (profiling runs)")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B tuning)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

@@ -23,6 +23,7 @@ SIGNATURES = {
     "hk_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "hk_kernel_class": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "hk_debug_force_generic": (ctypes.c_int, [ctypes.c_int]),
+    "hk_debug_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "hk_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
     "hk_shift": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_reposition": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),

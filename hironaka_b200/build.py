@@ -4,7 +4,8 @@
 
 Output: hironaka_b200/_lib/libhironaka_b200.so (git-ignored; travels to the GPU box with the
 gpurun snapshot).  The library is a plain C-ABI shared object (include/hironaka_b200.h); it is
-loaded with ctypes by hironaka_b200._lib and has no Python or torch dependency.
+loaded with ctypes by hironaka_b200._lib and has no Python or torch dependency.  The kernels are
+spread over several translation units that compile in parallel and are linked into one library.
 """
 from __future__ import annotations
 
@@ -12,20 +13,21 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
+OBJ_DIR = os.path.join(OUT_DIR, "obj")
 OUT = os.path.join(OUT_DIR, "libhironaka_b200.so")
-SOURCES = ["hk_capi.cu"]
-DEPS = ["hk_capi.cu", "hk_common.cuh", "hk_small.cuh", "hk_generic.cuh", "hk_experience.cuh", "hk_value.cuh", os.path.join("..", "..", "include", "hironaka_b200.h")]
+SOURCES = ["hk_capi.cu", "hk_small_i32_step.cu", "hk_small_i32_obs.cu", "hk_small_f32_step.cu", "hk_small_f32_obs.cu",
+           "hk_generic_i32.cu", "hk_generic_f32.cu"]
+HEADERS = ["hk_common.cuh", "hk_small.cuh", "hk_generic.cuh", "hk_experience.cuh", "hk_value.cuh", "hk_launch.cuh",
+           "hk_small_launch.inl", "hk_generic_launch.inl", os.path.join("..", "..", "include", "hironaka_b200.h")]
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
-]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMPILE_FLAGS = ARCH_FLAGS + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-c"]
+LINK_FLAGS = ARCH_FLAGS + ["-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
 def nvcc_path() -> str:
@@ -35,24 +37,47 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+def _newest_header() -> float:
+    return max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+
+
 def is_stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return _newest_header() > t or any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in SOURCES)
+
+
+def _compile(nvcc: str, src: str, verbose: bool):
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    cmd = [nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", obj, os.path.join(CSRC, src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, obj, r, cmd
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = nvcc_path()
+    hdr_t = _newest_header()
+    todo, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        fresh = os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(os.path.join(CSRC, src)))
+        if force or not fresh:
+            todo.append(src)
+    with ThreadPoolExecutor(max_workers=min(len(todo) or 1, os.cpu_count() or 1)) as pool:
+        for src, obj, r, cmd in pool.map(lambda s: _compile(nvcc, s, verbose), todo):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    r = subprocess.run([nvcc] + LINK_FLAGS + ["-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
     return OUT
 
 

@@ -11,22 +11,35 @@
 #include <new>
 
 #include "hk_experience.cuh"
-#include "hk_generic.cuh"
-#include "hk_small.cuh"
+#include "hk_launch.cuh"
 #include "hk_value.cuh"
 
 using hk::StepParams;
+using hk::kMaxDevices;
+
+namespace hk {
+int launch_small_i32_noobs(const StepParams& p, int dev, cudaStream_t stream);
+int launch_small_i32_obs(const StepParams& p, int dev, cudaStream_t stream);
+int launch_small_f32_noobs(const StepParams& p, int dev, cudaStream_t stream);
+int launch_small_f32_obs(const StepParams& p, int dev, cudaStream_t stream);
+int launch_small_i32(const StepParams& p, bool obs, int dev, cudaStream_t stream) {
+    return obs ? launch_small_i32_obs(p, dev, stream) : launch_small_i32_noobs(p, dev, stream);
+}
+int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream) {
+    return obs ? launch_small_f32_obs(p, dev, stream) : launch_small_f32_noobs(p, dev, stream);
+}
+}  // namespace hk
 
 namespace {
 
-constexpr int kMaxDevices = 64;
+std::atomic<int> g_use_pdl{0};  // programmatic dependent launch of the thread-per-game kernel (hk_debug_set_pdl)
 
 struct DevInfo {
     std::atomic<int> sms{0};
 };
 DevInfo g_dev[kMaxDevices];
 
-int device_sms(int dev) {
+int device_sms_impl(int dev) {
     if (dev < 0 || dev >= kMaxDevices) return 148;
     int v = g_dev[dev].sms.load(std::memory_order_relaxed);
     if (v == 0) {
@@ -35,150 +48,6 @@ int device_sms(int dev) {
         g_dev[dev].sms.store(v, std::memory_order_relaxed);
     }
     return v;
-}
-
-// per-kernel, per-device launch facts (dynamic smem opt-in + resident CTAs per SM), computed once
-struct KernelFacts {
-    std::atomic<int> ctas_per_sm[kMaxDevices];
-    KernelFacts() {
-        for (auto& c : ctas_per_sm) c.store(0);
-    }
-};
-
-template <typename K>
-int kernel_ctas_per_sm(K kernel, KernelFacts& facts, int dev, int threads, size_t smem, cudaError_t* err) {
-    int v = facts.ctas_per_sm[dev].load(std::memory_order_acquire);
-    if (v > 0) return v;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        *err = e;
-        return 0;
-    }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem);
-    if (e != cudaSuccess) {
-        *err = e;
-        return 0;
-    }
-    if (v < 1) v = 1;
-    facts.ctas_per_sm[dev].store(v, std::memory_order_release);
-    return v;
-}
-
-// ---- small (thread-per-game) family -----------------------------------------------------------
-// ring geometry of the thread-per-game kernel per shape: (warps per CTA, stages per warp)
-// (tools/tune_small.cu on B200, C2 workload: 4x3 = 95.6 us/step, 4x2 = 96.5, 3x3 = 102, 2x4 = 103)
-template <int N, int D, bool OBS>
-struct SmallTune {
-    static constexpr int WARPS = 4;
-    static constexpr int STAGES = OBS ? 2 : 3;  // the obs tile takes the room of the third stage
-};
-
-template <typename T, int N, int D, bool OBS, int WARPS, int STAGES>
-int launch_small_geom(const StepParams& p, int dev, cudaStream_t stream) {
-    using L = hk::SmallLayout<N, D, OBS, WARPS, STAGES>;
-    static KernelFacts facts;
-    auto kernel = hk::hk_small_kernel<T, N, D, OBS, WARPS, STAGES>;
-    cudaError_t err = cudaSuccess;
-    const int threads = WARPS * 32;
-    const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
-    if (err != cudaSuccess) return (int)err;
-    const long long ntiles = (p.B + 31) / 32;
-    long long ctas = (ntiles + WARPS - 1) / WARPS;
-    const long long cap = (long long)device_sms(dev) * per_sm;  // persistent: one wave
-    if (ctas > cap) ctas = cap;
-    kernel<<<(unsigned)ctas, threads, L::SMEM_BYTES, stream>>>(p);
-    return (int)cudaGetLastError();
-}
-
-template <typename T, int N, int D, bool OBS>
-int launch_small(const StepParams& p, int dev, cudaStream_t stream) {
-    // A one-launch rollout (T > 1) reads and writes the state once per T steps, so it is bound by
-    // issue rate, not by bytes in flight: one stage per warp and twice the warps
-    // (tools/tune_small.cu: 8x1 = 0.648 ms, 4x1 = 0.661, 4x2 = 0.733, 4x3 = 0.808 per 20-step rollout).
-    if constexpr (!OBS) {
-        if (p.T > 1) return launch_small_geom<T, N, D, false, 8, 1>(p, dev, stream);
-    }
-    return launch_small_geom<T, N, D, OBS, SmallTune<N, D, OBS>::WARPS, SmallTune<N, D, OBS>::STAGES>(p, dev, stream);
-}
-
-template <typename T, bool OBS>
-int dispatch_small(const StepParams& p, int dev, cudaStream_t stream) {
-    if (p.d == 3) {
-        if (p.N == 20) return launch_small<T, 20, 3, OBS>(p, dev, stream);
-        if (p.N == 10) return launch_small<T, 10, 3, OBS>(p, dev, stream);
-        if (p.N == 5) return launch_small<T, 5, 3, OBS>(p, dev, stream);
-    }
-    return HK_ERR_UNSUPPORTED;
-}
-
-bool is_small(int N, int d) { return d == 3 && (N == 20 || N == 10 || N == 5); }
-
-// ---- generic (warp-per-game) family -------------------------------------------------------------
-template <typename T, int D, bool OBS, int RT>
-int launch_generic_rt(const StepParams& p, int dev, cudaStream_t stream) {
-    auto kernel = hk::hk_generic_kernel<T, D, OBS, RT>;
-    const int W = p.N * D;
-    const int Wpad = (W + 3) & ~3;
-    const int R = (p.N + 31) / 32;
-    const int slot_words = Wpad * (OBS ? 3 : 2) + ((R + 3) & ~3);  // two state buffers (+ features) + live-mask words
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * slot_words * 4 > 160 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * slot_words * 4;
-    // launch facts depend on N through the shared-memory size: cache the last one per device
-    struct Facts {
-        std::atomic<size_t> smem_set{0};
-        std::atomic<long long> key{-1};
-        std::atomic<int> per_sm{0};
-    };
-    static Facts facts[kMaxDevices];
-    Facts& fc = facts[dev];
-    cudaError_t err = cudaSuccess;
-    if (smem > fc.smem_set.load(std::memory_order_acquire)) {
-        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        fc.smem_set.store(smem, std::memory_order_release);
-    }
-    const long long key = ((long long)smem << 8) | warps;
-    int per_sm = fc.per_sm.load(std::memory_order_acquire);
-    if (fc.key.load(std::memory_order_acquire) != key || per_sm <= 0) {
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
-        if (err != cudaSuccess) return (int)err;
-        if (per_sm < 1) per_sm = 1;
-        fc.per_sm.store(per_sm, std::memory_order_release);
-        fc.key.store(key, std::memory_order_release);
-    }
-    long long ctas = (p.B + warps - 1) / warps;
-    const long long cap = (long long)device_sms(dev) * per_sm;
-    if (ctas > cap) ctas = cap;
-    kernel<<<(unsigned)ctas, warps * 32, smem, stream>>>(p, warps, slot_words);
-    return (int)cudaGetLastError();
-}
-
-// rows-per-lane specialisations exist for the common dimensions; everything else takes run-time loops
-template <typename T, int D, bool OBS>
-int launch_generic(const StepParams& p, int dev, cudaStream_t stream) {
-    if constexpr (D >= 2 && D <= 5) {
-        if (p.N <= 32) return launch_generic_rt<T, D, OBS, 1>(p, dev, stream);
-        if (p.N <= 64) return launch_generic_rt<T, D, OBS, 2>(p, dev, stream);
-    }
-    return launch_generic_rt<T, D, OBS, 0>(p, dev, stream);
-}
-
-template <typename T, bool OBS>
-int dispatch_generic(const StepParams& p, int dev, cudaStream_t stream) {
-    switch (p.d) {
-        case 1: return launch_generic<T, 1, OBS>(p, dev, stream);
-        case 2: return launch_generic<T, 2, OBS>(p, dev, stream);
-        case 3: return launch_generic<T, 3, OBS>(p, dev, stream);
-        case 4: return launch_generic<T, 4, OBS>(p, dev, stream);
-        case 5: return launch_generic<T, 5, OBS>(p, dev, stream);
-        case 6: return launch_generic<T, 6, OBS>(p, dev, stream);
-        case 7: return launch_generic<T, 7, OBS>(p, dev, stream);
-        case 8: return launch_generic<T, 8, OBS>(p, dev, stream);
-        case 9: return launch_generic<T, 9, OBS>(p, dev, stream);
-        case 10: return launch_generic<T, 10, OBS>(p, dev, stream);
-        default: return HK_ERR_UNSUPPORTED;
-    }
 }
 
 int check_shape(long long B, int N, int d, int dtype) {
@@ -217,13 +86,10 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     const bool obs = p.obs != nullptr;
     // remove_repeated alone is not on the step path: it runs on the warp-per-game kernel for every shape
-    const bool small = is_small(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE);
-    if (dtype == HK_DTYPE_I32) {
-        if (small) return obs ? dispatch_small<int32_t, true>(p, dev, stream) : dispatch_small<int32_t, false>(p, dev, stream);
-        return obs ? dispatch_generic<int32_t, true>(p, dev, stream) : dispatch_generic<int32_t, false>(p, dev, stream);
-    }
-    if (small) return obs ? dispatch_small<float, true>(p, dev, stream) : dispatch_small<float, false>(p, dev, stream);
-    return obs ? dispatch_generic<float, true>(p, dev, stream) : dispatch_generic<float, false>(p, dev, stream);
+    const bool small = hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE);
+    if (dtype == HK_DTYPE_I32)
+        return small ? hk::launch_small_i32(p, obs, dev, stream) : hk::launch_generic_i32(p, obs, dev, stream);
+    return small ? hk::launch_small_f32(p, obs, dev, stream) : hk::launch_generic_f32(p, obs, dev, stream);
 }
 
 StepParams make_params(const void* in, void* out, long long B, int N, int d, float pad) {
@@ -244,6 +110,11 @@ std::atomic<int> g_force_generic{0};
 
 }  // namespace
 
+namespace hk {
+int device_sms(int dev) { return device_sms_impl(dev); }
+bool use_pdl() { return g_use_pdl.load(std::memory_order_relaxed) != 0; }
+}  // namespace hk
+
 extern "C" {
 
 int hk_version(void) { return HK_VERSION; }
@@ -260,7 +131,13 @@ const char* hk_error_string(int code) {
 
 int hk_kernel_class(int N, int d) {
     if (check_shape(1, N, d, HK_DTYPE_I32) != HK_OK) return HK_ERR_UNSUPPORTED;
-    return (is_small(N, d) && !g_force_generic.load()) ? 1 : 0;
+    return (hk::is_small_shape(N, d) && !g_force_generic.load()) ? 1 : 0;
+}
+
+// tuning hook: programmatic dependent launch on/off
+int hk_debug_set_pdl(int on) {
+    g_use_pdl.store(on ? 1 : 0);
+    return HK_OK;
 }
 
 // test hook: route small shapes through the generic warp-per-game kernel as well

@@ -235,15 +235,13 @@ __device__ __forceinline__ bool exceeds(const T (&x)[N * D], uint32_t lm, float 
 }
 
 // One full step of one game in registers.  Returns the new live mask; x holds garbage in dead rows.
-// Zeillinger's host on K register rows, thread-per-game: the rows go to the lane's shared-memory
-// scratch (stride ZS words) and an (i, j) double loop walks them in flat order.
-template <typename T, int K, int D, int ZS>
-__device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_t clm, uint32_t* scratch) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) scratch[k * ZS + c] = __float_as_uint(Elem<T>::to_float(y[k * D + c]));
-    }
+// Zeillinger's host, thread-per-game: the K compact rows are written (as floats) to the lane's
+// shared-memory scratch at stride ZS and an (i, j) double loop walks them in flat order.  The walk
+// is a separate NON-inlined function on shared memory only, so that this rarely used policy adds
+// a few stores and a call to each tier instead of its whole body (the tiers' hot loops have to
+// stay inside the instruction cache), and no register array escapes through a pointer.
+template <int D>
+__device__ __noinline__ uint32_t zeillinger_scratch(const uint32_t* scratch, int K, int ZS, uint32_t clm) {
     ZeilBest b;
     b.L = __int_as_float(0x7f800000);
     b.S = b.L;
@@ -274,19 +272,35 @@ __device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_
     return zeillinger_mask_from_diff<D>(vi, vj, found);
 }
 
-template <typename T, int N, int D, int RS = 0>
+template <typename T, int K, int D, int ZS>
+__device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_t clm, uint32_t* scratch) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) scratch[k * ZS + c] = __float_as_uint(Elem<T>::to_float(y[k * D + c]));
+    }
+    return zeillinger_scratch<D>(scratch, K, ZS, clm);
+}
+
+// POLICY: instantiation that can evaluate the fixed players (kept out of the ordinary step kernels)
+template <typename T, int N, int D, int RS = 0, bool POLICY = false>
 __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
                                               int32_t ax_in, uint32_t* scratch = nullptr) {
     if (ops & HK_OP_SHIFT) {
         uint32_t cm;
-        if (flags & HK_F_HOST_ALL_COORD) {
-            cm = (1u << D) - 1u;
-        } else if (flags & HK_F_HOST_ZEILLINGER) {
-            cm = zeillinger_rows<T, N, D, D>(x, lm, scratch);
+        int ax = ax_in;
+        if constexpr (POLICY) {
+            if (flags & HK_F_HOST_ALL_COORD) {
+                cm = (1u << D) - 1u;
+            } else if (flags & HK_F_HOST_ZEILLINGER) {
+                cm = zeillinger_rows<T, N, D, D>(x, lm, scratch);
+            } else {
+                cm = action_mask(ha, flags);
+            }
+            ax = agent_policy_axis(cm, ax_in, flags, D);
         } else {
             cm = action_mask(ha, flags);
         }
-        const int ax = agent_policy_axis(cm, ax_in, flags, D);
         bool apply = (ax >= 0) && (ax < D);
         if (flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
         if (flags & HK_F_FREEZE_ENDED) apply = apply && (__popc(lm) >= 2);
@@ -402,7 +416,7 @@ __host__ __device__ constexpr int next_lower_tier(int K) { return K > 16 ? 16 : 
 // Runs steps [st, T) of one tile on K compact rows; returns the step index at which it stopped
 // (T, or earlier when every game of the warp fits the next lower tier).  The lane's game area in
 // shared memory (`row`) holds the current state on entry and on exit.
-template <typename T, int N, int D, int K, bool OBS>
+template <typename T, int N, int D, int K, bool OBS, bool POLICY>
 __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, const T (&x)[N * D],
                                           uint32_t lm, int st, bool& exceed, float* orow, int OW) {
     const long long B = p.B;
@@ -442,7 +456,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
         }
         const bool prev_done = ls.cnt < 2;
-        clm = game_step<T, K, D, RS>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
+        clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
         ls.cnt = __popc(clm);
         const bool dn = ls.cnt < 2;
         if (ls.valid) {
@@ -475,7 +489,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             }
             store_game<T, N * D>(row, y);
         } else {
-            if (ROLLED || (p.flags & HK_F_HOST_ZEILLINGER)) {  // the scratch overwrote the game area: all padding, then the survivors
+            if (ROLLED || (POLICY && (p.flags & HK_F_HOST_ZEILLINGER))) {  // the scratch overwrote the game area: all padding, then the survivors
                 const uint32_t pw = (uint32_t)Elem<T>::bits(padv);
                 if constexpr ((N * D) % 4 == 0) {
 #pragma unroll
@@ -514,7 +528,7 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* s
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
 }
 
-template <typename T, int N, int D, bool OBS, int WARPS, int STAGES>
+template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p) {
     using L = SmallLayout<N, D, OBS, WARPS, STAGES>;
     constexpr int SMALL_WARPS = WARPS;
@@ -540,12 +554,14 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
     const bool write = (gout != nullptr);
     const bool mutate = p.ops != 0;
 
+    pdl_launch_dependents();  // the next launch of the stream may begin its prologue as SMs free up
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SMALL_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
+    pdl_wait_prior_grid();  // everything below reads or writes global memory of the previous launch
 
     auto tile_words = [&](long long t) -> int {
         long long left = B - (t << 5);
@@ -622,20 +638,20 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
             };
             if (N > 4 && lmax <= 4) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 4 ? 4 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 4 ? 4 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
             } else if (N > 8 && lmax <= 8) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 8 ? 8 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 8 ? 8 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
             } else if (N > 12 && lmax <= 12) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 12 ? 12 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 12 ? 12 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
                 normalised = normalised || (W % 4 == 0);
             } else if (N > 16 && lmax <= 16) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 16 ? 16 : N), OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 16 ? 16 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
                 normalised = normalised || (W % 4 == 0);
             } else {
-                st = tier_steps<T, N, D, N, OBS>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, N, OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
                 normalised = true;
             }
         } while (st < p.T);

@@ -1,0 +1,5 @@
+// thread-per-game kernel, int32_t state, instantiations WITH observation features
+#include "hk_small_launch.inl"
+namespace hk {
+int launch_small_i32_obs(const StepParams& p, int dev, cudaStream_t stream) { return dispatch_small<int32_t, true>(p, dev, stream); }
+}  // namespace hk

@@ -93,6 +93,9 @@ int hk_kernel_class(int N, int d);
 /* Test hook: when on != 0, shapes of the thread-per-game class are routed through the generic
  * warp-per-game kernel too (so both kernel families are parity-tested on every shape). */
 int hk_debug_force_generic(int on);
+/* Tuning hook: programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) of
+ * the thread-per-game kernel, on by default; results do not depend on it. */
+int hk_debug_set_pdl(int on);
 
 /* ---- the fused step ------------------------------------------------------------------
  * One launch = one game-step for B independent games:

@@ -24,7 +24,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch or 
     if name == "PointsBase":
         from .points_base import PointsBase
         return PointsBase
-    if name in ("GameBatch", "shard_range", "gather_rollout"):
+    if name in ("GameBatch", "shard_range", "gather_rollout", "compute_rho"):
         from . import engine
         return getattr(engine, name)
     if name == "HostSession":

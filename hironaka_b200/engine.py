@@ -130,6 +130,19 @@ class GameBatch:
         return _ops.features(self.points, flags=flags, obs_coord=coords if role == "agent" else None)
 
     @staticmethod
+    def details(done_count_initial: int, done_count: torch.Tensor, batch: int):
+        """Histogram of game lengths the way compute_rho accumulates it (jax_trainer.py:519-536):
+        details[t] = games found finished after t steps (recorded before step t is taken),
+        details[T] = games still running after T steps (last-step finishers are dropped, as there)."""
+        c = [done_count_initial] + [int(v) for v in done_count.tolist()]
+        T = len(c) - 1
+        d = [0] * (T + 1)
+        for t in range(T):
+            d[t] += c[t] - (c[t - 1] if t >= 1 else 0)
+        d[T] += batch - c[T]
+        return d
+
+    @staticmethod
     def rho(done_count_initial: int, done_count: torch.Tensor, batch: int) -> float:
         """rho = games finished / total steps played, from per-step finished counts
         (compute_rho, hironaka/jax/jax_trainer.py:519-555)."""
@@ -141,3 +154,37 @@ class GameBatch:
         details[T] += batch - c[T]  # games still running (:536); last-step finishers are dropped, as there
         denom = sum(i * n for i, n in enumerate(details))
         return float(sum(details[1:])) / denom if denom else float("nan")
+
+
+def compute_rho(host: str, agent: str, batch_size: int, spec: Tuple[int, int], max_value: int, max_length: int,
+                num_of_loops: int = 10, reposition: bool = True, generator: Optional[torch.Generator] = None,
+                device="cuda"):
+    """rho between a fixed host and a fixed agent, the validation loop of the reference
+    (JAXTrainer.compute_rho, hironaka/jax/jax_trainer.py:467-556) with every game-step on the device
+    and ONE launch per batch of games: root states randint[0, max_value) -> newton -> (reposition),
+    then max_length - 1 steps of `host` vs `agent`.
+
+    host: "random" | "all_coord" | "zeillinger";  agent: "random" | "choose_first" | "choose_last"
+    (hironaka/jax/players.py).  Random players draw their action streams with torch on the device;
+    the other players are evaluated inside the kernel.  Returns (rho, details) like the reference:
+    rho = sum(details[1:]) / sum(i * details[i])."""
+    n, d = spec
+    if host not in ("random", "all_coord", "zeillinger") or agent not in ("random", "choose_first", "choose_last"):
+        raise ValueError(f"unknown fixed player: {host!r} / {agent!r}")
+    steps = max_length - 1
+    ncls = 2 ** d - d - 1
+    details = [0] * max_length
+    for _ in range(num_of_loops):
+        pts = torch.randint(0, max_value, (batch_size, n, d), generator=generator, device=device, dtype=torch.int32)
+        gb = GameBatch(pts, semantics="jax", reposition=reposition, initial_filter=True,
+                       host_policy=None if host == "random" else host, agent_policy=None if agent == "random" else agent)
+        done0 = int(gb.dones().sum())
+        ha = torch.randint(0, ncls, (steps, batch_size), generator=generator, device=device, dtype=torch.int32) \
+            if host == "random" else None
+        ax = torch.randint(0, d, (steps, batch_size), generator=generator, device=device, dtype=torch.int32) \
+            if agent == "random" else None
+        _, _, dcount, _ = gb.rollout(ha, ax, want_length=False, steps=steps)
+        for t, v in enumerate(GameBatch.details(done0, dcount, batch_size)):
+            details[t] += v
+    denom = sum(i * v for i, v in enumerate(details))
+    return (float(sum(details[1:])) / denom if denom else float("nan")), details

@@ -417,6 +417,32 @@ def test_game_batch_and_rho():
     assert eq(gb.features("host"), cport.features(o, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE))
 
 
+def test_compute_rho_matches_reference_loop():
+    """engine.compute_rho (one launch per batch) against the reference's loop
+    (jax_trainer.py:502-556) replayed with the oracle on the same root states, for fixed players."""
+    from hironaka_b200 import compute_rho
+    B, N, d, max_len, mv = 2000, 20, 3, 12, 20
+    F = {"all_coord": 1 << 8, "zeillinger": 1 << 9, "choose_first": 1 << 10, "choose_last": 1 << 11}
+    for host, agent in (("zeillinger", "choose_first"), ("all_coord", "choose_last"), ("zeillinger", "choose_last")):
+        g = torch.Generator(device="cuda").manual_seed(7)
+        rho, details = compute_rho(host, agent, B, (N, d), mv, max_len, num_of_loops=2, reposition=True, generator=g)
+        g = torch.Generator(device="cuda").manual_seed(7)
+        exp = [0] * max_len
+        for _ in range(2):
+            pts = torch.randint(0, mv, (B, N, d), generator=g, device="cuda", dtype=torch.int32).cpu().numpy()
+            o = cport.step(pts, None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+            prev_done, done = 0, int(O.get_dones(o.astype(np.float32)).sum())
+            for step in range(max_len - 1):
+                exp[step] += done - prev_done
+                o, od, _, _ = cport.step(o, None, None, O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, F[host] | F[agent])
+                prev_done, done = done, int(od.sum())
+            exp[max_len - 1] += B - done
+        assert details == exp, (host, agent)
+        assert abs(rho - sum(exp[1:]) / sum(i * v for i, v in enumerate(exp))) < 1e-12
+    rho, details = compute_rho("random", "random", 4096, (20, 3), 20, 20, num_of_loops=1)
+    assert 0 < rho < 1 and sum(details) <= 4096
+
+
 def test_host_session_numpy_only():
     """hk_session_*: host (NumPy) buffers in and out, no torch tensors involved."""
     from hironaka_b200 import HostSession

@@ -36,6 +36,7 @@ SIGNATURES = {
     "hk_experience_append": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
                                             _p, _p, _i64, _p]),
     "hk_value_targets": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _p]),
+    "hk_pack_coords": (ctypes.c_int, [_p, _i32, _p, _i64, _i32, _p]),
     "hk_session_create": (ctypes.c_int, [ctypes.POINTER(_p), ctypes.c_int, _i64, _i32, _i32, _i32, _f32]),
     "hk_session_destroy": (ctypes.c_int, [_p]),
     "hk_session_set_state": (ctypes.c_int, [_p, _p]),

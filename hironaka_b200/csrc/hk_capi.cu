@@ -316,6 +316,21 @@ int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_p
     return (int)cudaGetLastError();
 }
 
+int hk_pack_coords(const void* coords, int32_t src_dtype, int32_t* mask, int64_t B, int32_t d, void* stream) {
+    if (B < 0 || d < 1 || d > 31 || !mask || (!coords && B > 0)) return HK_ERR_BAD_ARG;
+    if (B == 0) return HK_OK;
+    const unsigned blocks = (unsigned)((B + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+        case 0: hk::hk_pack_coords_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)coords, mask, B, d); break;
+        case 1: hk::hk_pack_coords_kernel<float><<<blocks, 256, 0, st>>>((const float*)coords, mask, B, d); break;
+        case 2: hk::hk_pack_coords_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)coords, mask, B, d); break;
+        case 3: hk::hk_pack_coords_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)coords, mask, B, d); break;
+        default: return HK_ERR_BAD_ARG;
+    }
+    return (int)cudaGetLastError();
+}
+
 // ---- host-buffer sessions ----------------------------------------------------------------------
 struct hk_session {
     int device;

@@ -71,4 +71,15 @@ __global__ void __launch_bounds__(256) hk_value_targets_kernel(const ValueParams
     }
 }
 
+// Multi-binary coordinate vectors [B, d] (the host action form the reference passes around:
+// decode_tensor output, hironaka/src/_fn.py:313-325) -> int32 bitmasks, bit k <=> coordinate k.
+template <typename S>
+__global__ void __launch_bounds__(256) hk_pack_coords_kernel(const S* coords, int32_t* mask, long long B, int d) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint32_t m = 0;
+    for (int k = 0; k < d; ++k) m |= ((float)coords[b * d + k] > 0.5f) ? (1u << k) : 0u;
+    mask[b] = (int32_t)m;
+}
+
 }  // namespace hk

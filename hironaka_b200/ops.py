@@ -14,6 +14,7 @@ from . import constants as C
 from ._lib import HironakaB200Error, check, lib
 
 _DT = {torch.int32: C.HK_DTYPE_I32, torch.float32: C.HK_DTYPE_F32}
+_PACK_DT = {torch.int32: 0, torch.float32: 1, torch.int64: 2, torch.uint8: 3, torch.bool: 3}
 
 
 class StepResult(NamedTuple):
@@ -76,7 +77,18 @@ def coords_to_mask(coords: Union[torch.Tensor, Sequence[Sequence[int]]], dimensi
         raise Exception(f"unsupported input type for coord. Got {type(coords)}.")
     if coords.dim() != 2 or coords.shape[1] != dimension:
         raise ValueError(f"coords must be [B, {dimension}]; got {tuple(coords.shape)}")
-    weights = (1 << torch.arange(dimension, device=coords.device, dtype=torch.int32))
+    if coords.is_cuda:  # one launch of hk_pack_coords
+        code = _PACK_DT.get(coords.dtype)
+        if code is None:
+            coords, code = coords.to(torch.float32), 1
+        coords = coords.contiguous()
+        mask = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            rc = lib().hk_pack_coords(coords.data_ptr(), code, mask.data_ptr(), coords.shape[0], dimension,
+                                      torch.cuda.current_stream(coords.device).cuda_stream)
+        check(rc, "hk_pack_coords")
+        return mask if mask.device == torch.device(device) else mask.to(device)
+    weights = (1 << torch.arange(dimension, device=coords.device, dtype=torch.int32))  # host-side lists / CPU tensors
     return ((coords > 0.5).to(torch.int32) * weights).sum(1, dtype=torch.int32).to(device)
 
 

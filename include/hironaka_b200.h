@@ -178,6 +178,12 @@ int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_p
                      int32_t T, int32_t W, int32_t dimension, int32_t offset, float discount, int32_t est_sign,
                      int32_t reward_sign, int32_t unified, void* stream);
 
+/* ---- host action packing ----------------------------------------------------------------------
+ * Multi-binary coordinate vectors coords[B, d] (what HostActionEncoder.decode_tensor and
+ * get_batch_decode return, hironaka/src/_fn.py:313-325, hironaka/jax/host_action_preprocess.py:58-65)
+ * -> int32 bitmasks mask[B] for hk_step.  src_dtype: 0 int32, 1 float32, 2 int64, 3 uint8/bool. */
+int hk_pack_coords(const void* coords, int32_t src_dtype, int32_t* mask, int64_t B, int32_t d, void* stream);
+
 /* ---- host-buffer sessions (numpy / ctypes callers; the _np_ops.py calling style) -------
  * A session owns the device state of one shard of B games on one GPU plus staging buffers
  * and a stream.  All pointers below are HOST pointers (pinned or pageable). */

@@ -366,6 +366,41 @@ def test_value_targets_and_rollout_postprocess():
                 assert np.allclose(got, exp, rtol=1e-5, atol=1e-6), (B, Tn, role, unified)
 
 
+def test_graphed_env_step():
+    from hironaka_b200 import functional as F
+    rng = np.random.default_rng(40)
+    B, N, d = 100, 20, 3
+    x = O.generate_pts(rng, (B, N, d), 20, rescale=False, reposition=True).astype(np.int32)
+    for role in ("host", "agent"):
+        g = F.GraphedEnvStep(role, (N, d), B)
+        g.points.copy_(T(x))
+        o = x
+        for t in range(4):
+            hid, ax, nxt = rng.integers(0, 4, B), rng.integers(0, 3, B), rng.integers(0, 4, B)
+            g.host_action.copy_(T(hid.astype(np.int32)))
+            g.axis.copy_(T(ax.astype(np.int32)))
+            if role == "agent":
+                g.next_coord.copy_(T(nxt.astype(np.int32)))
+            pts, done, rew, obs = g()
+            prev = O.get_dones(o.astype(np.float32))
+            o, od, _, _ = cport.step(o, hid, ax, O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE)
+            assert eq(pts, o) and eq(done, od.astype(bool)) and eq(rew, O.reward_fn(role, od.astype(bool), prev))
+            exp_obs = cport.features(o, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE | O.F_ACT_DISCRETE,
+                                     obs_coord=nxt.astype(np.int32) if role == "agent" else None)
+            assert eq(obs, exp_obs)
+
+
+def test_pack_coords_all_dtypes():
+    from hironaka_b200.ops import coords_to_mask
+    rng = np.random.default_rng(1)
+    for d in (2, 3, 5, 10):
+        mb = rng.integers(0, 2, (777, d))
+        exp = (mb * (1 << np.arange(d))).sum(1).astype(np.int32)
+        for dt in (torch.float32, torch.int32, torch.int64, torch.uint8, torch.bool, torch.float64, torch.float16):
+            got = coords_to_mask(torch.as_tensor(mb).to(dt).cuda(), d, torch.device("cuda", 0))
+            assert got.dtype == torch.int32 and eq(got, exp), (d, dt)
+
+
 def test_fused_env_step_matches_composition():
     """get_env_step (one launch) == take_actions + get_dones + reward_fn + feature_fn."""
     from hironaka_b200 import functional as F

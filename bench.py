@@ -394,6 +394,40 @@ def measure_secondary(torch, lib, C, dev):
                  "game_steps_per_s": B / (ms * 1e-3), "bound": "launch latency (1024 games = 123 KB per launch)",
                  "hbm_frac": B * (8 * N * d + 13) / (ms * 1e-3) / 1e9 / peak_hbm}
 
+    # C4: the ADE start configurations (N=5, d=3), B=4096, FusedGame semantics + replay-buffer append
+    try:
+        from hironaka_b200 import ReplayBuffer, ops as hops
+        ade = np.array([[[3, 0, 0], [0, 5, 0], [0, 0, 2]], [[2, 0, 0], [0, 3, 0], [0, 0, 3]], [[2, 0, 0], [0, 3, 0], [0, 0, 4]],
+                        [[2, 0, 0], [0, 2, 1], [0, 0, 5]], [[2, 0, 0], [0, 2, 0], [0, 0, 4]], [[3, 0, 0], [0, 5, 0], [0, 2, 2]]],
+                       dtype=np.float32)
+        B, N, d, T = 4096, 5, 3, 10
+        rng = np.random.default_rng(4)
+        x0 = -np.ones((B, N, d), np.float32)
+        x0[:, :3] = ade[rng.integers(0, 6, B)]
+        xs = torch.from_numpy(x0).to(dev)
+        pristine = xs.clone()
+        ha = torch.from_numpy(rng.integers(0, 4, size=(T, B), dtype=np.int32)).to(dev)
+        ax = torch.from_numpy(rng.integers(0, d, size=(T, B), dtype=np.int32)).to(dev)
+        buf = ReplayBuffer((N, d), 4, 1 << 16, dev)
+        fl = C.TORCH_SEMANTICS | C.HK_F_ACT_DISCRETE | C.HK_F_OBS_SORT_COORD0
+
+        def dqn_step(i):
+            t = i % T
+            if t == 0:
+                xs.copy_(pristine)
+            before = hops.features(xs, flags=C.HK_F_OBS_SORT_COORD0)
+            skip = hops.dones(xs)[0]
+            r = hops.step(xs, ha[t], ax[t], ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=fl, inplace=True, want_done=True,
+                          want_reward=True, want_obs=True)
+            buf.add_masked(skip, before, ha[t], r.reward, r.done, r.obs)
+        ms = timed(dqn_step, 200)
+        out["C4"] = {"workload": "6 ADE starts (search.py:123-128) padded to N=5, B=4096, FusedGame semantics, T=10; per step: "
+                                 "features + dones + fused step with features + order-preserving replay append (6 launches, "
+                                 "no host sync)", "us_per_step": ms * 1e3, "game_steps_per_s": B / (ms * 1e-3),
+                     "bound": "launch latency (Python-driven, 4096 games)"}
+    except Exception as e:
+        out["C4"] = {"error": repr(e)}
+
     # C5: dim=5, max_num_points=64, batch 256K, T=20 — the warp-per-game kernel, ALU-bound shape
     B, N, d, T = 1 << 18, 64, 5, 20
     x, ha, ax = make(B, N, d, T, 20, 5, True)
@@ -434,6 +468,8 @@ def measure_secondary(torch, lib, C, dev):
                  "kernel": "hk::hk_generic_kernel<int,5,false>", "ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
                  "ms_by_rollout_step": [round(float(v), 4) for v in per],
                  "hbm_frac": B * bytes5 / (ms * 1e-3) / 1e9 / peak_hbm,
+                 # SURVEY 8d accounting for the ALU-bound shape: game-steps/s x dense OPS(N,d) / INT32 peak
+                 "int32_frac_algorithmic": B * ops5 / (ms * 1e-3) / peak_int,
                  "int_ops_per_game_step_dense": ops5, "int32_peak": peak_int, "int32_peak_source": int_src,
                  "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
                  "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "

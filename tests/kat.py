@@ -113,3 +113,13 @@ VALUE_OBS_HOST = np.array([[[-1, -1, -1, -1, -1, -1, 1, 1, 14, -1, -1, -1, 4, 1,
                             [-1, -1, -1, -1, -1, -1, 1, 1, 14, -1, -1, -1, 4, 5, 3, 1, 1, 1],
                             [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 0, 0, 0],
                             [-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 4, 5, 3, 1, 1, 1]]], dtype=f32)
+
+# BASELINE config 4: the six surface-singularity (ADE) start configurations of hironaka/jax/search.py:123-128
+ADE_STARTS = np.array([
+    [[3, 0, 0], [0, 5, 0], [0, 0, 2]],
+    [[2, 0, 0], [0, 3, 0], [0, 0, 3]],
+    [[2, 0, 0], [0, 3, 0], [0, 0, 4]],
+    [[2, 0, 0], [0, 2, 1], [0, 0, 5]],
+    [[2, 0, 0], [0, 2, 0], [0, 0, 4]],
+    [[3, 0, 0], [0, 5, 0], [0, 2, 2]],
+], dtype=f32)

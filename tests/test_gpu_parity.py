@@ -363,6 +363,52 @@ def test_exceed_flag_and_errors(hb):
     assert ops.step(e, ops=O.OP_NEWTON, want_done=True).done.numel() == 0  # empty batch
 
 
+def test_config4_ade_starts_dqn_replay(hb):
+    """BASELINE config 4: the six ADE start configurations (search.py:123-128) padded to N = 5 and
+    replicated to B = 4096 with independent action streams, FusedGame semantics (shift -> newton ->
+    rescale; invalid action = no-op, ended games frozen), experiences of the games that were not over
+    appended in order to a replay buffer — state, done, reward and buffer contents vs the oracle."""
+    from hironaka_b200 import ReplayBuffer, ops
+    B, N, d, Tn = 4096, 5, 3, 10
+    rng = np.random.default_rng(44)
+    x = -np.ones((B, N, d), np.float32)
+    x[:, :3] = K.ADE_STARTS[rng.integers(0, 6, B)]
+    for scale in (False, True):
+        op_bits = O.OP_SHIFT | O.OP_NEWTON | (O.OP_RESCALE if scale else 0)
+        flags = TORCH_FLAGS | O.F_ACT_DISCRETE
+        o = cport.step(x, None, None, O.OP_NEWTON | (O.OP_RESCALE if scale else 0), 0)[0]
+        g = dev(x)
+        ops.step(g, ops=O.OP_NEWTON | (O.OP_RESCALE if scale else 0), inplace=True)
+        assert np.array_equal(g.cpu().numpy(), o)
+        buf = ReplayBuffer((N, d), 4, 1 << 15, torch.device("cuda"))
+        ref_obs, ref_act, ref_rew, ref_done, ref_next = [], [], [], [], []
+        for t in range(Tn):
+            ha = rng.integers(0, 4, B).astype(np.int32)
+            ax = rng.integers(0, 3, B).astype(np.int32)
+            obs_before = cport.features(o, O.F_OBS_SORT_COORD0).reshape(B, N, d)
+            prev_done = O.ended_batch(o)
+            feat_before = ops.features(g, flags=O.F_OBS_SORT_COORD0).view(B, N, d)
+            skip = ops.dones(g)[0]
+            r = ops.step(g, dev(ha), dev(ax), ops=op_bits, flags=flags, inplace=True, want_done=True, want_reward=True,
+                         want_obs=True)
+            o, od, orw, _ = cport.step(o, ha, ax, op_bits, flags)
+            assert np.array_equal(g.cpu().numpy(), o), (scale, t)
+            assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)) and np.array_equal(r.reward.cpu().numpy(), orw)
+            assert np.array_equal(skip.cpu().numpy(), prev_done)
+            next_feat = ops.features(g, flags=O.F_OBS_SORT_COORD0).view(B, N, d)
+            buf.add_masked(skip, feat_before, dev(ha), r.reward, r.done, next_feat)
+            keep = ~prev_done
+            ref_obs.append(obs_before[keep]); ref_act.append(ha[keep]); ref_rew.append(orw[keep])
+            ref_done.append(od.astype(bool)[keep]); ref_next.append(cport.features(o, O.F_OBS_SORT_COORD0).reshape(B, N, d)[keep])
+        n = sum(len(a) for a in ref_act)
+        assert buf.pos == n and not buf.full and n > 0
+        assert np.array_equal(buf.observations[:n].cpu().numpy(), np.concatenate(ref_obs))
+        assert np.array_equal(buf.next_observations[:n].cpu().numpy(), np.concatenate(ref_next))
+        assert np.array_equal(buf.actions[:n, 0].cpu().numpy(), np.concatenate(ref_act))
+        assert np.array_equal(buf.rewards[:n, 0].cpu().numpy(), np.concatenate(ref_rew))
+        assert np.array_equal(buf.dones[:n, 0].cpu().numpy(), np.concatenate(ref_done))
+
+
 # ---------------------------------------------------------------- BASELINE sizes
 
 

@@ -162,6 +162,23 @@ def cpu_rate(sample_games: int, steps: int, warmup: int, seed: int = 1234, threa
     return sample_games * steps / dt, cores, dt
 
 
+def reference_style_rate(games: int = 4096, steps: int = 10, seed: int = 77):
+    """The NumPy restatement that keeps the reference's own algorithm shape — materialised
+    [B,N,N,d] difference tensors per op, one array op per reference line (oracle/hk_oracle.py) —
+    timed on one host thread.  Context for the C port's number: this is what the reference's
+    array-library formulation costs on a CPU (BASELINE.md section 2 measured 7.6e4-9.1e4
+    game-steps/s for the real torch reference on 8 threads)."""
+    from oracle import hk_oracle as O
+    rng = np.random.default_rng(seed)
+    x = O.generate_pts(rng, (games, N_POINTS, DIM), MAX_VALUE, rescale=False, reposition=True)
+    ncls = 2 ** DIM - DIM - 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x, *_ = O.step(x, rng.integers(0, ncls, games), rng.integers(0, DIM, games),
+                       O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE)
+    return games * steps / (time.perf_counter() - t0)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -314,6 +331,9 @@ def run_gpu_arm(args):
         try:
             rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, 80, 5)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "reference_style_numpy": {"value": reference_style_rate(), "cores": 1,
+                                             "sample": "4096 games x 10 steps, oracle/hk_oracle.py (array-op restatement "
+                                                       "with the reference's [B,N,N,d] temporaries)"},
                    "sample": f"{CPU_SAMPLE_GAMES} games x 80 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
                              f"(C port of the reference step) over {cores} pthreads"}
         except Exception as e:  # the CPU baseline must never take the GPU line down

@@ -264,7 +264,8 @@ def test_fixed_players(hb, family, shape, dtype):
         ha = rng.integers(0, ncls, (Tn, B)).astype(np.int32)
         ax = rng.integers(0, d, (Tn, B)).astype(np.int32)
         host_fixed, agent_fixed = pol & (F_ALL | F_ZEIL), pol & (F_FIRST | F_LAST)
-        flags = pol | O.F_ACT_DISCRETE
+        # JAX semantics, and the torch ones (invalid action = no-op, ended games frozen) on every other policy
+        flags = pol | O.F_ACT_DISCRETE | (TORCH_FLAGS if (pol >> 8) % 2 else 0)
         o, g = x0, dev(x0)
         counts = []
         for t in range(Tn):

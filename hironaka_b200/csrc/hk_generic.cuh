@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                             if (!((mylive >> r) & 1u)) continue;
                             const int i = lane + 32 * r;
 #pragma unroll
-                            for (int k = 0; k < D; ++k) x[i * D + k] = __fdiv_rn(x[i * D + k], mx);
+                            for (int k = 0; k < D; ++k) {
+                                const float v = x[i * D + k];  // 0 / mx = 0: keep zeros (common after reposition) out of the divider
+                                x[i * D + k] = (v != 0.0f) ? __fdiv_rn(v, mx) : v;
+                            }
                         }
                     }
                 }
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
                         float v = Elem<T>::to_float(x[i * D + k]);
-                        v = resc ? __fdiv_rn(v, mx) : v;
+                        v = (resc && lv && v != 0.0f) ? __fdiv_rn(v, mx) : v;
                         f[i * D + k] = lv ? v : p.pad;
                     }
                 }

@@ -210,16 +210,47 @@ __device__ __forceinline__ uint32_t op_newton_rolled(T (&y)[K * D], uint32_t clm
 // rescale (float state): live entries / game max, max == 0 -> 1 (rescale_torch _torch_ops.py:136-146)
 template <int N, int D>
 __device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm) {
-    float mx = -1.0f;
+    float mx = -1.0f, mnpos = 3.0e38f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) mx = ((lm >> i) & 1u) ? fmaxf(mx, x[i * D + k]) : mx;
+        for (int k = 0; k < D; ++k) {
+            const float v = x[i * D + k];
+            const bool lv = (lm >> i) & 1u;
+            mx = lv ? fmaxf(mx, v) : mx;
+            mnpos = (lv && v > 0.0f) ? fminf(mnpos, v) : mnpos;
+        }
     }
     if (mx == 0.0f) mx = 1.0f;
     if (mx > 0.0f) {
+        // Dead rows are parked at +BIG and zeros are common after reposition; neither goes through
+        // the divider (0 / mx = 0 exactly, dead rows are rewritten with the padding value).
+        const GameDivider g = make_divider(mx, mnpos);
+        if (__all_sync(0xffffffffu, g.safe)) {  // warp-uniform choice of the division routine
 #pragma unroll
-        for (int i = 0; i < N * D; ++i) x[i] = __fdiv_rn(x[i], mx);
+            for (int i = 0; i < N; ++i) {
+                const bool lv = (lm >> i) & 1u;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float v = x[i * D + k];
+                    const bool use = lv && (v != 0.0f);
+                    const float q = divide_by_game_max(use ? v : mx, g);
+                    x[i * D + k] = use ? q : v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const bool lv = (lm >> i) & 1u;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float v = x[i * D + k];
+                    const bool use = lv && (v != 0.0f);
+                    const float q = divide_ieee(use ? v : mx, mx);
+                    x[i * D + k] = use ? q : v;
+                }
+            }
+        }
     }
 }
 
@@ -344,20 +375,35 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
         for (int q = 0; q < W; ++q) orow[q] = padf;
     }
     float f[K * D];
-    float mx = -1.0f;
+    float mx = -1.0f, mnpos = 3.0e38f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const float v = Elem<T>::to_float(y[k * D + c]);
+            const bool lv = (clm >> k) & 1u;
             f[k * D + c] = v;
-            mx = ((clm >> k) & 1u) ? fmaxf(mx, v) : mx;
+            mx = lv ? fmaxf(mx, v) : mx;
+            mnpos = (lv && v > 0.0f) ? fminf(mnpos, v) : mnpos;
         }
     }
     if (mx == 0.0f) mx = 1.0f;
     if ((flags & HK_F_OBS_RESCALE) && mx > 0.0f) {
+        const GameDivider g = make_divider(mx, mnpos);
+        const bool fast = __all_sync(0xffffffffu, g.safe);  // warp-uniform choice of the division routine
 #pragma unroll
-        for (int q = 0; q < K * D; ++q) f[q] = __fdiv_rn(f[q], mx);
+        for (int k = 0; k < K; ++k) {  // live, non-zero entries only (see op_rescale)
+            const bool lv = (clm >> k) & 1u;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const float v = f[k * D + c];
+                const bool use = lv && (v != 0.0f);
+                float q;
+                if (fast) q = divide_by_game_max(use ? v : mx, g);
+                else q = divide_ieee(use ? v : mx, mx);
+                f[k * D + c] = use ? q : v;
+            }
+        }
     }
     int rank[K];
     const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);

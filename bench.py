@@ -36,7 +36,7 @@ METRIC = "game_steps_per_sec"
 UNIT = "game-steps/s"
 N_POINTS, DIM, T_ROLLOUT, MAX_VALUE = 20, 3, 20, 20
 GAMES_PER_GPU = 1 << 20
-CPU_SAMPLE_GAMES = 1 << 19   # bounded sample of the C2 workload for the CPU arm (state 126 MB, ~1 s per 40 steps)
+CPU_SAMPLE_GAMES = int(os.environ.get("HK_BENCH_CPU_SAMPLE", 1 << 19))  # bounded sample of the C2 workload for the CPU arm (state 126 MB, ~1 s per 40 steps)
 MAX_RESIDENT_ROLLOUTS = 10  # distinct pre-generated batches; beyond K = 200 they are restored from pristine copies
 BYTES_PER_GAME_STEP = 8 * N_POINTS * DIM + 13  # int32 state r+w, 2 x int32 action, u8 done, f32 reward
 OPS_PER_GAME_STEP = N_POINTS * (N_POINTS - 1) * (DIM + 1) + 3 * N_POINTS * DIM + N_POINTS
@@ -497,8 +497,8 @@ def measure_secondary(torch, lib, C, dev):
 
     # C3: MCTS node expansion — latency per call at eval_batch_size 10/100/512 (N=20, d=3)
     lat = {}
-    for B in (10, 100, 512):
-        N, d, T = 20, 3, 20
+    for B, N in ((10, 20), (100, 20), (512, 20), (10, 5), (512, 5)):
+        d, T = 3, 20
         x, ha, ax = make(B, N, d, T, 20, 3, True)
         done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
         obs = torch.empty((B, N * d), dtype=torch.float32, device=dev)
@@ -518,7 +518,7 @@ def measure_secondary(torch, lib, C, dev):
                              C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, flags, -1.0, 1e8, gs)
             assert rc == 0
         graph_us = timed(lambda i: g.replay(), 2000) * 1e3
-        lat[str(B)] = {"stream_launch_us": stream_us, "graph_replay_us": graph_us}
+        lat[f"B={B},N={N}"] = {"stream_launch_us": stream_us, "graph_replay_us": graph_us}
     out["C3_step_with_features_us_per_call"] = lat
 
     # one-launch rollout (hk_rollout, T=20): the state is read and written once per 20 steps

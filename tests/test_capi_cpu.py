@@ -144,3 +144,19 @@ def test_rho_from_counts():
     rho = GameBatch.rho(2, torch.tensor([3, 6, 7]), 10)
     # details (compute_rho, jax_trainer.py:519-555): [2, 1, 3, 10-7=3] -> rho = (1+3+3) / (1*1 + 2*3 + 3*3)
     assert abs(rho - 7 / 16) < 1e-12
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` is the CPU arm (oracle C port on the host cores): it must run
+    without a GPU and print one JSON line with the contract's keys."""
+    import json
+    env = dict(os.environ, HK_BENCH_CPU_SAMPLE="4096")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "game_steps_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C2")
+    for k in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data"):
+        assert k in line

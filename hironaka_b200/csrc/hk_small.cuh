@@ -222,11 +222,15 @@ __device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm) {
         }
     }
     if (mx == 0.0f) mx = 1.0f;
-    if (mx > 0.0f) {
-        // Dead rows are parked at +BIG and zeros are common after reposition; neither goes through
-        // the divider (0 / mx = 0 exactly, dead rows are rewritten with the padding value).
-        const GameDivider g = make_divider(mx, mnpos);
-        if (__all_sync(0xffffffffu, g.safe)) {  // warp-uniform choice of the division routine
+    // Dead rows are parked at +BIG and zeros are common after reposition; neither goes through
+    // the divider (0 / mx = 0 exactly, dead rows are rewritten with the padding value).
+    // The choice of the division routine is warp-uniform; the vote is taken by ALL lanes, outside
+    // the per-game condition (a game without live rows has nothing to divide).
+    const bool act = mx > 0.0f;
+    const GameDivider g = make_divider(act ? mx : 1.0f, mnpos);
+    const bool fast = __all_sync(0xffffffffu, !act || g.safe);
+    if (act) {
+        if (fast) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const bool lv = (lm >> i) & 1u;
@@ -367,13 +371,8 @@ __device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
 template <typename T, int K, int D>
 __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm, const int (&slot)[K], uint32_t flags,
                                               float padf, float* orow, int W) {
-    // all padding first
-    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
-        const float4 pv = make_float4(padf, padf, padf, padf);
-        for (int q = 0; q < W / 4; ++q) reinterpret_cast<float4*>(orow)[q] = pv;
-    } else {
-        for (int q = 0; q < W; ++q) orow[q] = padf;
-    }
+    // The lane's obs row (W >= K*D floats) serves as scratch until the very end, when it is filled
+    // with the padding value and receives the live rows at their ranks.
     float f[K * D];
     float mx = -1.0f, mnpos = 3.0e38f;
 #pragma unroll
@@ -388,20 +387,38 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
         }
     }
     if (mx == 0.0f) mx = 1.0f;
-    if ((flags & HK_F_OBS_RESCALE) && mx > 0.0f) {
-        const GameDivider g = make_divider(mx, mnpos);
-        const bool fast = __all_sync(0xffffffffu, g.safe);  // warp-uniform choice of the division routine
+    if (flags & HK_F_OBS_RESCALE) {  // warp-uniform
+        // the vote on the division routine is taken by ALL lanes, outside the per-game condition
+        const bool act = mx > 0.0f;
+        const GameDivider g = make_divider(act ? mx : 1.0f, mnpos);
+        const bool fast = __all_sync(0xffffffffu, !act || g.safe);
+        if (fast) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {  // live, non-zero entries only (see op_rescale)
-            const bool lv = (clm >> k) & 1u;
+            for (int k = 0; k < K; ++k) {  // live, non-zero entries only (see op_rescale)
+                const bool lv = act && ((clm >> k) & 1u);
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const float v = f[k * D + c];
-                const bool use = lv && (v != 0.0f);
-                float q;
-                if (fast) q = divide_by_game_max(use ? v : mx, g);
-                else q = divide_ieee(use ? v : mx, mx);
-                f[k * D + c] = use ? q : v;
+                for (int c = 0; c < D; ++c) {
+                    const float v = f[k * D + c];
+                    const bool use = lv && (v != 0.0f);
+                    const float q = divide_by_game_max(use ? v : g.b, g);
+                    f[k * D + c] = use ? q : v;
+                }
+            }
+        } else {
+            // rare: some game of the warp has entries near the ends of the float range; the rows go
+            // through the scratch row and one out-of-line IEEE division loop
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool lv = act && ((clm >> k) & 1u);
+#pragma unroll
+                for (int c = 0; c < D; ++c) orow[k * D + c] = lv ? f[k * D + c] : 0.0f;
+            }
+            divide_row_ieee(orow, K * D, g.b);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool lv = act && ((clm >> k) & 1u);
+#pragma unroll
+                for (int c = 0; c < D; ++c) f[k * D + c] = lv ? orow[k * D + c] : f[k * D + c];
             }
         }
     }
@@ -411,26 +428,77 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
     const bool lexf = flags & HK_F_OBS_SORT_LEX_FIRST;
 #pragma unroll
     for (int k = 0; k < K; ++k) rank[k] = sorted ? 0 : slot[k];  // unsorted: every row stays in its slot
+    if (sorted) {
+        if constexpr (K <= 4) {
+            // tiny tier: all pairs in registers
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
+            for (int i = 0; i < K; ++i) {
 #pragma unroll
-        for (int j = i + 1; j < K; ++j) {
-            const bool both = sorted && (((clm >> i) & (clm >> j) & 1u) != 0);
-            // does row j sort strictly before row i?  (ties: lower slot first)
-            bool gt = f[j * D] > f[i * D];
-            if (lex) {  // last coordinate primary
+                for (int j = i + 1; j < K; ++j) {
+                    const bool both = ((clm >> i) & (clm >> j) & 1u) != 0;
+                    // does row j sort strictly before row i?  (ties: lower slot first)
+                    bool gt = f[j * D] > f[i * D];
+                    if (lex) {  // last coordinate primary
 #pragma unroll
-                for (int c = 1; c < D; ++c)
-                    gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
-            } else if (lexf) {  // coordinate 0 primary
-                gt = f[j * D + D - 1] > f[i * D + D - 1];
+                        for (int c = 1; c < D; ++c)
+                            gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
+                    } else if (lexf) {  // coordinate 0 primary
+                        gt = f[j * D + D - 1] > f[i * D + D - 1];
 #pragma unroll
-                for (int c = D - 2; c >= 0; --c)
-                    gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
+                        for (int c = D - 2; c >= 0; --c)
+                            gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
+                    }
+                    rank[i] += (both && gt) ? 1 : 0;
+                    rank[j] += (both && !gt) ? 1 : 0;
+                }
             }
-            rank[i] += (both && gt) ? 1 : 0;
-            rank[j] += (both && !gt) ? 1 : 0;
+        } else {
+            // Larger tiers: the competitor loop j is ROLLED (row j is re-read from the scratch row)
+            // and only the ranked rows k are unrolled.  The fully unrolled K^2/2 lexicographic
+            // compares of the 12/16/N-row tiers made this kernel 460 KB of SASS and
+            // instruction-fetch bound (ncu: icc hit rate 44-59 %).
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) orow[k * D + c] = f[k * D + c];
+            }
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+                if (!((clm >> j) & 1u)) continue;
+                float fj[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) fj[c] = orow[j * D + c];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    // does row j sort before row k?  strictly greater key, or equal key and lower slot
+                    bool gt = fj[0] > f[k * D];
+                    bool eq = fj[0] == f[k * D];
+                    if (lex) {
+#pragma unroll
+                        for (int c = 1; c < D; ++c) {
+                            gt = (fj[c] > f[k * D + c]) || ((fj[c] == f[k * D + c]) && gt);
+                            eq = eq && (fj[c] == f[k * D + c]);
+                        }
+                    } else if (lexf) {
+                        gt = fj[D - 1] > f[k * D + D - 1];
+                        eq = fj[D - 1] == f[k * D + D - 1];
+#pragma unroll
+                        for (int c = D - 2; c >= 0; --c) {
+                            gt = (fj[c] > f[k * D + c]) || ((fj[c] == f[k * D + c]) && gt);
+                            eq = eq && (fj[c] == f[k * D + c]);
+                        }
+                    }
+                    rank[k] += (gt || (eq && j < k)) ? 1 : 0;
+                }
+            }
         }
+    }
+    // all padding, then the live rows at their ranks
+    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
+        const float4 pv = make_float4(padf, padf, padf, padf);
+        for (int q = 0; q < W / 4; ++q) reinterpret_cast<float4*>(orow)[q] = pv;
+    } else {
+        for (int q = 0; q < W; ++q) orow[q] = padf;
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -462,9 +530,9 @@ __host__ __device__ constexpr int next_lower_tier(int K) { return K > 16 ? 16 : 
 // Runs steps [st, T) of one tile on K compact rows; returns the step index at which it stopped
 // (T, or earlier when every game of the warp fits the next lower tier).  The lane's game area in
 // shared memory (`row`) holds the current state on entry and on exit.
-template <typename T, int N, int D, int K, bool OBS, bool POLICY>
+template <typename T, int N, int D, int K, bool POLICY>
 __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, const T (&x)[N * D],
-                                          uint32_t lm, int st, bool& exceed, float* orow, int OW) {
+                                          uint32_t lm, int st, bool& exceed) {
     const long long B = p.B;
     const T padv = Elem<T>::pad(p.pad);
     const bool mutate = p.ops != 0;
@@ -556,17 +624,38 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             }
         }
     }
-    if constexpr (OBS) {
-        if (last && p.obs) {
-            if constexpr (K == N) {
+    return st;
+}
+
+// Observation features of the FINAL state of the tile, as a phase of its own after the steps: the
+// live rows are gathered again (their number has usually shrunk during the step, so the rank sort
+// runs on a smaller tier than the step did) and tier_features sorts them into the lane's obs row.
+template <typename T, int N, int D, int K>
+__device__ __forceinline__ void features_phase(const StepParams& p, const uint32_t* row, const T (&z)[N * D], uint32_t lm,
+                                               float* orow) {
+    T y[K * D];
+    int idx[K];
+    uint32_t clm = 0;
+    if constexpr (K == N) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) idx[k] = k;
-            }
-            tier_features<T, K, D>(y, clm, idx, p.flags, p.pad, orow, N * D);
+        for (int q = 0; q < N * D; ++q) y[q] = z[q];
+#pragma unroll
+        for (int k = 0; k < K; ++k) idx[k] = k;
+        clm = lm;
+    } else {
+        uint32_t m = lm;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool v = m != 0;
+            const int i = v ? (__ffs((int)m) - 1) : 0;
+            m &= m - 1;
+            idx[k] = i;
+            clm |= v ? (1u << k) : 0u;
+#pragma unroll
+            for (int c = 0; c < D; ++c) y[k * D + c] = x_row_value<T>(row, i * D + c);
         }
     }
-    (void)OW;
-    return st;
+    tier_features<T, K, D>(y, clm, idx, p.flags, p.pad, orow, N * D);
 }
 
 // ---- tile movement -------------------------------------------------------------------------------
@@ -684,20 +773,20 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
             };
             if (N > 4 && lmax <= 4) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 4 ? 4 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed);
             } else if (N > 8 && lmax <= 8) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 8 ? 8 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed);
             } else if (N > 12 && lmax <= 12) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 12 ? 12 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed);
                 normalised = normalised || (W % 4 == 0);
             } else if (N > 16 && lmax <= 16) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 16 ? 16 : N), OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed);
                 normalised = normalised || (W % 4 == 0);
             } else {
-                st = tier_steps<T, N, D, N, OBS, POLICY>(p, ls, row, x, lm, st, exceed, orow, OW);
+                st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed);
                 normalised = true;
             }
         } while (st < p.T);
@@ -725,6 +814,25 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         }
         if constexpr (OBS) {
             if (p.obs) {
+                {
+                    T z[W];
+                    load_game<T, W>(row, z);  // the new state, survivors scattered back to their slots
+                    if constexpr (Elem<T>::is_float) {
+#pragma unroll
+                        for (int q = 0; q < W; ++q) z[q] = z[q] + 0.0f;
+                    }
+                    const uint32_t zl = live_mask<T, N, D>(z);
+                    const int zmax = __reduce_max_sync(0xffffffffu, ls.valid ? __popc(zl) : 0);
+                    if (N > 4 && zmax <= 4) {
+                        features_phase<T, N, D, (N > 4 ? 4 : N)>(p, row, z, zl, orow);
+                    } else if (N > 8 && zmax <= 8) {
+                        features_phase<T, N, D, (N > 8 ? 8 : N)>(p, row, z, zl, orow);
+                    } else if (N > 12 && zmax <= 12) {
+                        features_phase<T, N, D, (N > 12 ? 12 : N)>(p, row, z, zl, orow);
+                    } else {
+                        features_phase<T, N, D, N>(p, row, z, zl, orow);
+                    }
+                }
                 if (p.obs_coord) {
                     const uint32_t ocm = ls.valid ? action_mask(load_action(p.obs_coord, ls.g, p.flags), p.flags) : 0u;
 #pragma unroll

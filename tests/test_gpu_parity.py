@@ -244,6 +244,24 @@ def test_random_features(hb, family, shape, dtype):
     assert np.array_equal(got[4], cport.features(exp_state, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE))
 
 
+@pytest.mark.parametrize("N", [5, 10, 20])
+def test_rescale_with_empty_games_in_a_warp(hb, N):
+    """Games without a live row sit next to live ones in the same warp: the per-game "anything to
+    divide?" condition differs between lanes, the warp-wide choice of the division routine must not
+    (regression: a vote taken under that condition let lanes run ahead of the obs-tile store)."""
+    rng = np.random.default_rng(N)
+    for B in (31, 64, 95):
+        x = random_state(rng, B, N, 3, max_value=9, dead_frac=0.3).astype(np.float32)
+        x[::3] = -1.0  # every third game is empty
+        x[1::7, 1:] = -1.0  # and some have a single point
+        for flags in (O.F_OBS_RESCALE, O.F_OBS_RESCALE | O.F_OBS_SORT_LEX, O.F_OBS_RESCALE | O.F_OBS_SORT_COORD0):
+            for ops_bits in (0, O.OP_RESCALE, O.OP_NEWTON | O.OP_RESCALE):
+                got = run_step(hb, x, None, None, ops_bits, flags, want_obs=True)
+                exp_state = cport.step(x, None, None, ops_bits, 0)[0] if ops_bits else x
+                assert np.array_equal(got[0], exp_state), (B, flags, ops_bits)
+                assert np.array_equal(got[4], cport.features(exp_state, flags)), (B, flags, ops_bits)
+
+
 F_ALL, F_ZEIL, F_FIRST, F_LAST = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 
 

@@ -13,15 +13,15 @@
 
 constexpr int N = 20, D = 3, T = 20;
 
-template <int WARPS, int STAGES>
+template <int WARPS, int STAGES, bool OBS = false>
 float launch(const hk::StepParams& p, cudaStream_t st, int sms, bool time_it, cudaEvent_t e0, cudaEvent_t e1) {
-    using L = hk::SmallLayout<N, D, false, WARPS, STAGES>;
-    auto k = hk::hk_small_kernel<int32_t, N, D, false, false, WARPS, STAGES>;
+    using L = hk::SmallLayout<N, D, OBS, WARPS, STAGES>;
+    auto k = hk::hk_small_kernel<int32_t, N, D, OBS, false, WARPS, STAGES>;
     static int per_sm = 0;
     if (!per_sm) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, WARPS * 32, L::SMEM_BYTES));
-        printf("  [W=%d S=%d] smem/CTA=%zu B, CTAs/SM=%d, warps/SM=%d\n", WARPS, STAGES, L::SMEM_BYTES, per_sm, per_sm * WARPS);
+        printf("  [W=%d S=%d OBS=%d] smem/CTA=%zu B, CTAs/SM=%d, warps/SM=%d\n", WARPS, STAGES, (int)OBS, L::SMEM_BYTES, per_sm, per_sm * WARPS);
     }
     long long ntiles = (p.B + 31) / 32;
     long long ctas = (ntiles + WARPS - 1) / WARPS;
@@ -34,7 +34,7 @@ float launch(const hk::StepParams& p, cudaStream_t st, int sms, bool time_it, cu
     return 0.f;
 }
 
-template <int WARPS, int STAGES>
+template <int WARPS, int STAGES, bool OBS = false>
 void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vector<int32_t>& ha, const std::vector<int32_t>& ax) {
     int sms = 148;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -42,6 +42,8 @@ void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vecto
     size_t sbytes = (size_t)B * N * D * 4;
     CK(cudaMalloc(&d_state, sbytes * R)); CK(cudaMalloc(&d_ha, (size_t)R * T * B * 4)); CK(cudaMalloc(&d_ax, (size_t)R * T * B * 4));
     CK(cudaMalloc(&d_done, B)); CK(cudaMalloc(&d_rew, (size_t)B * 4));
+    float* d_obs = nullptr;
+    if (OBS) CK(cudaMalloc(&d_obs, sbytes));
     CK(cudaMemcpy(d_state, pts.data(), sbytes * R, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ha, ha.data(), (size_t)R * T * B * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ax, ax.data(), (size_t)R * T * B * 4, cudaMemcpyHostToDevice));
@@ -53,22 +55,23 @@ void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vecto
     for (int r = 0; r < R; ++r) {
         int32_t* s = d_state + (size_t)r * B * N * D;
         p.in = s; p.out = s; p.ops = HK_OP_NEWTON | HK_OP_REPOSITION; p.flags = 0; p.host_action = nullptr; p.axis = nullptr; p.done = nullptr; p.reward = nullptr;
-        launch<WARPS, STAGES>(p, st, sms, true, e0, e1);
+        launch<WARPS, STAGES, false>(p, st, sms, true, e0, e1);
         CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); init_ms += ms;
         p.ops = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON; p.flags = HK_F_ACT_DISCRETE; p.done = d_done; p.reward = d_rew;
+        if (OBS) { p.obs = d_obs; p.flags |= HK_F_OBS_SORT_LEX | HK_F_OBS_RESCALE; }
         for (int t = 0; t < T; ++t) {
             p.host_action = d_ha + ((size_t)r * T + t) * B; p.axis = d_ax + ((size_t)r * T + t) * B;
-            launch<WARPS, STAGES>(p, st, sms, true, e0, e1);
+            launch<WARPS, STAGES, OBS>(p, st, sms, true, e0, e1);
             CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
             if (r > 0) by_step[t] += ms;  // rollout 0 is warm-up
         }
     }
     {   // floor of this data path: the same kernel with no op selected (load tile, store tile), and a plain D2D memcpy
-        p.ops = 0; p.flags = 0; p.host_action = nullptr; p.axis = nullptr; p.done = nullptr; p.reward = nullptr;
+        p.ops = 0; p.flags = 0; p.host_action = nullptr; p.axis = nullptr; p.done = nullptr; p.reward = nullptr; p.obs = nullptr;
         double cp = 0, mc = 0; float ms;
         for (int i = 0; i < 12; ++i) {
             int32_t* s = d_state + (size_t)(i % R) * B * N * D; p.in = s; p.out = s;
-            launch<WARPS, STAGES>(p, st, sms, true, e0, e1);
+            launch<WARPS, STAGES, false>(p, st, sms, true, e0, e1);
             CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); if (i >= 2) cp += ms;
         }
         for (int i = 0; i < 12; ++i) {
@@ -86,8 +89,8 @@ void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vecto
     unsigned long long cs = 1469598103934665603ull;
     for (size_t i = 0; i < out.size(); ++i) cs = (cs ^ (unsigned)out[i]) * 1099511628211ull;
     double tot = 0; for (int t = 0; t < T; ++t) { by_step[t] /= (R - 1); tot += by_step[t]; }
-    printf("W=%d S=%d: init %.1f us | mean/step %.2f us (%.3f of 6543.7 GB/s) | t0..t4: %.1f %.1f %.1f %.1f %.1f | t5..19 mean %.2f | checksum %016llx\n",
-           WARPS, STAGES, 1e3 * init_ms / R, 1e3 * tot / T, (double)B * 493 / (tot / T * 1e-3) / 6543.7e9,
+    printf("W=%d S=%d OBS=%d: init %.1f us | mean/step %.2f us (%.3f of 6543.7 GB/s) | t0..t4: %.1f %.1f %.1f %.1f %.1f | t5..19 mean %.2f | checksum %016llx\n",
+           WARPS, STAGES, (int)OBS, 1e3 * init_ms / R, 1e3 * tot / T, (double)B * (OBS ? 733 : 493) / (tot / T * 1e-3) / 6543.7e9,
            1e3 * by_step[0], 1e3 * by_step[1], 1e3 * by_step[2], 1e3 * by_step[3], 1e3 * by_step[4],
            1e3 * (tot - by_step[0] - by_step[1] - by_step[2] - by_step[3] - by_step[4]) / 15, cs);
     cudaFree(d_state); cudaFree(d_ha); cudaFree(d_ax); cudaFree(d_done); cudaFree(d_rew);

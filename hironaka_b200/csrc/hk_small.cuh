@@ -363,7 +363,8 @@ __device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
     return v;
 }
 
-// Observation features from the compact rows: optional rescale, stable descending rank sort
+// Observation features from the compact rows of the smallest tier (the steady state of a rollout),
+// everything in registers: optional rescale, stable descending rank sort
 // among the LIVE rows only (dead rows all equal the padding value, which is below every live key,
 // so they fill the tail of the observation in any stable order), scattered into the lane's row of
 // the obs tile.  (TensorPoints.get_features tensor_points.py:72-74; order_and_rescale
@@ -371,6 +372,7 @@ __device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
 template <typename T, int K, int D>
 __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm, const int (&slot)[K], uint32_t flags,
                                               float padf, float* orow, int W) {
+    static_assert(K <= 4, "tiers above 4 rows go through features_rolled");
     // The lane's obs row (W >= K*D floats) serves as scratch until the very end, when it is filled
     // with the padding value and receives the live rows at their ranks.
     float f[K * D];
@@ -429,8 +431,8 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
 #pragma unroll
     for (int k = 0; k < K; ++k) rank[k] = sorted ? 0 : slot[k];  // unsorted: every row stays in its slot
     if (sorted) {
-        if constexpr (K <= 4) {
-            // tiny tier: all pairs in registers
+        {
+            // all pairs in registers
 #pragma unroll
             for (int i = 0; i < K; ++i) {
 #pragma unroll
@@ -450,45 +452,6 @@ __device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm,
                     }
                     rank[i] += (both && gt) ? 1 : 0;
                     rank[j] += (both && !gt) ? 1 : 0;
-                }
-            }
-        } else {
-            // Larger tiers: the competitor loop j is ROLLED (row j is re-read from the scratch row)
-            // and only the ranked rows k are unrolled.  The fully unrolled K^2/2 lexicographic
-            // compares of the 12/16/N-row tiers made this kernel 460 KB of SASS and
-            // instruction-fetch bound (ncu: icc hit rate 44-59 %).
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) orow[k * D + c] = f[k * D + c];
-            }
-#pragma unroll 1
-            for (int j = 0; j < K; ++j) {
-                if (!((clm >> j) & 1u)) continue;
-                float fj[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) fj[c] = orow[j * D + c];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    // does row j sort before row k?  strictly greater key, or equal key and lower slot
-                    bool gt = fj[0] > f[k * D];
-                    bool eq = fj[0] == f[k * D];
-                    if (lex) {
-#pragma unroll
-                        for (int c = 1; c < D; ++c) {
-                            gt = (fj[c] > f[k * D + c]) || ((fj[c] == f[k * D + c]) && gt);
-                            eq = eq && (fj[c] == f[k * D + c]);
-                        }
-                    } else if (lexf) {
-                        gt = fj[D - 1] > f[k * D + D - 1];
-                        eq = fj[D - 1] == f[k * D + D - 1];
-#pragma unroll
-                        for (int c = D - 2; c >= 0; --c) {
-                            gt = (fj[c] > f[k * D + c]) || ((fj[c] == f[k * D + c]) && gt);
-                            eq = eq && (fj[c] == f[k * D + c]);
-                        }
-                    }
-                    rank[k] += (gt || (eq && j < k)) ? 1 : 0;
                 }
             }
         }
@@ -658,6 +621,216 @@ __device__ __forceinline__ void features_phase(const StepParams& p, const uint32
     tier_features<T, K, D>(y, clm, idx, p.flags, p.pad, orow, N * D);
 }
 
+// Observation features for more than 4 live rows: ONE rolled, out-of-line routine for every tier.
+// Unrolled per-tier versions (gather, rescale, K^2/2 lexicographic compares, scatter for K = 8, 12,
+// 20) made the step+features kernel 240-460 KB of SASS; with the warps of an SM in different tiers
+// it was instruction-fetch bound (ncu: icc hit rate 44-59 %, stall no_instruction).  Here the rows
+// are walked in loops whose trip count is the warp's maximum live count `zmax`:
+//   phase 0  per live row: game max / min-positive, and one 64-bit sort key
+//            (live bit | coordinates in sort order, 19 bits each | 31 - k) into the scratch row;
+//   phase 1  ranks by counting greater keys, four ranked rows per pass over the competitors; the
+//            ranks are packed 5 bits each into two registers;
+//   phase 2  the scratch row is filled with the padding value and every live row is read again from
+//            the state tile, rescaled and written at its rank.
+// Keys of distinct rows are distinct (the low bits break ties towards the lower slot: a stable
+// sort), dead entries sort below every live row, and the order of the raw integers is the order
+// of the rescaled values (RN division by a positive constant is strictly monotonic on distinct
+// integers below 2^23).  When some live value of the warp's games is not an integer below 2^19
+// (e.g. a rescaled float state) the rows are compared as rescaled floats instead (warp-uniform vote).
+// `skew` (0 .. 3, from the lane and the row stride) makes the key accesses bank-conflict free.
+template <typename T, int N, int D>
+__device__ __noinline__ void features_rolled(const uint32_t* row, uint32_t lm, int zmax, uint32_t flags, float padf,
+                                             float* orow, int skew) {
+    static_assert(N <= 24 && D >= 2, "ranks are packed 5 bits each into two 64-bit registers; the scratch row holds 2N+8 words");
+    constexpr int W = N * D;
+    constexpr bool CAN_PACK = (D * 19 + 7 <= 64);
+    constexpr int HI = N + 4;  // high key words after the low ones (+ the largest skew)
+    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
+    const bool lex = flags & HK_F_OBS_SORT_LEX;
+    const bool lexf = flags & HK_F_OBS_SORT_LEX_FIRST;
+    uint32_t* ks = reinterpret_cast<uint32_t*>(orow);
+
+    // ---- phase 0 ----
+    float mx = -1.0f, mnpos = 3.0e38f;
+    bool packable = CAN_PACK;
+    {
+        uint32_t m = lm;
+#pragma unroll 1
+        for (int k = 0; k < zmax; ++k) {
+            const bool v = m != 0;
+            const int i = v ? (__ffs((int)m) - 1) : 0;
+            m &= m - 1;
+            uint32_t iv[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const T val = x_row_value<T>(row, i * D + c);
+                const float fv = Elem<T>::to_float(val);
+                if constexpr (Elem<T>::is_float) {
+                    const int q = __float2int_rz(val);
+                    iv[c] = (uint32_t)q;
+                    packable = packable && (!v || ((float)q == val));
+                } else {
+                    iv[c] = (uint32_t)val;
+                }
+                packable = packable && (!v || iv[c] < (1u << 19));
+                mx = v ? fmaxf(mx, fv) : mx;
+                mnpos = (v && fv > 0.0f) ? fminf(mnpos, fv) : mnpos;
+            }
+            if constexpr (CAN_PACK) {
+                uint64_t q = 0;
+                if (lex) {  // last coordinate primary
+#pragma unroll
+                    for (int c = D - 1; c >= 0; --c) q = (q << 19) | (iv[c] & 0x7ffffu);
+                } else if (lexf) {  // coordinate 0 primary
+#pragma unroll
+                    for (int c = 0; c < D; ++c) q = (q << 19) | (iv[c] & 0x7ffffu);
+                } else {
+                    q = iv[0] & 0x7ffffu;
+                }
+                const uint64_t key = v ? ((1ull << 62) | (q << 5) | (uint32_t)(31 - k)) : (uint64_t)(31 - k);
+                ks[skew + k] = (uint32_t)key;
+                ks[HI + skew + k] = (uint32_t)(key >> 32);
+            }
+        }
+    }
+    if (mx == 0.0f) mx = 1.0f;
+    // both votes are taken by ALL lanes, outside any per-game condition
+    const bool act = (flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+    const GameDivider g = make_divider(act ? mx : 1.0f, mnpos);
+    const bool fast = __all_sync(0xffffffffu, !act || g.safe);
+    packable = __all_sync(0xffffffffu, packable);
+    auto rescaled = [&](float v) -> float {
+        const bool use = act && (v != 0.0f);  // 0 / mx = 0 exactly
+        const float a = use ? v : g.b;
+        const float q = fast ? divide_by_game_max(a, g) : __fdiv_rn(a, g.b);
+        return use ? q : v;
+    };
+
+    // ---- phase 1 ----
+    uint64_t rk0 = 0, rk1 = 0;  // rank of compact row k: 5 bits at 5k (k < 12) or 5(k - 12)
+    if (sorted) {
+        if (packable) {
+#pragma unroll 1
+            for (int kb = 0; kb < zmax; kb += 4) {
+                uint64_t key[4];
+                int r[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = kb + q < zmax;
+                    const uint32_t lo = ok ? ks[skew + kb + q] : 0xffffffffu;
+                    const uint32_t hi = ok ? ks[HI + skew + kb + q] : 0xffffffffu;
+                    key[q] = ((uint64_t)hi << 32) | lo;
+                    r[q] = 0;
+                }
+#pragma unroll 1
+                for (int j = 0; j < zmax; ++j) {
+                    const uint64_t kj = ((uint64_t)ks[HI + skew + j] << 32) | ks[skew + j];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) r[q] += (kj > key[q]) ? 1 : 0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int kk = kb + q;
+                    if (kk < zmax) {
+                        if (kk < 12) rk0 |= (uint64_t)r[q] << (5 * kk);
+                        else rk1 |= (uint64_t)r[q] << (5 * (kk - 12));
+                    }
+                }
+            }
+        } else {
+            // rescaled float rows into the scratch row (dead entries negative: below every live row)
+            uint32_t m = lm;
+#pragma unroll 1
+            for (int k = 0; k < zmax; ++k) {
+                const bool v = m != 0;
+                const int i = v ? (__ffs((int)m) - 1) : 0;
+                m &= m - 1;
+#pragma unroll
+                for (int c = 0; c < D; ++c)
+                    orow[k * D + c] = v ? rescaled(Elem<T>::to_float(x_row_value<T>(row, i * D + c))) : -1.0f;
+            }
+#pragma unroll 1
+            for (int kb = 0; kb < zmax; kb += 4) {
+                float fk[4][D];
+                int r[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = kb + q < zmax;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) fk[q][c] = ok ? orow[(kb + q) * D + c] : 0.0f;
+                    r[q] = 0;
+                }
+#pragma unroll 1
+                for (int j = 0; j < zmax; ++j) {
+                    float fj[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) fj[c] = orow[j * D + c];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // does row j sort before row kb+q?  strictly greater key, or equal key and lower slot
+                        bool gt = fj[0] > fk[q][0];
+                        bool eq = fj[0] == fk[q][0];
+                        if (lex) {
+#pragma unroll
+                            for (int c = 1; c < D; ++c) {
+                                gt = (fj[c] > fk[q][c]) || ((fj[c] == fk[q][c]) && gt);
+                                eq = eq && (fj[c] == fk[q][c]);
+                            }
+                        } else if (lexf) {
+                            gt = fj[D - 1] > fk[q][D - 1];
+                            eq = fj[D - 1] == fk[q][D - 1];
+#pragma unroll
+                            for (int c = D - 2; c >= 0; --c) {
+                                gt = (fj[c] > fk[q][c]) || ((fj[c] == fk[q][c]) && gt);
+                                eq = eq && (fj[c] == fk[q][c]);
+                            }
+                        }
+                        r[q] += (gt || (eq && j < kb + q)) ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int kk = kb + q;
+                    if (kk < zmax) {
+                        if (kk < 12) rk0 |= (uint64_t)r[q] << (5 * kk);
+                        else rk1 |= (uint64_t)r[q] << (5 * (kk - 12));
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- phase 2: all padding, then the live rows at their ranks ----
+    if constexpr ((W & 3) == 0) {
+        if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) {
+            const float4 pv = make_float4(padf, padf, padf, padf);
+#pragma unroll 1
+            for (int q = 0; q < W / 4; ++q) reinterpret_cast<float4*>(orow)[q] = pv;
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < W; ++q) orow[q] = padf;
+        }
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < W; ++q) orow[q] = padf;
+    }
+    {
+        uint32_t m = lm;
+#pragma unroll 1
+        for (int k = 0; k < zmax; ++k) {
+            const bool v = m != 0;
+            const int i = v ? (__ffs((int)m) - 1) : 0;
+            m &= m - 1;
+            const int rank = !sorted ? i : (int)(((k < 12) ? (rk0 >> (5 * k)) : (rk1 >> (5 * (k - 12)))) & 31u);
+            if (v) {
+#pragma unroll
+                for (int c = 0; c < D; ++c)
+                    orow[rank * D + c] = rescaled(Elem<T>::to_float(x_row_value<T>(row, i * D + c)));
+            }
+        }
+    }
+}
+
 // ---- tile movement -------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
@@ -823,14 +996,16 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                     }
                     const uint32_t zl = live_mask<T, N, D>(z);
                     const int zmax = __reduce_max_sync(0xffffffffu, ls.valid ? __popc(zl) : 0);
-                    if (N > 4 && zmax <= 4) {
-                        features_phase<T, N, D, (N > 4 ? 4 : N)>(p, row, z, zl, orow);
-                    } else if (N > 8 && zmax <= 8) {
-                        features_phase<T, N, D, (N > 8 ? 8 : N)>(p, row, z, zl, orow);
-                    } else if (N > 12 && zmax <= 12) {
-                        features_phase<T, N, D, (N > 12 ? 12 : N)>(p, row, z, zl, orow);
-                    } else {
+                    if constexpr (N <= 4) {
                         features_phase<T, N, D, N>(p, row, z, zl, orow);
+                    } else {
+                        if (zmax <= 4) {  // the steady state of a rollout: everything in registers
+                            features_phase<T, N, D, 4>(p, row, z, zl, orow);
+                        } else {
+                            // rows of stride OW words: lanes 32/g apart share a bank (g = largest power of two in OW)
+                            const int gpow = (OW & -OW) > 32 ? 32 : (OW & -OW);
+                            features_rolled<T, N, D>(row, zl, zmax, p.flags, p.pad, orow, (lane * gpow) >> 5);
+                        }
                     }
                 }
                 if (p.obs_coord) {

@@ -229,12 +229,19 @@ def test_random_features(hb, family, shape, dtype):
     rng = np.random.default_rng(N * 7 + d)
     x = random_state(rng, B, N, d, max_value=6, dead_frac=0.3).astype(dtype)  # small range => many key ties
     cm = rng.integers(0, 2 ** d, B)
-    for flags in (0, O.F_OBS_RESCALE, O.F_OBS_SORT_COORD0, O.F_OBS_SORT_LEX, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE,
-                  O.F_OBS_SORT_COORD0 | O.F_OBS_RESCALE):
-        for oc in (None, cm):
-            got = run_step(hb, x, None, None, 0, flags, want_obs=True, obs_coord=oc)[4]
-            exp = cport.features(x, flags, obs_coord=oc)
-            assert np.array_equal(got, exp), (flags, oc is None)
+    # the thread-per-game kernel ranks rows by packed integer keys while every live value is an integer
+    # below 2^19 and by float compares otherwise: cover both, and the border between them
+    variants = [x, np.where(x > 0, x * 80000, x).astype(dtype), np.where(x > 0, x * 100000, x).astype(dtype)]
+    if dtype == np.float32:
+        variants.append(np.where(x > 0, x + 0.5, x).astype(dtype))
+        variants.append(np.where(x > 0, x / 8.0, x).astype(dtype))
+    for vi, xv in enumerate(variants):
+        for flags in (0, O.F_OBS_RESCALE, O.F_OBS_SORT_COORD0, O.F_OBS_SORT_LEX, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE,
+                      O.F_OBS_SORT_COORD0 | O.F_OBS_RESCALE, 1 << 12):  # 1 << 12 = HK_F_OBS_SORT_LEX_FIRST (C port only)
+            for oc in (None, cm):
+                got = run_step(hb, xv, None, None, 0, flags, want_obs=True, obs_coord=oc)[4]
+                exp = cport.features(xv, flags, obs_coord=oc)
+                assert np.array_equal(got, exp), (vi, flags, oc is None)
     # fused: features of the state AFTER the step
     ha, ax = rng.integers(0, 2 ** d, B), rng.integers(0, d, B)
     ops_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON

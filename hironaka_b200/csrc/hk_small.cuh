@@ -363,115 +363,6 @@ __device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
     return v;
 }
 
-// Observation features from the compact rows of the smallest tier (the steady state of a rollout),
-// everything in registers: optional rescale, stable descending rank sort
-// among the LIVE rows only (dead rows all equal the padding value, which is below every live key,
-// so they fill the tail of the observation in any stable order), scattered into the lane's row of
-// the obs tile.  (TensorPoints.get_features tensor_points.py:72-74; order_and_rescale
-// util.py:186-196.)  Compact order is slot order, so ties resolve to the lowest slot first.
-template <typename T, int K, int D>
-__device__ __forceinline__ void tier_features(const T (&y)[K * D], uint32_t clm, const int (&slot)[K], uint32_t flags,
-                                              float padf, float* orow, int W) {
-    static_assert(K <= 4, "tiers above 4 rows go through features_rolled");
-    // The lane's obs row (W >= K*D floats) serves as scratch until the very end, when it is filled
-    // with the padding value and receives the live rows at their ranks.
-    float f[K * D];
-    float mx = -1.0f, mnpos = 3.0e38f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            const float v = Elem<T>::to_float(y[k * D + c]);
-            const bool lv = (clm >> k) & 1u;
-            f[k * D + c] = v;
-            mx = lv ? fmaxf(mx, v) : mx;
-            mnpos = (lv && v > 0.0f) ? fminf(mnpos, v) : mnpos;
-        }
-    }
-    if (mx == 0.0f) mx = 1.0f;
-    if (flags & HK_F_OBS_RESCALE) {  // warp-uniform
-        // the vote on the division routine is taken by ALL lanes, outside the per-game condition
-        const bool act = mx > 0.0f;
-        const GameDivider g = make_divider(act ? mx : 1.0f, mnpos);
-        const bool fast = __all_sync(0xffffffffu, !act || g.safe);
-        if (fast) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {  // live, non-zero entries only (see op_rescale)
-                const bool lv = act && ((clm >> k) & 1u);
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const float v = f[k * D + c];
-                    const bool use = lv && (v != 0.0f);
-                    const float q = divide_by_game_max(use ? v : g.b, g);
-                    f[k * D + c] = use ? q : v;
-                }
-            }
-        } else {
-            // rare: some game of the warp has entries near the ends of the float range; the rows go
-            // through the scratch row and one out-of-line IEEE division loop
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const bool lv = act && ((clm >> k) & 1u);
-#pragma unroll
-                for (int c = 0; c < D; ++c) orow[k * D + c] = lv ? f[k * D + c] : 0.0f;
-            }
-            divide_row_ieee(orow, K * D, g.b);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const bool lv = act && ((clm >> k) & 1u);
-#pragma unroll
-                for (int c = 0; c < D; ++c) f[k * D + c] = lv ? orow[k * D + c] : f[k * D + c];
-            }
-        }
-    }
-    int rank[K];
-    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
-    const bool lex = flags & HK_F_OBS_SORT_LEX;
-    const bool lexf = flags & HK_F_OBS_SORT_LEX_FIRST;
-#pragma unroll
-    for (int k = 0; k < K; ++k) rank[k] = sorted ? 0 : slot[k];  // unsorted: every row stays in its slot
-    if (sorted) {
-        {
-            // all pairs in registers
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-#pragma unroll
-                for (int j = i + 1; j < K; ++j) {
-                    const bool both = ((clm >> i) & (clm >> j) & 1u) != 0;
-                    // does row j sort strictly before row i?  (ties: lower slot first)
-                    bool gt = f[j * D] > f[i * D];
-                    if (lex) {  // last coordinate primary
-#pragma unroll
-                        for (int c = 1; c < D; ++c)
-                            gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
-                    } else if (lexf) {  // coordinate 0 primary
-                        gt = f[j * D + D - 1] > f[i * D + D - 1];
-#pragma unroll
-                        for (int c = D - 2; c >= 0; --c)
-                            gt = (f[j * D + c] > f[i * D + c]) || ((f[j * D + c] == f[i * D + c]) && gt);
-                    }
-                    rank[i] += (both && gt) ? 1 : 0;
-                    rank[j] += (both && !gt) ? 1 : 0;
-                }
-            }
-        }
-    }
-    // all padding, then the live rows at their ranks
-    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0)) {
-        const float4 pv = make_float4(padf, padf, padf, padf);
-        for (int q = 0; q < W / 4; ++q) reinterpret_cast<float4*>(orow)[q] = pv;
-    } else {
-        for (int q = 0; q < W; ++q) orow[q] = padf;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if ((clm >> k) & 1u) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) orow[rank[k] * D + c] = f[k * D + c];
-        }
-    }
-}
-
 // ---- compacted tiers ------------------------------------------------------------------------------
 // Under real play few of the N slots are live (mean 6 of 20 after the root filter, 3 after two
 // steps), and the O(K^2 d) filter only needs the live rows.  Each warp therefore picks a tier
@@ -590,38 +481,147 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
     return st;
 }
 
-// Observation features of the FINAL state of the tile, as a phase of its own after the steps: the
-// live rows are gathered again (their number has usually shrunk during the step, so the rank sort
-// runs on a smaller tier than the step did) and tier_features sorts them into the lane's obs row.
-template <typename T, int N, int D, int K>
-__device__ __forceinline__ void features_phase(const StepParams& p, const uint32_t* row, const T (&z)[N * D], uint32_t lm,
-                                               float* orow) {
-    T y[K * D];
-    int idx[K];
-    uint32_t clm = 0;
-    if constexpr (K == N) {
-#pragma unroll
-        for (int q = 0; q < N * D; ++q) y[q] = z[q];
-#pragma unroll
-        for (int k = 0; k < K; ++k) idx[k] = k;
-        clm = lm;
-    } else {
-        uint32_t m = lm;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const bool v = m != 0;
-            const int i = v ? (__ffs((int)m) - 1) : 0;
-            m &= m - 1;
-            idx[k] = i;
-            clm |= v ? (1u << k) : 0u;
-#pragma unroll
-            for (int c = 0; c < D; ++c) y[k * D + c] = x_row_value<T>(row, i * D + c);
-        }
+// Descending sort of N 32-bit keys in registers by a merge-exchange network (tools/gen_sortnet.py):
+// one compare-exchange is two min/max instructions, there is no branch and no memory access.
+template <int N>
+__device__ __forceinline__ void sort_keys_desc(uint32_t (&k)[N]) {
+#define HK_CE(i, j)                   \
+    {                                 \
+        const uint32_t a_ = k[i], b_ = k[j]; \
+        k[i] = max(a_, b_);           \
+        k[j] = min(a_, b_);           \
     }
-    tier_features<T, K, D>(y, clm, idx, p.flags, p.pad, orow, N * D);
+#include "hk_sortnet.inc"
+#undef HK_CE
 }
 
-// Observation features for more than 4 live rows: ONE rolled, out-of-line routine for every tier.
+// Observation features, fast path: every slot of the game becomes ONE
+// 32-bit key that holds the whole row -- the coordinates in sort order, 27/D bits each, and the
+// slot tag N - i (5 bits; lower slots sort first, so the sort is stable and keys of live rows are
+// distinct and non-zero) -- dead slots get key 0.  The N keys are sorted in registers by a
+// sorting network and the observation rows are DECODED from the sorted keys, rescaled and stored
+// 16 bytes at a time: no gather, no rank counting, no loop, no shared-memory scratch.  Where the
+// tag sits depends on the order: below all coordinates for the lexicographic orders, right
+// below the primary coordinate for the coordinate-0 order (the remaining coordinates then ride
+// along without influencing the order).  Unsorted features skip the network (slot order).
+// Valid when every live value of the warp's games is an integer below 2^(27/D); the routine votes
+// and returns false (warp-uniform) otherwise, and the caller falls back to features_rolled.
+// The order of the raw integers is the order of the rescaled values (RN division by a positive
+// constant is strictly monotonic on distinct integers below 2^23).
+template <typename T, int N, int D>
+__device__ __forceinline__ bool features_network(const T (&z)[N * D], uint32_t lm, int zmax, uint32_t flags, float padf,
+                                                 float* orow) {
+    static_assert(N <= 31 && D >= 2 && D <= 6, "5 tag bits, at least 4 bits per coordinate");
+    constexpr int W = N * D;
+    constexpr int BITS = 27 / D;
+    constexpr uint32_t FMASK = (1u << BITS) - 1u;
+    const bool sorted = flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
+    const bool lex = flags & HK_F_OBS_SORT_LEX;  // last coordinate primary: field c holds coordinate D-1-c
+    const bool coord0 = !lex && !(flags & HK_F_OBS_SORT_LEX_FIRST);
+
+    // integer view of the state, its maximum over live rows (unsigned: a negative entry in a live
+    // row disqualifies the game), and for float state the integrality of every live value
+    uint32_t iv[W];
+    uint32_t umax = 0;
+    bool packable = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const bool lv = (lm >> i) & 1u;
+        uint32_t rmax = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            if constexpr (Elem<T>::is_float) {
+                const int q = __float2int_rz(z[i * D + c]);
+                packable = packable && (!lv || ((float)q == z[i * D + c]));
+                iv[i * D + c] = (uint32_t)q;
+            } else {
+                iv[i * D + c] = (uint32_t)z[i * D + c];
+            }
+            rmax = max(rmax, iv[i * D + c]);
+        }
+        umax = lv ? max(umax, rmax) : umax;
+    }
+    packable = packable && (umax <= FMASK);
+    if (!__all_sync(0xffffffffu, packable)) return false;
+
+    // field shifts (warp-uniform): field 0 on top, the tag below everything or right below field 0
+    uint32_t sh[D];
+    sh[0] = 5 + (D - 1) * BITS;
+#pragma unroll
+    for (int c = 1; c < D; ++c) sh[c] = (coord0 ? 0 : 5) + (D - 1 - c) * BITS;
+    const uint32_t tag_sh = coord0 ? (D - 1) * BITS : 0;
+
+    uint32_t key[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        uint32_t q = (uint32_t)(N - i) << tag_sh;
+#pragma unroll
+        for (int c = 0; c < D; ++c) q |= (lex ? iv[i * D + (D - 1 - c)] : iv[i * D + c]) << sh[c];
+        key[i] = ((lm >> i) & 1u) ? q : 0u;
+    }
+    if (sorted) sort_keys_desc<N>(key);
+
+    // The sorted keys go to the TAIL of the lane's obs row (words W-N .. W-1) and the rows are decoded
+    // from there in a rolled loop, four rows (= D 16-byte stores) per trip, so that the decode exists
+    // once in the code instead of N*D times.  Writing rows 4t .. 4t+3 (words below 4 D (t+1))
+    // overwrites only key words that have been read: key j sits at word W-N+j, so the keys hit are
+    // j < 4 D (t+1) - (W-N) = 4(t+1) + (D-1)(4(t+1) - N) <= 4(t+1) for every trip but the last
+    // (4(t+1) <= N), and the last trip has read all remaining keys before it writes.
+    uint32_t* ks = reinterpret_cast<uint32_t*>(orow) + (W - N);
+    const bool vec = (reinterpret_cast<uintptr_t>(orow) & 15u) == 0;
+    if (N % 4 == 0 && (W - N) % 4 == 0 && vec) {
+#pragma unroll
+        for (int q = 0; q + 3 < N; q += 4) *reinterpret_cast<uint4*>(ks + q) = make_uint4(key[q], key[q + 1], key[q + 2], key[q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < N; ++q) ks[q] = key[q];
+    }
+    // rescale by the game maximum (max == 0 -> 1); the fast division is always safe here
+    // (divisor and dividends are integers in [1, 2^BITS))
+    const bool resc = flags & HK_F_OBS_RESCALE;
+    const GameDivider g = make_divider(umax == 0 ? 1.0f : (float)umax, 1.0f);
+#pragma unroll 1
+    for (int r0 = 0; r0 < N; r0 += 4) {
+        uint32_t kq[4];
+        if (N % 4 == 0 && (W - N) % 4 == 0 && vec) {
+            const uint4 t = *reinterpret_cast<const uint4*>(ks + r0);
+            kq[0] = t.x, kq[1] = t.y, kq[2] = t.z, kq[3] = t.w;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) kq[r] = (r0 + r < N) ? ks[r0 + r] : 0u;
+        }
+        float v[4 * D];
+        if (r0 < zmax || !sorted) {  // groups past the warp's live maximum are all padding
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) {  // coordinate c of the row held by key kq[r]
+                    const uint32_t fld = (kq[r] >> (lex ? sh[D - 1 - c] : sh[c])) & FMASK;
+                    const float x = (float)fld;
+                    const bool use = resc && (fld != 0);
+                    const float q = divide_by_game_max(use ? x : g.b, g);
+                    v[r * D + c] = (kq[r] == 0) ? padf : (use ? q : x);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4 * D; ++q) v[q] = padf;
+        }
+        if (N % 4 == 0 && vec) {
+#pragma unroll
+            for (int q = 0; q < D; ++q)
+                reinterpret_cast<float4*>(orow + r0 * D)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4 * D; ++q) {
+                if (r0 * D + q < W) orow[r0 * D + q] = v[q];
+            }
+        }
+    }
+    return true;
+}
+
+// Observation features, general path: ONE rolled, out-of-line routine for every live count.
 // Unrolled per-tier versions (gather, rescale, K^2/2 lexicographic compares, scatter for K = 8, 12,
 // 20) made the step+features kernel 240-460 KB of SASS; with the warps of an SM in different tiers
 // it was instruction-fetch bound (ncu: icc hit rate 44-59 %, stall no_instruction).  Here the rows
@@ -996,16 +996,16 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                     }
                     const uint32_t zl = live_mask<T, N, D>(z);
                     const int zmax = __reduce_max_sync(0xffffffffu, ls.valid ? __popc(zl) : 0);
-                    if constexpr (N <= 4) {
-                        features_phase<T, N, D, N>(p, row, z, zl, orow);
-                    } else {
-                        if (zmax <= 4) {  // the steady state of a rollout: everything in registers
-                            features_phase<T, N, D, 4>(p, row, z, zl, orow);
-                        } else {
-                            // rows of stride OW words: lanes 32/g apart share a bank (g = largest power of two in OW)
-                            const int gpow = (OW & -OW) > 32 ? 32 : (OW & -OW);
-                            features_rolled<T, N, D>(row, zl, zmax, p.flags, p.pad, orow, (lane * gpow) >> 5);
-                        }
+                    // Observation features of the FINAL state of the tile, as a phase of its own after the
+                    // steps.  Every warp takes the same route here whatever its live counts (sorting
+                    // network; the rolled routine only when values do not pack): per-tier variants made
+                    // the warps of an SM execute different code and the kernel instruction-fetch bound.
+                    bool built = false;
+                    if constexpr (D <= 6) built = features_network<T, N, D>(z, zl, zmax, p.flags, p.pad, orow);
+                    if (!built) {
+                        // rows of stride OW words: lanes 32/g apart share a bank (g = largest power of two in OW)
+                        const int gpow = (OW & -OW) > 32 ? 32 : (OW & -OW);
+                        features_rolled<T, N, D>(row, zl, zmax, p.flags, p.pad, orow, (lane * gpow) >> 5);
                     }
                 }
                 if (p.obs_coord) {

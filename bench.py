@@ -495,6 +495,42 @@ def measure_secondary(torch, lib, C, dev):
                  "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
                          "dense count; the dense count is what the root filter (64 live points) executes"}
 
+    # C2 with the fused host observation (kernel (c) of the north star): step + done/reward + features in one launch
+    try:
+        B, N, d, T = GAMES_PER_GPU, N_POINTS, DIM, T_ROLLOUT
+        x, ha, ax = make(B, N, d, T, MAX_VALUE, 11, True)
+        done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+        obs = torch.empty((B, N * d), dtype=torch.float32, device=dev)
+        pristine = x.clone()
+        oflags = C.HK_F_ACT_DISCRETE | C.HK_F_OBS_SORT_LEX | C.HK_F_OBS_RESCALE
+        per = []
+        for rep in range(4):
+            x.copy_(pristine)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+            ev[0].record()
+            for t in range(T):
+                rc = lib.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(),
+                                 rew.data_ptr(), None, obs.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32,
+                                 C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, oflags, -1.0, 1e8, stream)
+                assert rc == 0
+                ev[t + 1].record()
+            torch.cuda.synchronize()
+            if rep:
+                per.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
+        per = np.mean(np.array(per), axis=0)
+        ms = float(per.mean())
+        bytes_obs = 8 * N * d + 13 + 4 * N * d
+        out["C2_step_with_features"] = {
+            "workload": "C2, 1 Mi games, random play T=20; one launch per step = shift + reposition + newton + done/reward + "
+                        "host observation (rescaled, lexicographically sorted f32 rows)",
+            "kernel": "hk::hk_small_kernel<int,20,3,true>", "ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
+            "bytes_per_game_step": bytes_obs, "hbm_frac": B * bytes_obs / (ms * 1e-3) / 1e9 / peak_hbm,
+            "ms_by_rollout_step": [round(float(v), 4) for v in per]}
+        del x, obs, pristine
+    except Exception as e:
+        out["C2_step_with_features"] = {"error": repr(e)}
+
     # C3: MCTS node expansion — latency per call at eval_batch_size 10/100/512 (N=20, d=3)
     lat = {}
     for B, N in ((10, 20), (100, 20), (512, 20), (10, 5), (512, 5)):

@@ -34,6 +34,7 @@ HK_F_HOST_ZEILLINGER = 1 << 9
 HK_F_AGENT_FIRST = 1 << 10
 HK_F_AGENT_LAST = 1 << 11
 HK_F_OBS_SORT_LEX_FIRST = 1 << 12
+HK_F_STORE_ALL = 1 << 13
 
 # the two semantics of the reference
 TORCH_SEMANTICS = HK_F_NOOP_INVALID | HK_F_FREEZE_ENDED  # hironaka/src/_torch_ops.py:90-93

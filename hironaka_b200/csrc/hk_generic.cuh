@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     const bool vec_out = aligned16(p.out) && ((W & 3) == 0);
     const T padv = Elem<T>::pad(p.pad);
     const int OW = W + (p.obs_coord ? D : 0);
+    const bool inplace = (gout == gin) && !(p.flags & HK_F_STORE_ALL);
 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long nw = (long long)gridDim.x * warps_per_cta;
@@ -103,6 +104,11 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         cp_async_wait<1>();  // everything but the newest group has landed: game g is in buffer b
         __syncwarp();
         T* x = reinterpret_cast<T*>(slot + b * Wpad);
+
+        // Did the game change?  An unchanged game of an in-place call is not written back (in a long
+        // rollout most games have ended and sit at a fixed point).  Float state is always written
+        // (-0.0 is canonicalised), as is everything when out != in.
+        bool chg = Elem<T>::is_float || !inplace;
 
         // ---- liveness ----
         uint32_t mylive = 0;  // bit r <=> row lane + 32 r is live
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                         T s = Elem<T>::zero();
 #pragma unroll
                         for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + x[i * D + k] : s;
+                        chg = chg || (x[i * D + ax] != s);
                         x[i * D + ax] = s;
                     }
                 }
@@ -217,7 +224,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     if (!((mylive >> r) & 1u)) continue;
                     const int i = lane + 32 * r;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) x[i * D + k] = Elem<T>::zero();
+                    for (int k = 0; k < D; ++k) {
+                        chg = chg || (x[i * D + k] != Elem<T>::zero());
+                        x[i * D + k] = Elem<T>::zero();
+                    }
                 }
             } else if ((p.ops & HK_OP_REPOSITION) && cnt > 1) {
                 T mn[D];
@@ -234,7 +244,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < D; ++k) mn[k] = warp_min<T>(mn[k]);
+                for (int k = 0; k < D; ++k) {
+                    mn[k] = warp_min<T>(mn[k]);
+                    chg = chg || (mn[k] != Elem<T>::zero());
+                }
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     if (!((mylive >> r) & 1u)) continue;
@@ -261,6 +274,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     kill |= rep ? (1u << r) : 0u;
                 }
                 __syncwarp();
+                chg = chg || (kill != 0);
                 mylive &= ~kill;
             }
             // ---- newton: dedupe + dominance, reading the pre-removal state ----
@@ -335,6 +349,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     }
                 }
                 __syncwarp();
+                chg = chg || (kill != 0);
                 mylive &= ~kill;
             }
             // ---- rescale (float state) ----
@@ -396,7 +411,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     }
                 } else if (p.ops) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) x[i * D + k] = padv;
+                    for (int k = 0; k < D; ++k) {
+                        chg = chg || (x[i * D + k] != padv);
+                        x[i * D + k] = padv;
+                    }
                 }
             }
         }
@@ -408,7 +426,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
         }
         __syncwarp();
-        if (gout) {
+        if (gout && __any_sync(0xffffffffu, chg)) {
             const uint32_t* src = slot + b * Wpad;
             uint32_t* dst = gout + g * W;
             if (vec_out) {

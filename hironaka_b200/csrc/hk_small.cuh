@@ -15,6 +15,9 @@
 namespace hk {
 
 constexpr int SMALL_BAR_BYTES = 256;
+#ifndef HK_SPARSE_STORE_MAX
+#define HK_SPARSE_STORE_MAX 8  // at most this many changed games of a tile are written one by one (tools/tune_small.cu)
+#endif
 #ifndef HK_ROLLED_MIN
 #define HK_ROLLED_MIN 12  // smallest tier whose victim loop is rolled (tools/tune_small.cu)
 #endif
@@ -90,8 +93,10 @@ __device__ __forceinline__ uint32_t live_mask(const T (&x)[N * D]) {
 }
 
 // shift: x_a <- sum_{j in S} x_j on live rows (shift_torch _torch_ops.py:46-110, shift_jax _jax_ops.py:76-90)
+// `chg` (here and below) collects whether the op altered the game: unchanged games of an in-place
+// call are not written back (see the store phase of the kernel).
 template <typename T, int N, int D>
-__device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm, int a, bool apply) {
+__device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm, int a, bool apply, bool& chg) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         T s = Elem<T>::zero();
@@ -105,13 +110,17 @@ __device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm
         }
         const bool upd = apply && ((lm >> i) & 1u);
 #pragma unroll
-        for (int k = 0; k < D; ++k) x[i * D + k] = (upd && k == a) ? s : x[i * D + k];
+        for (int k = 0; k < D; ++k) {
+            const bool w = upd && (k == a);
+            chg = chg || (w && (s != x[i * D + k]));
+            x[i * D + k] = w ? s : x[i * D + k];
+        }
     }
 }
 
 // reposition: per coordinate subtract the min over live rows (reposition_torch _torch_ops.py:113-133)
 template <typename T, int N, int D>
-__device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm) {
+__device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm, bool& chg) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         T mn = Elem<T>::big();
@@ -120,6 +129,7 @@ __device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm) {
             T v = ((lm >> i) & 1u) ? x[i * D + k] : Elem<T>::big();
             mn = v < mn ? v : mn;
         }
+        chg = chg || (lm != 0 && mn != Elem<T>::zero());
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] - mn : x[i * D + k];
     }
@@ -320,7 +330,8 @@ __device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_
 // POLICY: instantiation that can evaluate the fixed players (kept out of the ordinary step kernels)
 template <typename T, int N, int D, int RS = 0, bool POLICY = false>
 __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
-                                              int32_t ax_in, uint32_t* scratch = nullptr) {
+                                              int32_t ax_in, bool& chg, uint32_t* scratch = nullptr) {
+    const uint32_t lm_in = lm;
     if (ops & HK_OP_SHIFT) {
         uint32_t cm;
         int ax = ax_in;
@@ -339,9 +350,9 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
         bool apply = (ax >= 0) && (ax < D);
         if (flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
         if (flags & HK_F_FREEZE_ENDED) apply = apply && (__popc(lm) >= 2);
-        op_shift<T, N, D>(x, lm, cm, ax, apply);
+        op_shift<T, N, D>(x, lm, cm, ax, apply, chg);
     }
-    if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm);
+    if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm, chg);
     if (ops & HK_OP_NEWTON) {
         if constexpr (RS > 0) {
             lm = op_newton_rolled<T, N, D, RS>(x, lm, scratch);
@@ -352,6 +363,7 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
     if constexpr (Elem<T>::is_float) {
         if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm);
     }
+    chg = chg || (lm != lm_in);
     return lm;
 }
 
@@ -386,7 +398,7 @@ __host__ __device__ constexpr int next_lower_tier(int K) { return K > 16 ? 16 : 
 // shared memory (`row`) holds the current state on entry and on exit.
 template <typename T, int N, int D, int K, bool POLICY>
 __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, const T (&x)[N * D],
-                                          uint32_t lm, int st, bool& exceed) {
+                                          uint32_t lm, int st, bool& exceed, bool& chg) {
     const long long B = p.B;
     const T padv = Elem<T>::pad(p.pad);
     const bool mutate = p.ops != 0;
@@ -417,6 +429,9 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
         }
         cvalid = clm;
     }
+    // Change tracking is exact in the smallest tier only (where the ended games of a long rollout
+    // live); a tile with more than 4 live rows in some game is busy: its games count as changed.
+    bool tchg = (K > 4) ? true : chg;
     for (; st < p.T;) {
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
@@ -424,7 +439,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
         }
         const bool prev_done = ls.cnt < 2;
-        clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
+        clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, tchg, row);
         ls.cnt = __popc(clm);
         const bool dn = ls.cnt < 2;
         if (ls.valid) {
@@ -446,6 +461,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
             if (st < p.T && __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0) <= LOWER) break;  // re-tier
         }
     }
+    chg = tchg;
     const bool last = st >= p.T;
     if (last && p.exceed_flag) exceed = exceeds<T, K, D>(y, clm, p.threshold);
     if (mutate) {
@@ -861,6 +877,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
     const T padv = Elem<T>::pad(p.pad);
     const bool write = (gout != nullptr);
     const bool mutate = p.ops != 0;
+    const bool inplace = (gout == gin) && !(p.flags & HK_F_STORE_ALL);
 
     pdl_launch_dependents();  // the next launch of the stream may begin its prologue as SMs free up
     if (lane == 0) {
@@ -918,6 +935,9 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
 
         bool exceed = false;
         bool normalised = false;
+        // Did this lane's game change?  Unchanged games of an in-place call are not written back.  Float
+        // state is always written (the kernel canonicalises -0.0), as is everything when out != in.
+        bool chg = Elem<T>::is_float || !inplace;
         ls.len = -1;
         int st = 0;
         do {
@@ -928,38 +948,56 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                 for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
             }
             const uint32_t lm = live_mask<T, N, D>(x);
+            // Every reference op rewrites dead rows with the padding value.  States produced by these
+            // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything
+            // else counts as a change of its game) and the rewrite below runs only if some game needs it.
+            bool any_junk = false;
+            if (mutate && !normalised) {
+                uint32_t diff = 0;
+                const uint32_t pbits = (uint32_t)Elem<T>::bits(padv);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    uint32_t dr = 0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) dr |= (uint32_t)Elem<T>::bits(x[i * D + c]) ^ pbits;
+                    diff |= ((lm >> i) & 1u) ? 0u : dr;
+                }
+                chg = chg || (diff != 0);
+                any_junk = __any_sync(0xffffffffu, diff != 0);
+            }
             ls.cnt = __popc(lm);
             if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
             const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
-            // the gathered tiers scatter only live rows, so dead rows are rewritten with the padding
-            // value first (every reference op does that); once per tile is enough
+            // the gathered tiers scatter only live rows: dead rows that need it are rewritten first
             auto prestore = [&]() {
                 if (mutate && !normalised) {
+                    if (any_junk) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) {
+                        for (int i = 0; i < N; ++i) {
 #pragma unroll
-                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                            for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                        }
+                        store_game<T, W>(row, x);
                     }
-                    store_game<T, W>(row, x);
                     normalised = true;
                 }
             };
             if (N > 4 && lmax <= 4) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed);
+                st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
             } else if (N > 8 && lmax <= 8) {
                 prestore();
-                st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed);
+                st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
             } else if (N > 12 && lmax <= 12) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed);
+                st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
                 normalised = normalised || (W % 4 == 0);
             } else if (N > 16 && lmax <= 16) {
                 if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed);
+                st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
                 normalised = normalised || (W % 4 == 0);
             } else {
-                st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed);
+                st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed, chg);
                 normalised = true;
             }
         } while (st < p.T);
@@ -972,16 +1010,39 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
             if (__any_sync(0xffffffffu, exceed && ls.valid) && lane == 0) *p.exceed_flag = 1;
         }
 
+        // ---- write-back.  In a long rollout most games have ended and sit at a fixed point (a lone
+        // point at the origin), so most games of an in-place step do not change: only changed games are
+        // written.  Many changed games -> the whole tile in one bulk store (rewriting an unchanged game
+        // is harmless); a few -> one coalesced copy per changed game; none -> nothing.
         bool stored = false;
         if (write) {
-            if (tma) {
-                fence_async_smem();
+            const uint32_t dirty = __ballot_sync(0xffffffffu, ls.valid && chg);
+            const int ndirty = __popc(dirty);
+            if (ndirty > HK_SPARSE_STORE_MAX) {
+                if (tma) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_store(gout + t * (long long)L::TILE_WORDS, stage, (uint32_t)words * 4u);
+                    stored = true;
+                } else {
+                    __syncwarp();
+                    warp_copy_words(gout + t * (long long)L::TILE_WORDS, stage, words, lane);
+                    __syncwarp();
+                }
+            } else if (ndirty > 0) {
                 __syncwarp();
-                if (lane == 0) bulk_store(gout + t * (long long)L::TILE_WORDS, stage, (uint32_t)words * 4u);
-                stored = true;
-            } else {
-                __syncwarp();
-                warp_copy_words(gout + t * (long long)L::TILE_WORDS, stage, words, lane);
+                uint32_t m = dirty;
+                while (m) {
+                    const int gi = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const uint32_t* src = stage + gi * W;
+                    uint32_t* dst = gout + (t * 32ll + gi) * W;
+                    if (W % 4 == 0 && tma_base) {
+                        if (lane < W / 4) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(src)[lane];
+                    } else {
+                        warp_copy_words(dst, src, W, lane);
+                    }
+                }
                 __syncwarp();
             }
         }

@@ -5,14 +5,17 @@
 namespace hk {
 namespace {
 
-// ring geometry of the thread-per-game kernel per shape: (warps per CTA, stages per warp)
-// (tools/tune_small.cu on B200, C2 workload: 4x3 = 95.6 us/step, 4x2 = 96.5, 3x3 = 102, 2x4 = 103)
+// ring geometry of the thread-per-game kernel per shape: (warps per CTA, stages per warp).
+// Since unchanged games are no longer written back, the steady state of a rollout is bound by the
+// instruction latency of each warp's tile loop rather than by bytes in flight, and warps per SM
+// count for more than stages per warp (tools/tune_small.cu on B200, C2 workload, us/step:
+// 8x1 = 72.9, 4x1 = 73.8, 4x2 = 73.8, 5x2 = 82.9, 4x3 = 84.5; with every game written, 4x3 = 94.8).
 template <int N, int D, bool OBS>
 struct SmallTune {
-    static constexpr int WARPS = 4;
+    static constexpr int WARPS = OBS ? 4 : 8;
     // step + features is issue- and latency-bound in the first steps of a rollout (many live rows):
     // one stage per warp and 12 warps per SM beat two stages and 8 warps (143.6 vs 152.7 us/step at C2)
-    static constexpr int STAGES = OBS ? 1 : 3;
+    static constexpr int STAGES = 1;
 };
 
 template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES>

@@ -83,6 +83,8 @@ extern "C" {
 
 #define HK_F_OBS_SORT_LEX_FIRST (1u << 12) /* rows sorted descending lexicographically, coordinate 0 primary: the order of
                                               ListPoints (Python sorted(points, reverse=True), hironaka/src/_list_ops.py:25) */
+#define HK_F_STORE_ALL (1u << 13) /* in-place calls (out == in) write back only the games that changed; set this to
+                                     rewrite every game (the results are identical; for measurements) */
 
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);

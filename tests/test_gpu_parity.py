@@ -269,6 +269,38 @@ def test_rescale_with_empty_games_in_a_warp(hb, N):
                 assert np.array_equal(got[4], cport.features(exp_state, flags)), (B, flags, ops_bits)
 
 
+@pytest.mark.parametrize("shape", [(1000, 20, 3), (333, 10, 3), (95, 5, 3), (300, 64, 5), (40, 16, 4)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_inplace_writes_only_changed_games(hb, family, shape, dtype):
+    """In-place steps write back only the games that changed (most games of a long rollout sit at a
+    fixed point).  The state must equal the oracle's after EVERY step, with and without
+    HK_F_STORE_ALL, for both flavours, from a start whose dead rows hold arbitrary negative values
+    (they must be normalised to the padding value) and whose ended games stay untouched."""
+    from hironaka_b200 import ops
+    B, N, d = shape
+    rng = np.random.default_rng(B + N)
+    T = 12
+    x0 = random_state(rng, B, N, d, max_value=5, dead_frac=0.5, dup_frac=0.1).astype(dtype)
+    junk = rng.random((B, N)) < 0.3  # dead rows that are not the padding value (still all-negative: well-formed)
+    x0[(x0[:, :, 0] < 0) & junk] = -7
+    x0[::5] = -1  # empty games
+    x0[1::5, 1:] = -1  # single-point games
+    x0[1::5, 0] = np.abs(x0[1::5, 0])
+    ha = rng.integers(0, 2 ** d, size=(T, B)).astype(np.int32)
+    ax = rng.integers(0, d, size=(T, B)).astype(np.int32)
+    for ops_bits, flags in ((O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, 0), (O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS),
+                            (O.OP_SHIFT, TORCH_FLAGS), (O.OP_REPOSITION, 0)):
+        o = x0.copy()
+        g_sparse, g_all = dev(x0), dev(x0)
+        for t in range(T):
+            o = cport.step(o, ha[t], ax[t], ops_bits, flags)[0]
+            ops.step(g_sparse, dev(ha[t]), dev(ax[t]), ops=ops_bits, flags=flags, inplace=True)
+            ops.step(g_all, dev(ha[t]), dev(ax[t]), ops=ops_bits, flags=flags | (1 << 13), inplace=True)
+            assert np.array_equal(g_sparse.cpu().numpy(), o), (ops_bits, flags, t)
+            assert np.array_equal(g_all.cpu().numpy(), o), (ops_bits, flags, t, "store_all")
+
+
 F_ALL, F_ZEIL, F_FIRST, F_LAST = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 
 

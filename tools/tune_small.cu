@@ -12,6 +12,9 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 constexpr int N = 20, D = 3, T = 20;
+#ifndef TUNE_EXTRA_FLAGS
+#define TUNE_EXTRA_FLAGS 0u
+#endif
 
 template <int WARPS, int STAGES, bool OBS = false>
 float launch(const hk::StepParams& p, cudaStream_t st, int sms, bool time_it, cudaEvent_t e0, cudaEvent_t e1) {
@@ -57,7 +60,7 @@ void run_variant(int B, int R, const std::vector<int32_t>& pts, const std::vecto
         p.in = s; p.out = s; p.ops = HK_OP_NEWTON | HK_OP_REPOSITION; p.flags = 0; p.host_action = nullptr; p.axis = nullptr; p.done = nullptr; p.reward = nullptr;
         launch<WARPS, STAGES, false>(p, st, sms, true, e0, e1);
         CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); init_ms += ms;
-        p.ops = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON; p.flags = HK_F_ACT_DISCRETE; p.done = d_done; p.reward = d_rew;
+        p.ops = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON; p.flags = HK_F_ACT_DISCRETE | TUNE_EXTRA_FLAGS; p.done = d_done; p.reward = d_rew;
         if (OBS) { p.obs = d_obs; p.flags |= HK_F_OBS_SORT_LEX | HK_F_OBS_RESCALE; }
         for (int t = 0; t < T; ++t) {
             p.host_action = d_ha + ((size_t)r * T + t) * B; p.axis = d_ax + ((size_t)r * T + t) * B;

@@ -93,10 +93,8 @@ __device__ __forceinline__ uint32_t live_mask(const T (&x)[N * D]) {
 }
 
 // shift: x_a <- sum_{j in S} x_j on live rows (shift_torch _torch_ops.py:46-110, shift_jax _jax_ops.py:76-90)
-// `chg` (here and below) collects whether the op altered the game: unchanged games of an in-place
-// call are not written back (see the store phase of the kernel).
 template <typename T, int N, int D>
-__device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm, int a, bool apply, bool& chg) {
+__device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm, int a, bool apply) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         T s = Elem<T>::zero();
@@ -110,17 +108,13 @@ __device__ __forceinline__ void op_shift(T (&x)[N * D], uint32_t lm, uint32_t cm
         }
         const bool upd = apply && ((lm >> i) & 1u);
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const bool w = upd && (k == a);
-            chg = chg || (w && (s != x[i * D + k]));
-            x[i * D + k] = w ? s : x[i * D + k];
-        }
+        for (int k = 0; k < D; ++k) x[i * D + k] = (upd && k == a) ? s : x[i * D + k];
     }
 }
 
 // reposition: per coordinate subtract the min over live rows (reposition_torch _torch_ops.py:113-133)
 template <typename T, int N, int D>
-__device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm, bool& chg) {
+__device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         T mn = Elem<T>::big();
@@ -129,7 +123,6 @@ __device__ __forceinline__ void op_reposition(T (&x)[N * D], uint32_t lm, bool& 
             T v = ((lm >> i) & 1u) ? x[i * D + k] : Elem<T>::big();
             mn = v < mn ? v : mn;
         }
-        chg = chg || (lm != 0 && mn != Elem<T>::zero());
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i * D + k] = ((lm >> i) & 1u) ? x[i * D + k] - mn : x[i * D + k];
     }
@@ -330,8 +323,7 @@ __device__ __forceinline__ uint32_t zeillinger_rows(const T (&y)[K * D], uint32_
 // POLICY: instantiation that can evaluate the fixed players (kept out of the ordinary step kernels)
 template <typename T, int N, int D, int RS = 0, bool POLICY = false>
 __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32_t ops, uint32_t flags, int32_t ha,
-                                              int32_t ax_in, bool& chg, uint32_t* scratch = nullptr) {
-    const uint32_t lm_in = lm;
+                                              int32_t ax_in, uint32_t* scratch = nullptr) {
     if (ops & HK_OP_SHIFT) {
         uint32_t cm;
         int ax = ax_in;
@@ -350,9 +342,9 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
         bool apply = (ax >= 0) && (ax < D);
         if (flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
         if (flags & HK_F_FREEZE_ENDED) apply = apply && (__popc(lm) >= 2);
-        op_shift<T, N, D>(x, lm, cm, ax, apply, chg);
+        op_shift<T, N, D>(x, lm, cm, ax, apply);
     }
-    if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm, chg);
+    if (ops & HK_OP_REPOSITION) op_reposition<T, N, D>(x, lm);
     if (ops & HK_OP_NEWTON) {
         if constexpr (RS > 0) {
             lm = op_newton_rolled<T, N, D, RS>(x, lm, scratch);
@@ -363,7 +355,6 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
     if constexpr (Elem<T>::is_float) {
         if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm);
     }
-    chg = chg || (lm != lm_in);
     return lm;
 }
 
@@ -378,7 +369,7 @@ __device__ __forceinline__ T x_row_value(const uint32_t* row, int w) {
 // ---- compacted tiers ------------------------------------------------------------------------------
 // Under real play few of the N slots are live (mean 6 of 20 after the root filter, 3 after two
 // steps), and the O(K^2 d) filter only needs the live rows.  Each warp therefore picks a tier
-// K in {4, 8, 12, 16, N} from the maximum live count over its 32 games (warp-uniform, no
+// K in {2, 4, 8, 12, 16, N} from the maximum live count over its 32 games (warp-uniform, no
 // divergence), gathers every lane's live rows into K register rows through the lane's own
 // shared-memory copy of the game (slot order is kept, so the lowest-index-wins dedupe rule is
 // unchanged), runs the steps on the K rows and scatters the survivors back to their slots.  In a
@@ -391,7 +382,9 @@ struct LaneState {
     int32_t len;
 };
 
-__host__ __device__ constexpr int next_lower_tier(int K) { return K > 16 ? 16 : (K > 12 ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0))); }
+__host__ __device__ constexpr int next_lower_tier(int K) {
+    return K > 16 ? 16 : (K > 12 ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : (K > 2 ? 2 : 0))));
+}
 
 // Runs steps [st, T) of one tile on K compact rows; returns the step index at which it stopped
 // (T, or earlier when every game of the warp fits the next lower tier).  The lane's game area in
@@ -429,17 +422,29 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
         }
         cvalid = clm;
     }
-    // Change tracking is exact in the smallest tier only (where the ended games of a long rollout
-    // live); a tile with more than 4 live rows in some game is busy: its games count as changed.
+    // Did the game change?  Exact for the games that matter, those with at most one live row (the
+    // ended games of a long rollout, nearly all of which sit at a fixed point): their only row is
+    // compact row 0 and it is compared before and after the step.  A game with two or more live
+    // rows counts as changed, as does every game of a busier tile (tiers above 4 rows).
     bool tchg = (K > 4) ? true : chg;
     for (; st < p.T;) {
+        T before[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) before[c] = y[c];
+        const uint32_t clm_before = clm;
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
             if (p.host_action) ha_n = load_action(p.host_action, (long long)(st + 1) * B + ls.g, p.flags);
             if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * B + ls.g, p.flags);
         }
         const bool prev_done = ls.cnt < 2;
-        clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, tchg, row);
+        clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
+        if constexpr (K <= 4) {
+            bool diff = (clm != clm_before) || (clm_before > 1u);  // compact rows fill from 0: > 1 means two or more rows
+#pragma unroll
+            for (int c = 0; c < D; ++c) diff = diff || ((clm & 1u) && (Elem<T>::bits(y[c]) != Elem<T>::bits(before[c])));
+            tchg = tchg || diff;
+        }
         ls.cnt = __popc(clm);
         const bool dn = ls.cnt < 2;
         if (ls.valid) {
@@ -947,23 +952,30 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
 #pragma unroll
                 for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
             }
-            const uint32_t lm = live_mask<T, N, D>(x);
             // Every reference op rewrites dead rows with the padding value.  States produced by these
             // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything
             // else counts as a change of its game) and the rewrite below runs only if some game needs it.
+            // One pass yields the live mask (sign of coordinate 0) and the check.
             bool any_junk = false;
-            if (mutate && !normalised) {
-                uint32_t diff = 0;
+            uint32_t lm;
+            {
+                const bool check = mutate && !normalised;
                 const uint32_t pbits = (uint32_t)Elem<T>::bits(padv);
+                uint32_t dead = 0, diff = 0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
+                    const uint32_t sgn = (uint32_t)(Elem<T>::bits(x[i * D]) >> 31);  // all ones <=> dead row
+                    dead |= sgn & (1u << i);
                     uint32_t dr = 0;
 #pragma unroll
                     for (int c = 0; c < D; ++c) dr |= (uint32_t)Elem<T>::bits(x[i * D + c]) ^ pbits;
-                    diff |= ((lm >> i) & 1u) ? 0u : dr;
+                    diff |= dr & sgn;
                 }
-                chg = chg || (diff != 0);
-                any_junk = __any_sync(0xffffffffu, diff != 0);
+                lm = ~dead & ((N == 32) ? 0xffffffffu : ((1u << N) - 1u));
+                if (check) {
+                    chg = chg || (diff != 0);
+                    any_junk = __any_sync(0xffffffffu, diff != 0);
+                }
             }
             ls.cnt = __popc(lm);
             if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
@@ -982,7 +994,10 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                     normalised = true;
                 }
             };
-            if (N > 4 && lmax <= 4) {
+            if (N > 2 && lmax <= 2) {  // the tail of a rollout: ended games and two-point games only
+                prestore();
+                st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            } else if (N > 4 && lmax <= 4) {
                 prestore();
                 st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
             } else if (N > 8 && lmax <= 8) {

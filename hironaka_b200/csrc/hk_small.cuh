@@ -383,7 +383,7 @@ struct LaneState {
 };
 
 __host__ __device__ constexpr int next_lower_tier(int K) {
-    return K > 16 ? 16 : (K > 12 ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : (K > 2 ? 2 : 0))));
+    return K > 16 ? 16 : (K > 12 ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0)));  // (the 2-row tier is for single steps only)
 }
 
 // Runs steps [st, T) of one tile on K compact rows; returns the step index at which it stopped
@@ -426,7 +426,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
     // ended games of a long rollout, nearly all of which sit at a fixed point): their only row is
     // compact row 0 and it is compared before and after the step.  A game with two or more live
     // rows counts as changed, as does every game of a busier tile (tiers above 4 rows).
-    bool tchg = (K > 4) ? true : chg;
+    bool tchg = (K > 4 || p.T > 1) ? true : chg;  // (a multi-step rollout changes every game that is worth playing)
     for (; st < p.T;) {
         T before[D];
 #pragma unroll
@@ -439,7 +439,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
         }
         const bool prev_done = ls.cnt < 2;
         clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
-        if constexpr (K <= 4) {
+        if (K <= 4 && p.T == 1) {
             bool diff = (clm != clm_before) || (clm_before > 1u);  // compact rows fill from 0: > 1 means two or more rows
 #pragma unroll
             for (int c = 0; c < D; ++c) diff = diff || ((clm & 1u) && (Elem<T>::bits(y[c]) != Elem<T>::bits(before[c])));
@@ -994,7 +994,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                     normalised = true;
                 }
             };
-            if (N > 2 && lmax <= 2) {  // the tail of a rollout: ended games and two-point games only
+            if (N > 2 && p.T == 1 && lmax <= 2) {  // the tail of a rollout driven step by step: ended games and two-point games only
                 prestore();
                 st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
             } else if (N > 4 && lmax <= 4) {

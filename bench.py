@@ -312,9 +312,18 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peak()
     avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
     achieved = B * BYTES_PER_GAME_STEP / avg_launch_s / 1e9
+    traffic = traffic_per_launch()
     roofline = {
         "bound": "hbm", "kernel": "hk::hk_small_kernel<int,20,3,false>", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(), "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        # `achieved` uses SURVEY 8d's algorithmic bytes (every game read AND written every step).  In-place steps
+        # write back only the games that changed, so the bytes that really move (`traffic`, ncu) are fewer and
+        # `frac` can exceed 1; `physical` is the same launch counted in moved bytes, and
+        # secondary.C2_write_back.store_all is the kernel made to write every game (HK_F_STORE_ALL).
+        "physical": None if not traffic else {"bytes_per_launch": traffic, "gbps": traffic / avg_launch_s / 1e9,
+                                              "frac": traffic / avg_launch_s / 1e9 / peak},
+        "store_all_frac": None if not secondary or "store_all" not in secondary.get("C2_write_back", {}) else
+        secondary["C2_write_back"]["store_all"]["hbm_frac_algorithmic"],
         "algorithmic_bytes_per_launch": B * BYTES_PER_GAME_STEP, "avg_launch_ms": avg_launch_s * 1e3,
         "min_launch_ms": float(np.min(per_launch_ms)), "max_launch_ms": float(np.max(per_launch_ms)),
         "int_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s,
@@ -494,6 +503,42 @@ def measure_secondary(torch, lib, C, dev):
                  "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
                  "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
                          "dense count; the dense count is what the root filter (64 live points) executes"}
+
+    # C2 with HK_F_STORE_ALL: every game written back every step (what the roofline's algorithmic bytes assume)
+    try:
+        B, N, d, T = GAMES_PER_GPU, N_POINTS, DIM, T_ROLLOUT
+        x, ha, ax = make(B, N, d, T, MAX_VALUE, 12, True)
+        done, rew = torch.empty(B, dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.float32, device=dev)
+        pristine = x.clone()
+        res = {}
+        for name, extra in (("changed_games_only", 0), ("store_all", C.HK_F_STORE_ALL)):
+            per = []
+            for rep in range(4):
+                x.copy_(pristine)
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+                ev[0].record()
+                for t in range(T):
+                    rc = lib.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(),
+                                     rew.data_ptr(), None, None, None, None, B, N, d, C.HK_DTYPE_I32,
+                                     C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, C.HK_F_ACT_DISCRETE | extra,
+                                     -1.0, 1e8, stream)
+                    assert rc == 0
+                    ev[t + 1].record()
+                torch.cuda.synchronize()
+                if rep:
+                    per.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
+            per = np.mean(np.array(per), axis=0)
+            ms = float(per.mean())
+            res[name] = {"ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
+                         "hbm_frac_algorithmic": B * (8 * N * d + 13) / (ms * 1e-3) / 1e9 / peak_hbm,
+                         "ms_by_rollout_step": [round(float(v), 4) for v in per]}
+        res["workload"] = ("C2, 1 Mi games, one 20-step random-play rollout, in place: the default (only games that "
+                           "changed are written back) against HK_F_STORE_ALL (every game rewritten every step)")
+        out["C2_write_back"] = res
+        del x, pristine
+    except Exception as e:
+        out["C2_write_back"] = {"error": repr(e)}
 
     # C2 with the fused host observation (kernel (c) of the north star): step + done/reward + features in one launch
     try:

@@ -498,8 +498,15 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
         const int slot = t & 1;
         int32_t* ha = s->host_action + (size_t)slot * s->B;
         int32_t* ax = s->axis + (size_t)slot * s->B;
-        // copy stream: wait until the step that last used this slot has run, then upload step t
-        if (t >= 2) HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[slot], 0));
+        // copy stream: wait until the step that last used this slot has run, bring that step's result
+        // back to the host (on this stream, so that the 4-byte read does not sit between two kernels of
+        // the compute stream), then upload step t
+        if (t >= 2) {
+            HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[slot], 0));
+            if (done_count_host)
+                HK_CUDA(cudaMemcpyAsync(s->counts_pinned + (t - 2), s->counts + (t - 2), 4, cudaMemcpyDeviceToHost,
+                                        s->copy_stream));
+        }
         HK_CUDA(cudaMemcpyAsync(ha, (const char*)host_action_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
                                 s->copy_stream));
         HK_CUDA(cudaMemcpyAsync(ax, (const char*)axis_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
@@ -515,10 +522,15 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
         int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
         if (rc != HK_OK) return rc;
         HK_CUDA(cudaEventRecord(s->freed[slot], s->stream));
-        if (done_count_host)  // the step's result goes back to the host right after the step
-            HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (done_count_host) {  // the results of the last two steps
+        for (int t = (T >= 2 ? T - 2 : 0); t < T; ++t) {
+            HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[t & 1], 0));
+            HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->copy_stream));
+        }
     }
     HK_CUDA(cudaStreamSynchronize(s->stream));
+    HK_CUDA(cudaStreamSynchronize(s->copy_stream));
     if (done_count_host) memcpy(done_count_host, s->counts_pinned, (size_t)T * 4);
     return HK_OK;
 }

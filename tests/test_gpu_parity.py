@@ -40,12 +40,25 @@ def dev(a):
 
 def run_step(hb, x_np, ha, ax, ops_bits, flags, pad=-1.0, want_obs=False, obs_coord=None):
     from hironaka_b200 import ops
-    r = ops.step(dev(x_np), None if ha is None else dev(ha.astype(np.int32)),
-                 None if ax is None else dev(ax.astype(np.int32)), ops=ops_bits, flags=flags, padding_value=pad,
-                 inplace=False, want_done=True, want_reward=True, want_num_points=True, want_obs=want_obs,
-                 obs_coord=None if obs_coord is None else dev(obs_coord.astype(np.int32)))
-    return (r.state.cpu().numpy(), r.done.cpu().numpy(), r.reward.cpu().numpy(), r.num_points.cpu().numpy(),
-            None if r.obs is None else r.obs.cpu().numpy())
+    def call(x, inplace):
+        return ops.step(x, None if ha is None else dev(ha.astype(np.int32)),
+                        None if ax is None else dev(ax.astype(np.int32)), ops=ops_bits, flags=flags, padding_value=pad,
+                        inplace=inplace, want_done=True, want_reward=True, want_num_points=True, want_obs=want_obs,
+                        obs_coord=None if obs_coord is None else dev(obs_coord.astype(np.int32)))
+    r = call(dev(x_np), False)
+    out = (r.state.cpu().numpy(), r.done.cpu().numpy(), r.reward.cpu().numpy(), r.num_points.cpu().numpy(),
+           None if r.obs is None else r.obs.cpu().numpy())
+    # the same call in place (out == in) takes other routes through the library (changed games / rows
+    # only are written back; large games go to the compacting kernel): it must give the same answers
+    xi = dev(x_np)
+    ri = call(xi, True)
+    same = np.array_equal(xi.cpu().numpy().view(np.int32), out[0].view(np.int32))
+    assert same, "in-place state differs from out-of-place"
+    assert np.array_equal(ri.done.cpu().numpy(), out[1]) and np.array_equal(ri.reward.cpu().numpy(), out[2])
+    assert np.array_equal(ri.num_points.cpu().numpy(), out[3])
+    if want_obs:
+        assert np.array_equal(ri.obs.cpu().numpy(), out[4])
+    return out
 
 
 @pytest.fixture(params=[False, True], ids=["family=auto", "family=generic"])

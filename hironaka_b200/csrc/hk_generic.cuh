@@ -106,9 +106,8 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         T* x = reinterpret_cast<T*>(slot + b * Wpad);
 
         // Did the game change?  An unchanged game of an in-place call is not written back (in a long
-        // rollout most games have ended and sit at a fixed point).  Float state is always written
-        // (-0.0 is canonicalised), as is everything when out != in.
-        bool chg = Elem<T>::is_float || !inplace;
+        // rollout most games have ended and sit at a fixed point); everything is when out != in.
+        bool chg = !inplace;
 
         // ---- liveness ----
         uint32_t mylive = 0;  // bit r <=> row lane + 32 r is live
@@ -120,7 +119,11 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             if (i < N) {
                 if constexpr (Elem<T>::is_float) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) x[i * D + k] = x[i * D + k] + 0.0f;  // canonicalise -0.0
+                    for (int k = 0; k < D; ++k) {  // canonicalise -0.0 (a game that held one counts as changed)
+                        const float v = x[i * D + k], c = v + 0.0f;
+                        chg = chg || (__float_as_int(v) != __float_as_int(c));
+                        x[i * D + k] = c;
+                    }
                 }
                 lv = x[i * D] >= Elem<T>::zero();
             }
@@ -373,7 +376,9 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
 #pragma unroll
                             for (int k = 0; k < D; ++k) {
                                 const float v = x[i * D + k];  // 0 / mx = 0: keep zeros (common after reposition) out of the divider
-                                x[i * D + k] = (v != 0.0f) ? __fdiv_rn(v, mx) : v;
+                                const float q = (v != 0.0f) ? __fdiv_rn(v, mx) : v;
+                                chg = chg || (q != v);
+                                x[i * D + k] = q;
                             }
                         }
                     }

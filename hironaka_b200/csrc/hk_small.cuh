@@ -16,7 +16,7 @@ namespace hk {
 
 constexpr int SMALL_BAR_BYTES = 256;
 #ifndef HK_SPARSE_STORE_MAX
-#define HK_SPARSE_STORE_MAX 8  // at most this many changed games of a tile are written one by one (tools/tune_small.cu)
+#define HK_SPARSE_STORE_MAX 16  // at most this many changed games of a tile are written one by one (tools/tune_small.cu: 4 -> 71.2, 8 -> 68.3, 16 -> 67.3, 32 -> 75.7 us/step at C2)
 #endif
 #ifndef HK_ROLLED_MIN
 #define HK_ROLLED_MIN 12  // smallest tier whose victim loop is rolled (tools/tune_small.cu)
@@ -940,17 +940,23 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
 
         bool exceed = false;
         bool normalised = false;
-        // Did this lane's game change?  Unchanged games of an in-place call are not written back.  Float
-        // state is always written (the kernel canonicalises -0.0), as is everything when out != in.
-        bool chg = Elem<T>::is_float || !inplace;
+        // Did this lane's game change?  Unchanged games of an in-place call are not written back
+        // (everything is when out != in).
+        bool chg = !inplace;
         ls.len = -1;
         int st = 0;
         do {
             T x[W];
             load_game<T, W>(row, x);
             if constexpr (Elem<T>::is_float) {
+                uint32_t canon = 0;
 #pragma unroll
-                for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;  // canonicalise -0.0
+                for (int q = 0; q < W; ++q) {  // canonicalise -0.0 (a game that held one counts as changed)
+                    const float c = x[q] + 0.0f;
+                    canon |= (uint32_t)__float_as_int(x[q]) ^ (uint32_t)__float_as_int(c);
+                    x[q] = c;
+                }
+                chg = chg || (canon != 0);
             }
             // Every reference op rewrites dead rows with the padding value.  States produced by these
             // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything

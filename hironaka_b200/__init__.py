@@ -9,6 +9,7 @@ Layers (bottom up):
   functional       drop-in for hironaka/jax/util.py (take_actions, get_dones, reward_fn, feature_fn, ...)
   GameBatch        resident int32 batches, fused T-step rollouts, sharding + rollout all-gather
   HostSession      NumPy host-buffer sessions over hk_session_*
+  VecHironaka*Env  batched forms of the gym environments (hironaka/gym_env)
 """
 from . import constants
 from .constants import *  # noqa: F401,F403
@@ -36,10 +37,13 @@ def __getattr__(name):  # lazy: importing the package must not require torch or 
     if name == "FusedGame":
         from .fused_game import FusedGame
         return FusedGame
+    if name in ("VecHironakaAgentEnv", "VecHironakaHostEnv"):
+        from . import vec_env
+        return getattr(vec_env, name)
     if name == "HostActionEncoder":
         from .host_action import HostActionEncoder
         return HostActionEncoder
-    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build", "fused_game", "players", "replay_buffer"):
+    if name in ("ops", "src", "functional", "engine", "session", "host_action", "build", "fused_game", "players", "replay_buffer", "vec_env"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

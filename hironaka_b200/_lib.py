@@ -31,6 +31,7 @@ SIGNATURES = {
     "hk_rescale": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "hk_features": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_dones": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "hk_host_policy": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_rollout": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _u32, _u32, _f32, _p]),
     "hk_experience_scratch_words": (_i64, [_i64]),
     "hk_experience_append": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,

@@ -219,6 +219,18 @@ int hk_dones(const void* state_in, uint8_t* done, int32_t* num_points, int64_t B
     return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
 }
 
+int hk_host_policy(const void* state_in, int32_t* coord_mask, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                   uint32_t flags, float padding_value, void* stream) {
+    if (coord_mask == nullptr) return HK_ERR_BAD_ARG;
+    const uint32_t host = flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER);
+    if (host == 0 || host == (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER)) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, nullptr, B, N, d, padding_value);
+    p.ops = HK_OP_SHIFT;  // the players are evaluated where the shift would use them; nothing is moved or written
+    p.flags = host | HK_F_AGENT_FIRST;  // (the agent's choice is not used: nothing moves)
+    p.host_out = coord_mask;
+    return run(p, dtype, 1 /* the warp-per-game family evaluates it for every shape */, (cudaStream_t)stream);
+}
+
 int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action_t, const int32_t* axis_t,
                uint8_t* done_t, float* reward_t, int32_t* done_count, int32_t* length, int64_t B, int32_t N,
                int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value,

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             const bool prev_done = cnt < 2;
 
             // ---- shift ----
+            if ((p.ops & HK_OP_SHIFT) && cnt == 0 && p.host_out && lane == 0) p.host_out[g] = 0;
             if ((p.ops & HK_OP_SHIFT) && cnt > 0) {
                 uint32_t cm;
                 if (p.flags & HK_F_HOST_ALL_COORD) {
@@ -204,6 +205,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                 }
                 ax = agent_policy_axis(cm, ax, p.flags, D);
                 bool apply = (ax >= 0) && (ax < D);
+                if (p.host_out) {  // hk_host_policy: report the host's choice, move nothing
+                    if (lane == 0) p.host_out[g] = (int32_t)cm;
+                    apply = false;
+                }
                 if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
                 if (p.flags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
                 if (apply) {

@@ -205,6 +205,21 @@ def dones(state: torch.Tensor, want_num_points: bool = False):
     return done.view(torch.bool), npts
 
 
+def host_policy(state: torch.Tensor, host: str, padding_value: float = -1.0) -> torch.Tensor:
+    """Coordinate set a fixed host ("zeillinger" | "all_coord") would choose on each game, as an int32
+    bitmask [B] (hk_host_policy); nothing is moved.  Pairs are scanned in slot order, so a state kept in
+    ListPoints order reproduces hironaka/host.py:50-92."""
+    dt = _require_state(state)
+    flag = {"zeillinger": C.HK_F_HOST_ZEILLINGER, "all_coord": C.HK_F_HOST_ALL_COORD}[host]
+    B, N, d = state.shape
+    mask = torch.empty(B, dtype=torch.int32, device=state.device)
+    with torch.cuda.device(state.device):
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        rc = lib().hk_host_policy(_ptr(state), _ptr(mask), B, N, d, dt, flag, float(padding_value), stream)
+    check(rc, "hk_host_policy")
+    return mask
+
+
 def _single_op(fn_name: str, state: torch.Tensor, inplace: bool, padding_value: float) -> Optional[torch.Tensor]:
     dt = _require_state(state)
     B, N, d = state.shape

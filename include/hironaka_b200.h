@@ -141,6 +141,16 @@ int hk_features(const void* state_in, float* obs, const int32_t* obs_coord, int6
 int hk_dones(const void* state_in, uint8_t* done, int32_t* num_points, int64_t B, int32_t N, int32_t d,
              int32_t dtype, void* stream);
 
+/* The coordinate set a FIXED HOST would choose on each game, as a bitmask (bit k <=> coordinate k),
+ * without moving anything: flags = HK_F_HOST_ALL_COORD (AllCoordHost, hironaka/host.py:44-47;
+ * all_coord_host_fn, hironaka/jax/players.py:42-52) or HK_F_HOST_ZEILLINGER (Zeillinger,
+ * hironaka/host.py:50-92; zeillinger_fn, players.py:55-105: pairs of live rows in slot order, so a
+ * state kept in ListPoints order reproduces host.py).  A game without live rows gets 0.  This is what
+ * a host-side environment returns to the agent as `coords` (HironakaHostEnv.step,
+ * hironaka/gym_env/hironaka_host_env.py:62-66). */
+int hk_host_policy(const void* state_in, int32_t* coord_mask, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                   uint32_t flags, float padding_value, void* stream);
+
 /* ---- multi-step rollout ------------------------------------------------------------------
  * T consecutive steps with the state held on chip between steps: one read and one write of
  * the state per T steps.  Action streams are [T,B].  Outputs per step are optional:

@@ -1,0 +1,127 @@
+"""GPU: the vectorised environments (hironaka_b200.vec_env) against fixtures from the REAL reference
+environments and, on larger batches, against the NumPy restatement that those fixtures pin
+(tests/env_restatement.py, tests/test_gym_env_cpu.py)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from tests import env_restatement as E  # noqa: E402
+from tests.test_gym_env_cpu import AGENT_SETS, HOST_SETS  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(mask, d):
+    return (mask[:, None] >> np.arange(d)) & 1
+
+
+@pytest.mark.parametrize("name", sorted(AGENT_SETS))
+def test_vec_agent_env_against_reference_fixture(golden_dir, name):
+    from hironaka_b200 import VecHironakaAgentEnv
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = AGENT_SETS[name]
+    B, N, d = g["points"].shape
+    discrete = g["actions"].ndim == 2
+    env = VecHironakaAgentEnv(B, agent="choose_first", use_discrete_actions_for_host=discrete, dimension=d,
+                              max_num_points=N, **cfg)
+    ref = E.AgentEnv(N, d, **cfg)
+    exact = not cfg["scale_observation"]
+    o = env.reset(torch.from_numpy(g["points"])).cpu().numpy()
+    assert np.array_equal(o, ref.reset(g["points"]))
+    if exact:
+        assert np.array_equal(o, g["obs0"])
+    for t in range(g["actions"].shape[0]):
+        a = g["actions"][t]
+        obs, rew, stop, _ = env.step(torch.from_numpy(a))
+        robs, rrew, rstop = ref.step(a if discrete else E.multibinary_to_mask(a))
+        assert np.array_equal(obs.cpu().numpy(), robs), (name, t)
+        assert np.array_equal(rew.cpu().numpy().astype(np.float64), rrew), (name, t)
+        assert np.array_equal(stop.cpu().numpy(), rstop), (name, t)
+        if exact:  # and therefore the real environment, bit for bit
+            assert np.array_equal(obs.cpu().numpy(), g["obs"][t]) and np.array_equal(rrew, g["reward"][t])
+            assert np.array_equal(rstop, g["stopped"][t])
+
+
+@pytest.mark.parametrize("name", sorted(HOST_SETS))
+def test_vec_host_env_against_reference_fixture(golden_dir, name):
+    from hironaka_b200 import VecHironakaHostEnv
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = dict(HOST_SETS[name])
+    host = cfg.pop("host")
+    B, N, d = g["points"].shape
+    env = VecHironakaHostEnv(B, host={"Zeillinger": "zeillinger", "AllCoordHost": "all_coord"}[host], dimension=d,
+                             max_num_points=N, **cfg)
+    ref = E.HostEnv(N, d, host=host, **cfg)
+    exact = not cfg["scale_observation"]
+    o = env.reset(torch.from_numpy(g["points"]))
+    robs, rcoords = ref.reset(g["points"])
+    assert np.array_equal(o["points"].cpu().numpy(), robs)
+    assert np.array_equal(o["coords"].cpu().numpy(), bits(rcoords, d))
+    if exact:
+        assert np.array_equal(o["points"].cpu().numpy(), g["obs0"]) and np.array_equal(o["coords"].cpu().numpy(), g["coords0"])
+    alive = np.ones(B, bool)
+    for t in range(g["actions"].shape[0]):
+        o, rew, stop, _ = env.step(torch.from_numpy(g["actions"][t]))
+        robs, rcoords, rrew, rstop = ref.step(g["actions"][t])
+        assert np.array_equal(o["points"].cpu().numpy(), robs), (name, t)
+        assert np.array_equal(o["coords"].cpu().numpy(), bits(rcoords, d)), (name, t)
+        assert np.allclose(rew.cpu().numpy(), rrew), (name, t)
+        assert np.array_equal(stop.cpu().numpy(), rstop), (name, t)
+        if exact:
+            assert np.array_equal(o["points"].cpu().numpy()[alive], g["obs"][t][alive])
+            assert np.array_equal(o["coords"].cpu().numpy()[alive], g["coords"][t][alive])
+            alive &= ~g["stopped"][t]
+
+
+@pytest.mark.parametrize("shape", [(3000, 20, 3), (1000, 10, 3), (500, 16, 4)], ids=lambda s: "x".join(map(str, s)))
+def test_vec_envs_on_large_batches(shape):
+    """Both environments against the restatement on batches far beyond what the one-game-at-a-time
+    reference plays in reasonable time, with thresholds that trigger."""
+    from hironaka_b200 import VecHironakaAgentEnv, VecHironakaHostEnv
+    B, N, d = shape
+    rng = np.random.default_rng(B + N)
+    pts = rng.integers(0, 12, size=(B, N, d)).astype(np.int32)
+    cfg = dict(scale_observation=True, step_threshold=7, value_threshold=400, reward_based_on_point_reduction=True)
+    env = VecHironakaAgentEnv(B, agent="choose_first", dimension=d, max_num_points=N, **cfg)
+    ref = E.AgentEnv(N, d, **cfg)
+    assert np.array_equal(env.reset(torch.from_numpy(pts)).cpu().numpy(), ref.reset(pts))
+    for t in range(9):
+        a = rng.integers(0, 2, size=(B, d)).astype(np.int32)
+        obs, rew, stop, _ = env.step(torch.from_numpy(a))
+        robs, rrew, rstop = ref.step(E.multibinary_to_mask(a))
+        assert np.array_equal(obs.cpu().numpy(), robs) and np.array_equal(rew.cpu().numpy().astype(np.float64), rrew)
+        assert np.array_equal(stop.cpu().numpy(), rstop)
+    hcfg = dict(scale_observation=True, value_threshold=400, invalid_move_penalty=-0.25)
+    henv = VecHironakaHostEnv(B, host="zeillinger", dimension=d, max_num_points=N, **hcfg)
+    href = E.HostEnv(N, d, host="Zeillinger", **hcfg)
+    o = henv.reset(torch.from_numpy(pts))
+    robs, rcoords = href.reset(pts)
+    assert np.array_equal(o["points"].cpu().numpy(), robs) and np.array_equal(o["coords"].cpu().numpy(), bits(rcoords, d))
+    for t in range(9):
+        a = rng.integers(0, d, size=B).astype(np.int32)
+        o, rew, stop, _ = henv.step(torch.from_numpy(a))
+        robs, rcoords, rrew, rstop = href.step(a)
+        assert np.array_equal(o["points"].cpu().numpy(), robs), t
+        assert np.array_equal(o["coords"].cpu().numpy(), bits(rcoords, d)), t
+        assert np.allclose(rew.cpu().numpy(), rrew) and np.array_equal(stop.cpu().numpy(), rstop)
+
+
+def test_host_policy_agrees_with_fused_player():
+    """hk_host_policy reports the set the fused Zeillinger host plays: stepping with the reported mask
+    equals stepping with HK_F_HOST_ZEILLINGER."""
+    from hironaka_b200 import constants as C, ops
+    rng = np.random.default_rng(3)
+    for (B, N, d) in ((777, 20, 3), (300, 10, 3), (200, 16, 4), (64, 64, 5)):
+        x = rng.integers(0, 9, size=(B, N, d)).astype(np.int32)
+        x[rng.random((B, N)) < 0.4] = -1
+        st = torch.from_numpy(x).cuda()
+        ops.step(st, ops=C.HK_OP_NEWTON, inplace=True)
+        mask = ops.host_policy(st, "zeillinger")
+        assert torch.equal(ops.host_policy(st, "all_coord"), torch.full_like(mask, (1 << d) - 1) * (ops.dones(st, True)[1] > 0))
+        a, b = st.clone(), st.clone()
+        ops.step(a, None, None, ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=C.HK_F_HOST_ZEILLINGER | C.HK_F_AGENT_FIRST, inplace=True)
+        ops.step(b, mask, None, ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=C.HK_F_AGENT_FIRST, inplace=True)
+        assert torch.equal(a, b)

@@ -16,12 +16,16 @@ namespace hk {
 
 template <typename T>
 __device__ __forceinline__ T warp_min(T v) {
+    if constexpr (!Elem<T>::is_float) {
+        return (T)__reduce_min_sync(0xffffffffu, (int)v);  // one REDUX instead of five shuffle + min rounds
+    } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        T u = __shfl_xor_sync(0xffffffffu, v, o);
-        v = u < v ? u : v;
+        for (int o = 16; o > 0; o >>= 1) {
+            T u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = u < v ? u : v;
+        }
+        return v;
     }
-    return v;
 }
 
 __device__ __forceinline__ float warp_maxf(float v) {
@@ -53,7 +57,12 @@ __device__ __forceinline__ int32_t dominance_word(const T (&xi)[D], const T* x, 
     return t;
 }
 
-// smem per warp: two state buffers x[2][Wpad], then (OBS) f[Wpad] floats, then lmw[ceil(N/32)]
+// words per row of the compact live-row list: D coordinates + the slot number, rounded up to an even
+// count so that a pair of rows is a whole number of 16-byte words
+__host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2) & ~1; }
+
+// smem per warp: two state buffers x[2][Wpad], then (OBS) f[Wpad] floats, then lmw[ceil(N/32)] (padded to
+// 4 words), then the compact list of live rows, (N + 1) * generic_compact_stride(D) words
 // RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
 // guards become predication) or 0 for any N (run-time loops).
 template <typename T, int D, bool OBS, int RT>
@@ -68,6 +77,8 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * slot_words;
     float* f = reinterpret_cast<float*>(slot + 2 * Wpad);
     uint32_t* lmw = slot + 2 * Wpad + (OBS ? Wpad : 0);
+    constexpr int CSTRIDE = generic_compact_stride(D);                            // words per compact row (even)
+    uint32_t* comp = lmw + ((((N + 31) >> 5) + 3) & ~3);                          // (N + 1) compact rows, 16-byte aligned
 
     const uint32_t* gin = reinterpret_cast<const uint32_t*>(p.in);
     uint32_t* gout = reinterpret_cast<uint32_t*>(p.out);
@@ -84,7 +95,17 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         uint32_t* dst = slot + b * Wpad;
         const uint32_t* src = gin + g * W;
         if (vec_in) {
-            for (int c = lane; c < (W >> 2); c += 32) cp_async_16(dst + 4 * c, src + 4 * c);
+            if constexpr (RT > 0) {  // at most RT*32 rows: a fixed number of 16-byte chunks per lane, guarded
+                constexpr int ITERS = (RT * 32 * D / 4 + 31) / 32;
+                const uint32_t* s16 = src + 4 * lane;
+                uint32_t* d16 = dst + 4 * lane;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    if (lane + 32 * it < (W >> 2)) cp_async_16(d16 + 128 * it, s16 + 128 * it);
+                }
+            } else {
+                for (int c = lane; c < (W >> 2); c += 32) cp_async_16(dst + 4 * c, src + 4 * c);
+            }
         } else {
             for (int w = lane; w < W; w += 32) cp_async_4(dst + w, src + w);
         }
@@ -287,15 +308,48 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             }
             // ---- newton: dedupe + dominance, reading the pre-removal state ----
             if ((p.ops & HK_OP_NEWTON) && cnt >= 2) {
+                // The live rows are first copied, in slot order, into a COMPACT list in shared memory (row k at
+                // k*CSTRIDE: D coordinates, then the slot number), so that the dominator loop walks it linearly
+                // with 16-byte broadcast loads, two dominators per trip, instead of decoding ballot words into row
+                // addresses on every trip (that bookkeeping and the scalar loads were half of the loop's
+                // instructions).  An odd count is padded with a copy of the last row: AND-accumulation is idempotent.
+                int base = 0;
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, (mylive >> r) & 1u);
-                    if (lane == 0) lmw[r] = bal;
+                    const bool lv = (mylive >> r) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, lv);
+                    if (lv) {
+                        const int i = lane + 32 * r;
+                        uint32_t* dst = comp + (base + __popc(bal & ((1u << lane) - 1u))) * CSTRIDE;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) dst[k] = (uint32_t)Elem<T>::bits(x[i * D + k]);
+                        dst[D] = (uint32_t)i;
+                    }
+                    base += __popc(bal);
                 }
                 __syncwarp();
+                if ((base & 1) && lane <= D) comp[base * CSTRIDE + lane] = comp[(base - 1) * CSTRIDE + lane];
+                __syncwarp();
+                const int npairs = (base + 1) >> 1;
                 uint32_t kill = 0;
+                auto load_pair = [&](int pr, T (&xa)[D], T (&xb)[D], int& ja, int& jb) {
+                    uint32_t w[2 * CSTRIDE];
+                    const uint4* src = reinterpret_cast<const uint4*>(comp + pr * 2 * CSTRIDE);
+#pragma unroll
+                    for (int q = 0; q < CSTRIDE / 2; ++q) {
+                        const uint4 v = src[q];
+                        w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        xa[k] = Elem<T>::from_bits(w[k]);
+                        xb[k] = Elem<T>::from_bits(w[CSTRIDE + k]);
+                    }
+                    ja = (int)w[D];
+                    jb = (int)w[CSTRIDE + D];
+                };
                 if (R <= 2) {
-                    // both rows of the lane ride on the same broadcast of dominator j
+                    // both rows of the lane ride on the same broadcast of the dominator pair
                     const int i0 = lane, i1 = lane + 32;
                     const bool l0 = mylive & 1u, l1 = (mylive >> 1) & 1u;
                     T a0[D], a1[D];
@@ -305,34 +359,22 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                         a1[k] = l1 ? x[i1 * D + k] : Elem<T>::big();
                     }
                     int32_t acc0 = (int32_t)0x80000000, acc1 = (int32_t)0x80000000;
-                    _Pragma("unroll UNR")
-                    for (int r2 = 0; r2 < R; ++r2) {
-                        uint32_t m = lmw[r2];
-                        while (m) {
-                            // two dominators per trip (the second repeats the first when the count is odd:
-                            // AND-accumulation is idempotent), so ten broadcast loads are in flight together
-                            const int ja = 32 * r2 + __ffs((int)m) - 1;
-                            m &= m - 1;
-                            const int jb = m ? (32 * r2 + __ffs((int)m) - 1) : ja;
-                            m &= m - 1;
-                            T xa[D], xb[D];
+                    for (int pr = 0; pr < npairs; ++pr) {
+                        T xa[D], xb[D];
+                        int ja, jb;
+                        load_pair(pr, xa, xb, ja, jb);
+                        int32_t t0a = Elem<T>::bits(a0[0] - xa[0]), t1a = Elem<T>::bits(a1[0] - xa[0]);
+                        int32_t t0b = Elem<T>::bits(a0[0] - xb[0]), t1b = Elem<T>::bits(a1[0] - xb[0]);
 #pragma unroll
-                            for (int k = 0; k < D; ++k) {
-                                xa[k] = x[ja * D + k];
-                                xb[k] = x[jb * D + k];
-                            }
-                            int32_t t0a = Elem<T>::bits(a0[0] - xa[0]), t1a = Elem<T>::bits(a1[0] - xa[0]);
-                            int32_t t0b = Elem<T>::bits(a0[0] - xb[0]), t1b = Elem<T>::bits(a1[0] - xb[0]);
-#pragma unroll
-                            for (int k = 1; k < D; ++k) {
-                                t0a |= Elem<T>::bits(a0[k] - xa[k]);
-                                t1a |= Elem<T>::bits(a1[k] - xa[k]);
-                                t0b |= Elem<T>::bits(a0[k] - xb[k]);
-                                t1b |= Elem<T>::bits(a1[k] - xb[k]);
-                            }
-                            acc0 &= (t0a - ((ja >= i0) ? 1 : 0)) & (t0b - ((jb >= i0) ? 1 : 0));
-                            acc1 &= (t1a - ((ja >= i1) ? 1 : 0)) & (t1b - ((jb >= i1) ? 1 : 0));
+                        for (int k = 1; k < D; ++k) {
+                            t0a |= Elem<T>::bits(a0[k] - xa[k]);
+                            t1a |= Elem<T>::bits(a1[k] - xa[k]);
+                            t0b |= Elem<T>::bits(a0[k] - xb[k]);
+                            t1b |= Elem<T>::bits(a1[k] - xb[k]);
                         }
+                        // ties only kill from a lower slot; this also neutralises the self pair
+                        acc0 &= (t0a - ((ja >= i0) ? 1 : 0)) & (t0b - ((jb >= i0) ? 1 : 0));
+                        acc1 &= (t1a - ((ja >= i1) ? 1 : 0)) & (t1b - ((jb >= i1) ? 1 : 0));
                     }
                     kill = ((acc0 >= 0) ? 1u : 0u) | ((acc1 >= 0) ? 2u : 0u);
                 } else {
@@ -344,14 +386,17 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
 #pragma unroll
                         for (int k = 0; k < D; ++k) xi[k] = lv ? x[i * D + k] : Elem<T>::big();
                         int32_t acc = (int32_t)0x80000000;
-                        _Pragma("unroll UNR")
-                        for (int r2 = 0; r2 < R; ++r2) {
-                            uint32_t m = lmw[r2];
-                            while (m) {
-                                const int j = 32 * r2 + __ffs((int)m) - 1;
-                                m &= m - 1;
-                                acc &= dominance_word<T, D>(xi, x, i, j);
+                        for (int pr = 0; pr < npairs; ++pr) {
+                            T xa[D], xb[D];
+                            int ja, jb;
+                            load_pair(pr, xa, xb, ja, jb);
+                            int32_t ta = Elem<T>::bits(xi[0] - xa[0]), tb = Elem<T>::bits(xi[0] - xb[0]);
+#pragma unroll
+                            for (int k = 1; k < D; ++k) {
+                                ta |= Elem<T>::bits(xi[k] - xa[k]);
+                                tb |= Elem<T>::bits(xi[k] - xb[k]);
                             }
+                            acc &= (ta - ((ja >= i) ? 1 : 0)) & (tb - ((jb >= i) ? 1 : 0));
                         }
                         kill |= (acc >= 0) ? (1u << r) : 0u;
                     }
@@ -419,11 +464,14 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
 #pragma unroll
                         for (int k = 0; k < D; ++k) exceed |= Elem<T>::to_float(x[i * D + k]) >= p.threshold;
                     }
-                } else if (p.ops) {
+                } else if (p.ops) {  // every reference op rewrites dead rows with the padding value: usually they hold it
+                    uint32_t bad = 0;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        chg = chg || (x[i * D + k] != padv);
-                        x[i * D + k] = padv;
+                    for (int k = 0; k < D; ++k) bad |= (uint32_t)Elem<T>::bits(x[i * D + k]) ^ (uint32_t)Elem<T>::bits(padv);
+                    if (bad) {
+                        chg = true;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) x[i * D + k] = padv;
                     }
                 }
             }

@@ -11,7 +11,8 @@ int launch_generic_rt(const StepParams& p, int dev, cudaStream_t stream) {
     const int W = p.N * D;
     const int Wpad = (W + 3) & ~3;
     const int R = (p.N + 31) / 32;
-    const int slot_words = Wpad * (OBS ? 3 : 2) + ((R + 3) & ~3);  // two state buffers (+ features) + live-mask words
+    // two state buffers (+ features) + live-mask words + the compact list of live rows (N + 1 rows)
+    const int slot_words = Wpad * (OBS ? 3 : 2) + ((R + 3) & ~3) + (((p.N + 1) * generic_compact_stride(D) + 3) & ~3);
     int warps = 8;
     while (warps > 1 && (size_t)warps * slot_words * 4 > 160 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * slot_words * 4;

@@ -46,17 +46,6 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// One dominance word for victim row xi against dominator row j of the shared game:
-// sign 0 <=> row j kills the victim (see op_newton in hk_small.cuh for the derivation).
-template <typename T, int D>
-__device__ __forceinline__ int32_t dominance_word(const T (&xi)[D], const T* x, int i, int j) {
-    int32_t t = Elem<T>::bits(xi[0] - x[j * D]);
-#pragma unroll
-    for (int k = 1; k < D; ++k) t |= Elem<T>::bits(xi[k] - x[j * D + k]);
-    t -= (j >= i) ? 1 : 0;  // ties only kill from a lower slot; also neutralises the self pair
-    return t;
-}
-
 // words per row of the compact live-row list: D coordinates + the slot number, rounded up to an even
 // count so that a pair of rows is a whole number of 16-byte words
 __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2) & ~1; }

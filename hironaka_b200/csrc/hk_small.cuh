@@ -18,9 +18,6 @@ constexpr int SMALL_BAR_BYTES = 256;
 #ifndef HK_SPARSE_STORE_MAX
 #define HK_SPARSE_STORE_MAX 16  // at most this many changed games of a tile are written one by one (tools/tune_small.cu: 4 -> 71.2, 8 -> 68.3, 16 -> 67.3, 32 -> 75.7 us/step at C2)
 #endif
-#ifndef HK_ROLLED_MIN
-#define HK_ROLLED_MIN 12  // smallest tier whose victim loop is rolled (tools/tune_small.cu)
-#endif
 
 // WARPS warps per CTA, each with a private ring of STAGES tiles.  With STAGES >= 3 the refill of a
 // stage is issued one iteration after its store (cp.async.bulk.wait_group.read 1), so the issuing

@@ -454,8 +454,29 @@ def measure_secondary(torch, lib, C, dev):
                                  "features + dones + fused step with features + order-preserving replay append (6 launches, "
                                  "no host sync)", "us_per_step": ms * 1e3, "game_steps_per_s": B / (ms * 1e-3),
                      "bound": "launch latency (Python-driven, 4096 games)"}
+        # the same replay-buffer generation through the FusedGame drop-in with fixed players, eager and as a CUDA graph
+        from hironaka_b200 import FusedGame, TensorPoints
+        from hironaka_b200.players import AllCoordHostModule, ChooseFirstAgentModule
+        game = FusedGame(AllCoordHostModule(d, N, dev), ChooseFirstAgentModule(d, N, dev), device=dev)
+        pts4 = TensorPoints(pristine.clone(), device=dev)
+        buf2 = ReplayBuffer((N, d), 4, 1 << 16, dev)
+        graph = game.graphed_step_into(buf2, pts4, "host", scale_observation=True, exploration_rate=0.2)
+
+        def eager(i):
+            if i % T == 0:
+                pts4.points.copy_(pristine)
+            game.step_into(buf2, pts4, "host", scale_observation=True, exploration_rate=0.2)
+
+        def graphed(i):
+            if i % T == 0:
+                pts4.points.copy_(pristine)
+            graph.replay()
+        out["C4"]["fused_game_step_into_us"] = {"eager": timed(eager, 100) * 1e3, "cuda_graph": timed(graphed, 300) * 1e3,
+                                                "note": "FusedGame.step_into with AllCoord host / ChooseFirst agent modules, "
+                                                        "exploration 0.2, scale_observation: nets, noise, fused step, "
+                                                        "features, order-preserving append"}
     except Exception as e:
-        out["C4"] = {"error": repr(e)}
+        out["C4"] = {**out.get("C4", {}), "error": repr(e)}
 
     # C5: dim=5, max_num_points=64, batch 256K, T=20 — the warp-per-game kernel, ALU-bound shape
     B, N, d, T = 1 << 18, 64, 5, 20

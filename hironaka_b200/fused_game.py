@@ -96,6 +96,34 @@ class FusedGame:
             buffer.add_masked(done, {"points": observations, "coords": host_move}, agent_move, reward, next_done,
                               {"points": next_observations, "coords": next_host_move})
 
+    def graphed_step_into(self, buffer, points: TensorPoints, sample_for: str, masked=True, scale_observation=True,
+                          exploration_rate=0.2, warmup: int = 2) -> "torch.cuda.CUDAGraph":
+        """``step_into`` captured ONCE in a CUDA graph; ``graph.replay()`` then plays one move of every
+        game and appends the experiences, with no Python between the launches.  This is the form for
+        replay-buffer generation at DQN batch sizes (a few thousand games), where the step is a few
+        dozen small launches and the eager version is bound by Python and launch latency
+        (BASELINE config 4).  Legal because no entry point of the library allocates or synchronises and
+        the buffer's write position lives on the device; the nets' inference and the exploration
+        noise (torch RNG, graph-safe) are captured with it.  `points` and `buffer` must stay the same
+        objects (the graph holds their storage); the warm-up moves are undone before the capture."""
+        dev = points.points.device
+        saved = points.points.clone()
+        counters = [t.clone() for t in (buffer._pos, buffer._full, buffer._appended)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):  # allocator, shared-memory opt-in, lazy module state
+                self.step_into(buffer, points, sample_for, masked, scale_observation, exploration_rate)
+            points.points.copy_(saved)
+            for t, c in zip((buffer._pos, buffer._full, buffer._appended), counters):
+                t.copy_(c)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step_into(buffer, points, sample_for, masked, scale_observation, exploration_rate)
+        return graph
+
     def host_move(self, points: TensorPoints, masked=True, exploration_rate=0.0) -> Tuple[torch.Tensor, torch.Tensor]:
         """Host net -> argmax (or noise) -> multi-binary host move (fused_game.py:104-122)."""
         with torch.inference_mode():

@@ -290,6 +290,43 @@ def test_fused_game_step_into_buffer_matches_step():
                 assert torch.equal(b1.next_observations[k], b2.next_observations[k])
 
 
+def test_fused_game_graphed_step_into():
+    """step_into captured in a CUDA graph: replays fill the buffer and move the points exactly as the
+    eager calls do (deterministic players, no exploration), with the warm-up moves undone."""
+    from hironaka_b200 import FusedGame, ReplayBuffer, TensorPoints
+    from hironaka_b200.players import AllCoordHostModule, ChooseFirstAgentModule
+    dev_ = torch.device("cuda")
+    rng = np.random.default_rng(11)
+    B, N, d = 4096, 5, 3
+    x = -np.ones((B, N, d), np.float32)
+    x[:, :4] = rng.integers(0, 9, (B, 4, d))
+    for sample_for in ("host", "agent"):
+        game = FusedGame(AllCoordHostModule(d, N, dev_), ChooseFirstAgentModule(d, N, dev_), device=dev_)
+        shape = (N, d) if sample_for == "host" else {"points": (N, d), "coords": (d,)}
+        b1, b2 = ReplayBuffer(shape, 4, 1 << 15, dev_), ReplayBuffer(shape, 4, 1 << 15, dev_)
+        p1, p2 = TensorPoints(T(x)), TensorPoints(T(x))
+        for p in (p1, p2):
+            p.get_newton_polytope()
+        graph = game.graphed_step_into(b2, p2, sample_for, scale_observation=True, exploration_rate=0.0)
+        assert b2.pos == 0 and torch.equal(p1.points, p2.points)  # the warm-up left no trace
+        for _ in range(5):
+            game.step_into(b1, p1, sample_for, scale_observation=True, exploration_rate=0.0)
+            graph.replay()
+        torch.cuda.synchronize()
+        assert b1.pos == b2.pos and b1.pos > 0
+        assert torch.equal(p1.points, p2.points)
+        n = b1.pos
+        for a, b in ((b1.actions, b2.actions), (b1.rewards, b2.rewards), (b1.dones, b2.dones)):
+            assert torch.equal(a[:n], b[:n])
+        if sample_for == "host":
+            assert torch.equal(b1.observations[:n], b2.observations[:n])
+            assert torch.equal(b1.next_observations[:n], b2.next_observations[:n])
+        else:
+            for k in ("points", "coords"):
+                assert torch.equal(b1.observations[k][:n], b2.observations[k][:n])
+                assert torch.equal(b1.next_observations[k][:n], b2.next_observations[k][:n])
+
+
 # ---- functional JAX-style API (test/testJAX.py:80-153,205-219,461-488) ------------------------
 def test_functional_api():
     from hironaka_b200 import functional as F

@@ -50,12 +50,14 @@ __device__ __forceinline__ void cp_async_wait() {
 // count so that a pair of rows is a whole number of 16-byte words
 __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2) & ~1; }
 
-// smem per warp: two state buffers x[2][Wpad], then (OBS) f[Wpad] floats, then lmw[ceil(N/32)] (padded to
+// smem per warp: DEPTH + 1 state buffers x[DEPTH + 1][Wpad] (the games up to DEPTH iterations ahead are in
+// flight while the current one is processed), then (OBS) f[Wpad] floats, then lmw[ceil(N/32)] (padded to
 // 4 words), then the compact list of live rows, (N + 1) * generic_compact_stride(D) words
 // RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
 // guards become predication) or 0 for any N (run-time loops).
-template <typename T, int D, bool OBS, int RT>
+template <typename T, int D, bool OBS, int RT, int DEPTH>
 __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
+    constexpr int NBUF = DEPTH + 1;
     constexpr int UNR = RT > 0 ? RT : 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     const int R = RT > 0 ? RT : ((N + 31) >> 5);
     const int Wpad = (W + 3) & ~3;
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * slot_words;
-    float* f = reinterpret_cast<float*>(slot + 2 * Wpad);
-    uint32_t* lmw = slot + 2 * Wpad + (OBS ? Wpad : 0);
+    float* f = reinterpret_cast<float*>(slot + NBUF * Wpad);
+    uint32_t* lmw = slot + NBUF * Wpad + (OBS ? Wpad : 0);
     constexpr int CSTRIDE = generic_compact_stride(D);                            // words per compact row (even)
     uint32_t* comp = lmw + ((((N + 31) >> 5) + 3) & ~3);                          // (N + 1) compact rows, 16-byte aligned
 
@@ -76,6 +78,13 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     const T padv = Elem<T>::pad(p.pad);
     const int OW = W + (p.obs_coord ? D : 0);
     const bool inplace = (gout == gin) && !(p.flags & HK_F_STORE_ALL);
+    // the short path for ended games covers plain single steps only
+    const bool ended_fast_path =
+        p.T == 1 && !(OBS && p.obs) && !p.host_out && !(p.ops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON)) &&
+        !(p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
+    const bool compact_path =
+        p.T == 1 && !(OBS && p.obs) && !p.host_out && !(p.ops & HK_OP_DEDUPE) &&
+        !(p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long nw = (long long)gridDim.x * warps_per_cta;
@@ -101,17 +110,30 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     };
 
     int b = 0;
-    if (gw < p.B) prefetch(gw, 0);
-    cp_async_commit();
-    for (long long g = gw; g < p.B; g += nw, b ^= 1) {
-        if (g + nw < p.B) prefetch(g + nw, b ^ 1);
-        cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
-        int32_t ha = 3, ax = 0;
-        if (p.ops & HK_OP_SHIFT) {
-            if (p.host_action) ha = load_action(p.host_action, g, p.flags);
-            if (p.axis) ax = load_action(p.axis, g, p.flags);
+    int32_t ha_nx = 3, ax_nx = 0;
+    if ((p.ops & HK_OP_SHIFT) && gw < p.B) {
+        if (p.host_action) ha_nx = load_action(p.host_action, gw, p.flags);
+        if (p.axis) ax_nx = load_action(p.axis, gw, p.flags);
+    }
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) {
+        if (gw + k * nw < p.B) prefetch(gw + k * nw, k);
+        cp_async_commit();
+    }
+    for (long long g = gw; g < p.B; g += nw, b = (b + 1 == NBUF) ? 0 : b + 1) {
+        {   // the buffer that held the previous game is free: the game DEPTH iterations ahead goes there
+            const int bn = (b + DEPTH >= NBUF) ? b + DEPTH - NBUF : b + DEPTH;
+            if (g + DEPTH * nw < p.B) prefetch(g + DEPTH * nw, bn);
         }
-        cp_async_wait<1>();  // everything but the newest group has landed: game g is in buffer b
+        cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
+        // this game's actions were requested one iteration ago (a dependent global load per game would
+        // otherwise sit on the critical path of the short iterations); request the next game's now
+        int32_t ha = ha_nx, ax = ax_nx;
+        if ((p.ops & HK_OP_SHIFT) && g + nw < p.B) {
+            if (p.host_action) ha_nx = load_action(p.host_action, g + nw, p.flags);
+            if (p.axis) ax_nx = load_action(p.axis, g + nw, p.flags);
+        }
+        cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
         T* x = reinterpret_cast<T*>(slot + b * Wpad);
 
@@ -139,6 +161,234 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
             }
             cnt += __popc(__ballot_sync(0xffffffffu, lv));
             mylive |= lv ? (1u << r) : 0u;
+        }
+        // ---- ended games, single step: a short path of their own ----
+        // Most games of a long rollout have at most one live row; nothing of the machinery below
+        // (ballot rounds, the step loop, the filter) applies to them.  The lone row's lane plays the
+        // step, lane 0 writes the outputs (done before the step: no reward), and the state is stored
+        // only if the row moved or a dead row needed normalising.
+        if (cnt <= 1 && ended_fast_path) {
+            bool exceed = false;
+            _Pragma("unroll UNR")
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + 32 * r;
+                if (i >= N) continue;
+                if ((mylive >> r) & 1u) {
+                    T v[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = x[i * D + k];
+                    if (p.ops & HK_OP_SHIFT) {
+                        const uint32_t cm = action_mask(ha, p.flags);
+                        bool apply = (ax >= 0) && (ax < D) && !(p.flags & HK_F_FREEZE_ENDED);
+                        if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                        T s = Elem<T>::zero();
+#pragma unroll
+                        for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + v[k] : s;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) v[k] = (apply && k == ax) ? s : v[k];
+                    }
+                    if (p.ops & HK_OP_REPOSITION) {  // a lone point minus its own coordinates
+#pragma unroll
+                        for (int k = 0; k < D; ++k) v[k] = Elem<T>::zero();
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        chg = chg || (Elem<T>::bits(v[k]) != Elem<T>::bits(x[i * D + k]));
+                        x[i * D + k] = v[k];
+                        exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
+                    }
+                } else if (p.ops) {
+                    uint32_t bad = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) bad |= (uint32_t)Elem<T>::bits(x[i * D + k]) ^ (uint32_t)Elem<T>::bits(padv);
+                    if (bad) {
+                        chg = true;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) x[i * D + k] = padv;
+                    }
+                }
+            }
+            if (lane == 0) {
+                if (p.done) p.done[g] = 1;
+                if (p.reward) p.reward[g] = (p.flags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
+                if (p.done_count) atomicAdd(p.done_count, 1);
+                if (p.num_points) p.num_points[g] = cnt;
+                if (p.length) p.length[g] = 0;
+            }
+            if (p.exceed_flag) {
+                if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
+            }
+            __syncwarp();
+            if (gout && __any_sync(0xffffffffu, chg)) {
+                const uint32_t* src = slot + b * Wpad;
+                uint32_t* dst = gout + g * W;
+                if (vec_out) {
+                    for (int c = lane; c < (W >> 2); c += 32)
+                        reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+                } else {
+                    for (int w = lane; w < W; w += 32) dst[w] = src[w];
+                }
+            }
+            __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
+            continue;
+        }
+        // ---- games with 2 .. 32 live rows, single step: one COMPACT row per lane ----
+        // The general path below keeps the padded layout (lane l owns rows l, l+32, ...) and pays for it
+        // with ballot rounds and row loops in every op: ~1 200 warp-instructions for a three-point
+        // game.  Here the live rows are compacted first (the list the filter needs anyway), lane v
+        // takes compact row v, the whole step runs on one row per lane, and the survivors go back to
+        // their slots: ~150 + 12 per live row.
+        if (cnt >= 2 && cnt <= 32 && compact_path) {
+            int base = 0;
+            _Pragma("unroll UNR")
+            for (int r = 0; r < R; ++r) {
+                const bool lv = (mylive >> r) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, lv);
+                if (lv) {
+                    const int i = lane + 32 * r;
+                    uint32_t* dst = comp + (base + __popc(bal & ((1u << lane) - 1u))) * CSTRIDE;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) dst[k] = (uint32_t)Elem<T>::bits(x[i * D + k]);
+                    dst[D] = (uint32_t)i;
+                }
+                base += __popc(bal);
+            }
+            __syncwarp();
+            const bool act = lane < cnt;
+            T v[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) v[k] = act ? Elem<T>::from_bits(comp[lane * CSTRIDE + k]) : Elem<T>::big();
+            const int myslot = act ? (int)comp[lane * CSTRIDE + D] : 0;
+            bool rowchg = false;
+            if (p.ops & HK_OP_SHIFT) {
+                const uint32_t cm = action_mask(ha, p.flags);
+                bool apply = (ax >= 0) && (ax < D);
+                if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                if (apply && act) {  // (HK_F_FREEZE_ENDED: this game has two or more live rows)
+                    T s = Elem<T>::zero();
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + v[k] : s;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        if (k == ax) {
+                            rowchg = rowchg || (v[k] != s);
+                            v[k] = s;
+                        }
+                    }
+                }
+            }
+            if (p.ops & HK_OP_REPOSITION) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const T mn = warp_min<T>(v[k]);  // idle lanes hold +BIG
+                    rowchg = rowchg || (mn != Elem<T>::zero());
+                    v[k] = act ? v[k] - mn : v[k];
+                }
+            }
+            uint32_t live = (cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+            if (p.ops & HK_OP_NEWTON) {
+                __syncwarp();
+                if (act) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) comp[lane * CSTRIDE + k] = (uint32_t)Elem<T>::bits(v[k]);
+                }
+                __syncwarp();
+                if ((cnt & 1) && lane <= D) comp[cnt * CSTRIDE + lane] = comp[(cnt - 1) * CSTRIDE + lane];
+                __syncwarp();
+                int32_t acc = (int32_t)0x80000000;
+                const int npairs = (cnt + 1) >> 1;
+                for (int pr = 0; pr < npairs; ++pr) {  // two dominators per trip, 16-byte broadcast loads
+                    uint32_t w[2 * CSTRIDE];
+                    const uint4* src = reinterpret_cast<const uint4*>(comp + pr * 2 * CSTRIDE);
+#pragma unroll
+                    for (int q = 0; q < CSTRIDE / 2; ++q) {
+                        const uint4 u = src[q];
+                        w[4 * q] = u.x, w[4 * q + 1] = u.y, w[4 * q + 2] = u.z, w[4 * q + 3] = u.w;
+                    }
+                    int32_t ta = 0, tb = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        ta |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[k]));
+                        tb |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[CSTRIDE + k]));
+                    }
+                    // compact order is slot order: ties only kill from a lower position (also neutralises the
+                    // self pair; the padding copy of the last row sits at position cnt >= every lane)
+                    acc &= (ta - ((2 * pr >= lane) ? 1 : 0)) & (tb - ((2 * pr + 1 >= lane) ? 1 : 0));
+                }
+                live = __ballot_sync(0xffffffffu, act && (acc < 0));
+            }
+            const bool alive = (live >> lane) & 1u;
+            if constexpr (Elem<T>::is_float) {
+                if (p.ops & HK_OP_RESCALE) {
+                    float mx = -1.0f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) mx = alive ? fmaxf(mx, v[k]) : mx;
+                    mx = warp_maxf(mx);
+                    if (mx == 0.0f) mx = 1.0f;
+                    if (mx > 0.0f && alive) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float q = (v[k] != 0.0f) ? __fdiv_rn(v[k], mx) : v[k];
+                            rowchg = rowchg || (q != v[k]);
+                            v[k] = q;
+                        }
+                    }
+                }
+            }
+            // survivors and killed rows go back to their slots of the padded game
+            bool exceed = false;
+            if (act && (rowchg || !alive)) {
+                chg = true;
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[myslot * D + k] = alive ? v[k] : padv;
+            }
+            if (alive && p.exceed_flag) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
+            }
+            if (p.ops) {  // dead rows that do not hold the padding value are normalised, as every reference op does
+                _Pragma("unroll UNR")
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i >= N || ((mylive >> r) & 1u)) continue;
+                    uint32_t bad = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) bad |= (uint32_t)Elem<T>::bits(x[i * D + k]) ^ (uint32_t)Elem<T>::bits(padv);
+                    if (bad) {
+                        chg = true;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) x[i * D + k] = padv;
+                    }
+                }
+            }
+            const int ncnt = __popc(live);
+            const bool dn = ncnt < 2;
+            if (lane == 0) {
+                if (p.done) p.done[g] = dn ? 1 : 0;
+                if (p.reward) {
+                    const float rw = dn ? 1.0f : 0.0f;  // the game was not done before this step
+                    p.reward[g] = (p.flags & HK_F_ROLE_AGENT) ? -rw : rw;
+                }
+                if (p.done_count && dn) atomicAdd(p.done_count, 1);
+                if (p.num_points) p.num_points[g] = ncnt;
+                if (p.length) p.length[g] = dn ? 1 : 2;
+            }
+            if (p.exceed_flag) {
+                if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
+            }
+            __syncwarp();
+            if (gout && __any_sync(0xffffffffu, chg)) {
+                const uint32_t* src = slot + b * Wpad;
+                uint32_t* dst = gout + g * W;
+                if (vec_out) {
+                    for (int c = lane; c < (W >> 2); c += 32)
+                        reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+                } else {
+                    for (int w = lane; w < W; w += 32) dst[w] = src[w];
+                }
+            }
+            __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
+            continue;
         }
         int32_t len = (cnt < 2) ? 0 : p.T + 1;
         for (int st = 0; st < p.T; ++st) {

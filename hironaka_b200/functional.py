@@ -249,3 +249,59 @@ def rollout_postprocess(rollouts, role: str, dimension: int, discount: float, us
                                     1 if use_unified_tree else 0, torch.cuda.current_stream(o.device).cuda_stream)
     check(rc, "hk_value_targets")
     return obs.reshape(-1, W), policy.reshape(-1, policy.shape[2]), out.reshape(-1).to(value.dtype)
+
+
+# ---- policy-side glue of util.py (tensor plumbing around the nets; no game arithmetic) ------------------
+
+@functools.lru_cache()
+def get_value_est_fn(role: str) -> Callable:
+    """Value estimate of an unfinished game from its point count: +-1 / max(num_points, 1)
+    (get_value_est_fn, util.py:152-169)."""
+    sign = 1 if role == "host" else -1
+
+    def est_fn(last_values: torch.Tensor, num_points: torch.Tensor) -> torch.Tensor:
+        return 1.0 / torch.clamp(num_points.to(torch.float32), min=1.0) * sign
+    return est_fn
+
+
+def apply_agent_action_mask(agent_policy: Callable, dimension: int) -> Callable:
+    """Masks an agent policy with the host's coordinate choice, read from the last `dimension` entries
+    of the observation (apply_agent_action_mask, util.py:287-305): masked-out logits become -inf."""
+
+    def masked_agent_policy(x: torch.Tensor, *args, **kwargs):
+        mask = x[..., x.shape[-1] - dimension:] > 0.5
+        policy_prior, value_prior = agent_policy(x, *args, **kwargs)
+        return torch.where(mask, policy_prior, torch.full_like(policy_prior, float("-inf"))), value_prior
+
+    masked_agent_policy.__name__ = getattr(agent_policy, "__name__", type(agent_policy).__name__)
+    return masked_agent_policy
+
+
+def action_wrapper(policy_value_fn: Callable, dimension: Optional[int] = None) -> Callable:
+    """(policy_logits, value) function -> one-hot action function, with the agent's action mask when
+    `dimension` is given (action_wrapper, util.py:308-327)."""
+    masked_action = policy_value_fn if dimension is None else apply_agent_action_mask(policy_value_fn, dimension)
+
+    def wrapped_action_fn(x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        out, _ = masked_action(x, *args, **kwargs)
+        return torch.nn.functional.one_hot(out.argmax(dim=-1), out.shape[-1]).to(out.dtype)
+
+    wrapped_action_fn.__name__ = getattr(policy_value_fn, "__name__", type(policy_value_fn).__name__)
+    return wrapped_action_fn
+
+
+def rollout_sanity_tests(rollout, spec: Tuple[int, int]) -> bool:
+    """The reference's check of a rollout (obs, policy, value) (rollout_sanity_tests, util.py:395-423):
+    masked-out actions of agent states must carry -inf logits, and the policy must not already be a
+    softmax (rows that sum to 1 with entries in [0, 1])."""
+    obs, policy, value = rollout
+    n, d = spec
+    if obs.shape[-1] == (n + 1) * d:
+        mask = obs[..., -d:] > 0.5
+        is_host = (~mask).all(dim=-1, keepdim=True)  # host observations are padded with zeros there
+        mask = torch.cat([mask | is_host, is_host.expand(*is_host.shape[:-1], policy.shape[-1] - d)], dim=-1)
+        if bool((policy[~mask] != float("-inf")).any()):
+            return False
+    soft = torch.isclose(policy.sum(dim=-1), torch.ones((), dtype=policy.dtype, device=policy.device)).all() and \
+        ((policy <= 1.0) & (policy >= 0.0)).all()
+    return not bool(soft)

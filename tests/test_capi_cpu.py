@@ -160,3 +160,27 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C2")
     for k in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data"):
         assert k in line
+
+
+def test_policy_glue_of_functional():
+    """get_value_est_fn / apply_agent_action_mask / action_wrapper / rollout_sanity_tests
+    (hironaka/jax/util.py:152-169,287-327,395-423): tensor plumbing, runs anywhere."""
+    torch = pytest.importorskip("torch")
+    from hironaka_b200 import functional as F
+    est = F.get_value_est_fn("agent")(torch.zeros(3), torch.tensor([0, 2, 5]))
+    assert torch.allclose(est, torch.tensor([-1.0, -0.5, -0.2]))
+    n, d = 4, 3
+    obs = torch.zeros(2, (n + 1) * d)
+    obs[0, -d:] = torch.tensor([1.0, 0.0, 1.0])
+    obs[1, -d:] = torch.tensor([0.0, 1.0, 1.0])
+
+    def policy(x):
+        return torch.tensor([[0.1, 5.0, 0.3], [2.0, 0.1, 0.3]]), torch.zeros(2)
+    masked, _ = F.apply_agent_action_mask(policy, d)(obs)
+    assert masked[0].tolist() == [pytest.approx(0.1), float("-inf"), pytest.approx(0.3)]
+    act = F.action_wrapper(policy, d)(obs)
+    assert act.tolist() == [[0.0, 0.0, 1.0], [0.0, 0.0, 1.0]]
+    assert F.rollout_sanity_tests((obs, masked, torch.zeros(2)), (n, d))
+    assert not F.rollout_sanity_tests((obs, policy(obs)[0], torch.zeros(2)), (n, d))  # mask not applied
+    soft = torch.softmax(torch.randn(2, 3), dim=-1)
+    assert not F.rollout_sanity_tests((torch.zeros(2, n * d), soft, torch.zeros(2)), (n, d))  # already a softmax

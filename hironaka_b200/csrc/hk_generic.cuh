@@ -1,14 +1,15 @@
 // hk_generic.cuh — warp-per-game step kernel for any (N <= 1024, d <= 10).
 //
-// Mapping (DESIGN.md "K-warp"): one warp owns one game at a time; lane l owns rows l, l+32, ...
-// The game's N*d words are double-buffered in the warp's private shared-memory slots with
-// cp.async (LDGSTS): while game g is processed, game g + (number of warps) streams in, so every
-// warp always has one game in flight (games of this class are 1-16 KB, too small for an efficient
-// TMA transaction each).  Results leave through coalesced 16-byte stores.  The dominance filter
-// broadcasts candidate dominators j from shared memory (uniform address => one wavefront) and
-// iterates ONLY over live j (warp-uniform loop over the ballot words), so cost tracks the number
-// of live points rather than N.  This is the kernel for BASELINE config 5 (N=64, d=5) and for
-// remove_repeated alone.
+// Mapping (DESIGN.md "K-warp"): one warp owns one game at a time.  The game's N*d words are
+// double-buffered in the warp's private shared-memory slots with cp.async (LDGSTS): while game g is
+// processed, game g + (number of warps) streams in (games of this class are 1-16 KB, too small for an
+// efficient TMA transaction each); results leave through coalesced 16-byte stores, and an unchanged
+// game of an in-place call is not stored at all.  After the liveness pass a game takes one of three
+// routes: ended games (<= 1 live row) a short path of their own; games with 2-32 live rows are
+// compacted and stepped with ONE compact row per lane; everything else (more live rows, multi-step
+// rollouts, fused observation, fixed players, remove_repeated) runs on the padded layout, lane l
+// owning rows l, l+32, ..., with the compact list of live rows feeding the dominator loop.  This is
+// the kernel for BASELINE config 5 (N=64, d=5).
 #pragma once
 #include "hk_common.cuh"
 

@@ -1,14 +1,17 @@
 // hk_small.cuh — thread-per-game step kernel for small games (N <= 32, N*d words in registers).
 //
 // Mapping (DESIGN.md "K-small"): one lane owns one game; a warp owns tiles of 32 consecutive
-// games.  Each warp runs a private STAGES-deep shared-memory ring: lane 0 issues one TMA bulk
-// load per tile (32*N*d*4 contiguous bytes), all lanes wait on the stage's mbarrier, read
-// their own game with conflict-free vector LDS (game stride N*d words: 16-byte reads are
-// conflict-free when N*d/4 is odd, 8-byte when N*d/2 is odd, 4-byte when N*d is odd — true for
-// (20,3), (10,3), (5,3)), run the whole step in registers with every loop fully unrolled, write
-// the new state back into the same stage and lane 0 issues one TMA bulk store.  No CTA-wide
-// barrier exists anywhere; warps drift freely, which overlaps one warp's loads with another's
-// ALU phase.
+// games.  Each warp has a private shared-memory ring of STAGES tiles (one in the shipped geometry):
+// lane 0 issues one TMA bulk load per tile (32*N*d*4 contiguous bytes), all lanes wait on the stage's
+// mbarrier and read their own game with conflict-free vector LDS (game stride N*d words: 16-byte
+// reads are conflict-free when N*d/4 is odd, 8-byte when N*d/2 is odd, 4-byte when N*d is odd —
+// true for (20,3), (10,3), (5,3)).  The warp picks a tier from the largest live count among its 32
+// games, every lane gathers its live rows into that many register rows and runs the step there
+// (small tiers fully unrolled, 12 and 16 rows with a rolled victim loop).  Only games that changed
+// are written back when the call is in place: one TMA bulk store of the tile when many did, one
+// coalesced copy per game when few did, nothing when none did.  The fused observation features
+// (OBS) are a second phase on the new state: a sorting network on packed row keys.  No CTA-wide
+// barrier exists anywhere; warps drift freely, which overlaps one warp's loads with another's ALU phase.
 #pragma once
 #include "hk_common.cuh"
 

@@ -184,8 +184,11 @@ __device__ __forceinline__ uint32_t op_newton_rolled(T (&y)[K * D], uint32_t clm
         }
     }
     uint32_t kill = 0;
+    // compact rows fill from 0: rows past the highest one that is live in SOME game of the warp are dead
+    // in every lane and need no pass (the tier is chosen by the maximum, so this trims its rounding)
+    const int kb = 32 - __clz((int)__reduce_or_sync(0xffffffffu, clm));
 #pragma unroll 1
-    for (int i = 0; i < K; ++i) {
+    for (int i = 0; i < kb; ++i) {
         T v[D];
         if constexpr (RS == 4 && D == 3) {
             const uint4 q = *reinterpret_cast<const uint4*>(scratch + i * 4);

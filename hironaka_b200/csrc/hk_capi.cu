@@ -68,9 +68,12 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
         const bool agent_fixed = p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
         if ((p.flags & HK_F_HOST_ALL_COORD) && (p.flags & HK_F_HOST_ZEILLINGER)) return HK_ERR_BAD_ARG;
         if ((p.flags & HK_F_AGENT_FIRST) && (p.flags & HK_F_AGENT_LAST)) return HK_ERR_BAD_ARG;
+        const bool packed = p.flags & HK_F_ACT_PACKED;
+        if (packed && (host_fixed || agent_fixed || p.d > 5)) return HK_ERR_BAD_ARG;
         if (host_fixed) p.host_action = nullptr;
-        if (agent_fixed) p.axis = nullptr;
-        if ((p.ops & HK_OP_SHIFT) && ((!host_fixed && p.host_action == nullptr) || (!agent_fixed && p.axis == nullptr)))
+        if (agent_fixed || packed) p.axis = nullptr;
+        if ((p.ops & HK_OP_SHIFT) &&
+            ((!host_fixed && p.host_action == nullptr) || (!agent_fixed && !packed && p.axis == nullptr)))
             return HK_ERR_BAD_ARG;
     }
     if ((p.ops & HK_OP_RESCALE) && dtype != HK_DTYPE_F32) return HK_ERR_UNSUPPORTED;
@@ -464,14 +467,15 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
                     float* reward_host, int32_t* done_count_host, uint32_t ops, uint32_t flags) {
     if (!s) return HK_ERR_BAD_ARG;
     DeviceGuard guard_(s->device);
-    const size_t abytes = (size_t)s->B * ((flags & HK_F_ACT_U8) ? 1 : 4);
+    const bool packed = flags & HK_F_ACT_PACKED;
+    const size_t abytes = (size_t)s->B * ((flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4);
     if ((ops & HK_OP_SHIFT) && host_action_host)
         HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, abytes, cudaMemcpyHostToDevice, s->stream));
-    if ((ops & HK_OP_SHIFT) && axis_host)
+    if ((ops & HK_OP_SHIFT) && axis_host && !packed)
         HK_CUDA(cudaMemcpyAsync(s->axis, axis_host, abytes, cudaMemcpyHostToDevice, s->stream));
     StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
     p.host_action = host_action_host ? s->host_action : nullptr;
-    p.axis = axis_host ? s->axis : nullptr;
+    p.axis = (axis_host && !packed) ? s->axis : nullptr;
     p.done = done_host ? s->done : nullptr;
     p.reward = reward_host ? s->reward : nullptr;
     p.ops = ops;
@@ -491,7 +495,8 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
 
 int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                        int32_t* done_count_host, uint32_t ops, uint32_t flags) {
-    if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || !axis_host) return HK_ERR_BAD_ARG;
+    const bool packed = flags & HK_F_ACT_PACKED;
+    if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || (!axis_host && !packed)) return HK_ERR_BAD_ARG;
     DeviceGuard guard_(s->device);
     if (s->counts_cap < T) {
         cudaFree(s->counts);
@@ -503,7 +508,7 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
         HK_CUDA(cudaMallocHost((void**)&s->counts_pinned, (size_t)T * 4));
         s->counts_cap = T;
     }
-    const size_t esz = (flags & HK_F_ACT_U8) ? 1 : 4;
+    const size_t esz = (flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4;
     const size_t abytes = (size_t)s->B * esz;
     HK_CUDA(cudaMemsetAsync(s->counts, 0, (size_t)T * 4, s->stream));
     for (int t = 0; t < T; ++t) {
@@ -521,13 +526,14 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
         }
         HK_CUDA(cudaMemcpyAsync(ha, (const char*)host_action_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
                                 s->copy_stream));
-        HK_CUDA(cudaMemcpyAsync(ax, (const char*)axis_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
-                                s->copy_stream));
+        if (!packed)
+            HK_CUDA(cudaMemcpyAsync(ax, (const char*)axis_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
+                                    s->copy_stream));
         HK_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
         HK_CUDA(cudaStreamWaitEvent(s->stream, s->ready[slot], 0));
         StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
         p.host_action = ha;
-        p.axis = ax;
+        p.axis = packed ? nullptr : ax;
         p.done_count = s->counts + t;
         p.ops = ops;
         p.flags = flags;

@@ -113,8 +113,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     int b = 0;
     int32_t ha_nx = 3, ax_nx = 0;
     if ((p.ops & HK_OP_SHIFT) && gw < p.B) {
-        if (p.host_action) ha_nx = load_action(p.host_action, gw, p.flags);
-        if (p.axis) ax_nx = load_action(p.axis, gw, p.flags);
+        load_actions(p, gw, ha_nx, ax_nx);
     }
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) {
@@ -131,8 +130,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         // otherwise sit on the critical path of the short iterations); request the next game's now
         int32_t ha = ha_nx, ax = ax_nx;
         if ((p.ops & HK_OP_SHIFT) && g + nw < p.B) {
-            if (p.host_action) ha_nx = load_action(p.host_action, g + nw, p.flags);
-            if (p.axis) ax_nx = load_action(p.axis, g + nw, p.flags);
+            load_actions(p, g + nw, ha_nx, ax_nx);
         }
         cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
@@ -395,8 +393,7 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
         for (int st = 0; st < p.T; ++st) {
             int32_t ha_n = 3, ax_n = 0;
             if ((p.ops & HK_OP_SHIFT) && st + 1 < p.T) {
-                if (p.host_action) ha_n = load_action(p.host_action, (long long)(st + 1) * p.B + g, p.flags);
-                if (p.axis) ax_n = load_action(p.axis, (long long)(st + 1) * p.B + g, p.flags);
+                load_actions(p, (long long)(st + 1) * p.B + g, ha_n, ax_n);
             }
             const bool prev_done = cnt < 2;
 

@@ -60,15 +60,24 @@ class HostSession:
         double-buffered against the running step, the finished-game count of every step is read
         back; returns int32 [T].  Pass pinned arrays (e.g. torch.empty(..., pin_memory=True).numpy())
         for full PCIe speed."""
-        want = np.uint8 if flags & C.HK_F_ACT_U8 else np.int32
+        packed = bool(flags & C.HK_F_ACT_PACKED)  # one uint8 per game-step: host action | axis << 5; `axes` unused
+        want = np.uint8 if flags & (C.HK_F_ACT_U8 | C.HK_F_ACT_PACKED) else np.int32
         ha = np.ascontiguousarray(host_actions, dtype=want)
-        ax = np.ascontiguousarray(axes, dtype=want)
-        if ha.ndim != 2 or ha.shape[1] != self.B or ax.shape != ha.shape:
+        ax = None if packed else np.ascontiguousarray(axes, dtype=want)
+        if ha.ndim != 2 or ha.shape[1] != self.B or (ax is not None and ax.shape != ha.shape):
             raise ValueError("host_actions and axes must be [T, B]")
         counts = np.zeros(ha.shape[0], dtype=np.int32)
-        check(lib().hk_session_rollout(self._h, ha.ctypes.data, ax.ctypes.data, ha.shape[0], counts.ctypes.data,
-                                       ops, flags), "hk_session_rollout")
+        check(lib().hk_session_rollout(self._h, ha.ctypes.data, None if ax is None else ax.ctypes.data, ha.shape[0],
+                                       counts.ctypes.data, ops, flags), "hk_session_rollout")
         return counts
+
+    @staticmethod
+    def pack_actions(host_actions: np.ndarray, axes: np.ndarray) -> np.ndarray:
+        """HK_F_ACT_PACKED encoding of two action streams: host action (< 32) | axis (< 8) << 5, uint8."""
+        ha, ax = np.asarray(host_actions), np.asarray(axes)
+        if ha.max(initial=0) > 31 or ax.max(initial=0) > 7 or ha.min(initial=0) < 0 or ax.min(initial=0) < 0:
+            raise ValueError("packed actions need host actions < 32 and axes < 8")
+        return (ha.astype(np.uint8) | (ax.astype(np.uint8) << 5)).astype(np.uint8)
 
     def close(self) -> None:
         if self._h:

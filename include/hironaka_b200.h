@@ -85,6 +85,10 @@ extern "C" {
                                               ListPoints (Python sorted(points, reverse=True), hironaka/src/_list_ops.py:25) */
 #define HK_F_STORE_ALL (1u << 13) /* in-place calls (out == in) write back only the games that changed; set this to
                                      rewrite every game (the results are identical; for measurements) */
+#define HK_F_ACT_PACKED (1u << 14) /* host_action[] is a uint8 array holding BOTH players' actions, one byte per game(-step):
+                                      the host action (coordinate bitmask or discrete id, < 32) in the low 5 bits, the agent's
+                                      axis (< 8) in the high 3 bits; axis[] is ignored.  Halves the bytes of an action stream
+                                      again (1 instead of 2 per game-step).  Needs d <= 5; not with the fixed players. */
 
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);

@@ -562,12 +562,35 @@ def test_uint8_actions_and_session_rollout():
                                 None, B, N, d, C.HK_DTYPE_I32, op_bits, rc_flags, -1.0, 1e8,
                                 torch.cuda.current_stream().cuda_stream))
         assert eq(st, o)
-        # host-buffer session, int32 and uint8 streams
-        for u8 in (False, True):
+        # one packed byte per game-step (HK_F_ACT_PACKED: id | axis << 5), per-step launches and a one-launch rollout
+        packed = HostSession.pack_actions(ha, ax)
+        st = T(x)
+        for t in range(Tn):
+            pk = T(packed[t])
+            check(lib().hk_step(st.data_ptr(), st.data_ptr(), pk.data_ptr(), None, None, None, None, None, None, None,
+                                B, N, d, C.HK_DTYPE_I32, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED, -1.0, 1e8,
+                                torch.cuda.current_stream().cuda_stream))
+        assert eq(st, o)
+        st, pk = T(x), T(packed)
+        dc = torch.zeros(Tn, dtype=torch.int32, device="cuda")
+        check(lib().hk_rollout(st.data_ptr(), st.data_ptr(), pk.data_ptr(), None, None, None, dc.data_ptr(), None, B, N, d,
+                               Tn, C.HK_DTYPE_I32, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED, -1.0,
+                               torch.cuda.current_stream().cuda_stream))
+        assert eq(st, o) and dc.tolist() == counts
+        # packed actions are refused where they cannot be represented or make no sense
+        assert lib().hk_step(st.data_ptr(), st.data_ptr(), pk.data_ptr(), None, None, None, None, None, None, None, B, N, d,
+                             C.HK_DTYPE_I32, op_bits, C.HK_F_ACT_PACKED | C.HK_F_AGENT_FIRST, -1.0, 1e8,
+                             torch.cuda.current_stream().cuda_stream) != 0
+        # host-buffer session: int32, uint8 and packed streams
+        for mode in ("i32", "u8", "packed"):
             s = HostSession(x)
-            dt = np.uint8 if u8 else np.int32
-            got = s.rollout(ha.astype(dt), ax.astype(dt), op_bits, C.HK_F_ACT_DISCRETE | (C.HK_F_ACT_U8 if u8 else 0))
-            assert got.tolist() == counts and np.array_equal(s.get_state(), o)
+            if mode == "packed":
+                got = s.rollout(packed, None, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED)
+            else:
+                dt = np.uint8 if mode == "u8" else np.int32
+                got = s.rollout(ha.astype(dt), ax.astype(dt), op_bits,
+                                C.HK_F_ACT_DISCRETE | (C.HK_F_ACT_U8 if mode == "u8" else 0))
+            assert got.tolist() == counts and np.array_equal(s.get_state(), o), mode
             s.close()
 
 

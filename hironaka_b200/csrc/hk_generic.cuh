@@ -90,17 +90,23 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long nw = (long long)gridDim.x * warps_per_cta;
 
+    // lane l copies the 16-byte chunks l, l+32, ... of a game: how many that is
+    const int chunks = W >> 2;
+    const int chunk_iters = (chunks >> 5) + (((chunks & 31) > lane) ? 1 : 0);
     auto prefetch = [&](long long g, int b) {
         uint32_t* dst = slot + b * Wpad;
         const uint32_t* src = gin + g * W;
         if (vec_in) {
             if constexpr (RT > 0) {  // at most RT*32 rows: a fixed number of 16-byte chunks per lane, guarded
                 constexpr int ITERS = (RT * 32 * D / 4 + 31) / 32;
-                const uint32_t* s16 = src + 4 * lane;
-                uint32_t* d16 = dst + 4 * lane;
+                // one shared-memory address and one global address per call, immediate offsets per chunk
+                const uint32_t d16 = smem_u32(dst) + 16u * lane;
+                const char* s16 = reinterpret_cast<const char*>(src) + 16 * lane;
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
-                    if (lane + 32 * it < (W >> 2)) cp_async_16(d16 + 128 * it, s16 + 128 * it);
+                    if (it < chunk_iters)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d16 + 512u * it), "l"(s16 + 512 * it)
+                                     : "memory");
                 }
             } else {
                 for (int c = lane; c < (W >> 2); c += 32) cp_async_16(dst + 4 * c, src + 4 * c);
@@ -194,7 +200,10 @@ __global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, 
                     for (int k = 0; k < D; ++k) {
                         chg = chg || (Elem<T>::bits(v[k]) != Elem<T>::bits(x[i * D + k]));
                         x[i * D + k] = v[k];
-                        exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
+                    }
+                    if (p.exceed_flag) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
                     }
                 } else if (p.ops) {
                     uint32_t bad = 0;

@@ -125,3 +125,37 @@ def test_host_policy_agrees_with_fused_player():
         ops.step(a, None, None, ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=C.HK_F_HOST_ZEILLINGER | C.HK_F_AGENT_FIRST, inplace=True)
         ops.step(b, mask, None, ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=C.HK_F_AGENT_FIRST, inplace=True)
         assert torch.equal(a, b)
+
+
+def test_vec_agent_env_random_agent_and_generated_points():
+    """RandomAgent: the axis is drawn uniformly among the chosen coordinates (fewer than two chosen:
+    no move); reset() without points draws them like generate_points (hironaka/src/_fn.py:184-185)."""
+    from hironaka_b200 import VecHironakaAgentEnv
+    B, N, d = 20000, 10, 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    env = VecHironakaAgentEnv(B, agent="random", dimension=d, max_num_points=N, max_value=15, scale_observation=False,
+                              generator=g)
+    obs = env.reset()
+    assert obs.shape == (B, N, d) and float(obs.max()) < 15 and float(obs.min()) >= -1
+    before = env.points.clone()
+    # single coordinate chosen: nothing may move
+    a = torch.zeros((B, d), dtype=torch.int32)
+    a[:, 1] = 1
+    env.step(a)
+    assert torch.equal(env.points, before)
+    # two coordinates chosen: exactly one of them receives the sum, each about half of the time
+    a[:, 2] = 1
+    live = before[:, :, 0] >= 0
+    env.step(a)
+    # undo the filter's effect by recomputing the shift on the old state for both candidate axes
+    s = before[:, :, 1] + before[:, :, 2]
+    moved1 = before.clone(); moved1[:, :, 1] = torch.where(live, s, moved1[:, :, 1])
+    moved2 = before.clone(); moved2[:, :, 2] = torch.where(live, s, moved2[:, :, 2])
+    from hironaka_b200 import constants as C, ops
+    for m in (moved1, moved2):
+        ops.step(m, ops=C.HK_OP_NEWTON, inplace=True)
+    is1 = (env.points == moved1).reshape(B, -1).all(1)
+    is2 = (env.points == moved2).reshape(B, -1).all(1)
+    assert bool((is1 | is2).all())
+    frac = float((is1 & ~is2).float().sum() / ((is1 ^ is2).float().sum() + 1e-9))
+    assert 0.45 < frac < 0.55, frac

@@ -314,6 +314,44 @@ def test_inplace_writes_only_changed_games(hb, family, shape, dtype):
             assert np.array_equal(g_all.cpu().numpy(), o), (ops_bits, flags, t, "store_all")
 
 
+@pytest.mark.parametrize("shape", [(40003, 20, 3), (30001, 10, 3), (20001, 5, 3), (6011, 64, 5), (4001, 16, 4), (1003, 33, 3)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_changed_games_only_equals_store_all_under_caller_rewrites(hb, shape):
+    """Long in-place rollouts, both dtypes and flavours, while the caller overwrites some games between
+    steps (dead rows that are not the padding value included): the default write-back of changed games
+    only and HK_F_STORE_ALL must stay identical in state and in every output.  The two kernel families
+    are covered by the shapes."""
+    from hironaka_b200 import constants as C, ops
+    B, N, d = shape
+    rng = np.random.default_rng(B)
+    for dtype in (torch.int32, torch.float32):
+        for ops_bits, flags in ((C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, 0),
+                                (C.HK_OP_SHIFT | C.HK_OP_NEWTON, C.TORCH_SEMANTICS)):
+            x = rng.integers(0, 12, (B, N, d)).astype(np.int32)
+            x[rng.random((B, N)) < 0.4] = -1
+            a = torch.from_numpy(x).cuda().to(dtype)
+            b = a.clone()
+            for t in range(16):
+                ha = torch.from_numpy(rng.integers(0, 2 ** d, B).astype(np.int32)).cuda()
+                ax = torch.from_numpy(rng.integers(0, d, B).astype(np.int32)).cuda()
+                ra = ops.step(a, ha, ax, ops=ops_bits, flags=flags, inplace=True, want_done=True, want_reward=True,
+                              want_num_points=True)
+                rb = ops.step(b, ha, ax, ops=ops_bits, flags=flags | C.HK_F_STORE_ALL, inplace=True, want_done=True,
+                              want_reward=True, want_num_points=True)
+                assert torch.equal(a, b), (dtype, ops_bits, t)
+                assert torch.equal(ra.done, rb.done) and torch.equal(ra.reward, rb.reward), (dtype, ops_bits, t)
+                assert torch.equal(ra.num_points, rb.num_points), (dtype, ops_bits, t)
+                if t % 5 == 3:
+                    idx = torch.from_numpy(rng.permutation(B)[:B // 40]).cuda()  # distinct games
+                    fresh = rng.integers(-3, 9, (B // 40, N, d)).astype(np.int32)
+                    dead = fresh[:, :, 0] < 0
+                    fresh[dead] = -5                       # dead rows that are not the padding value
+                    fresh[~dead] = np.maximum(fresh[~dead], 0)
+                    fresh = torch.from_numpy(fresh).cuda().to(dtype)
+                    a[idx] = fresh
+                    b[idx] = fresh
+
+
 F_ALL, F_ZEIL, F_FIRST, F_LAST = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 
 

@@ -13,6 +13,10 @@
 #pragma once
 #include "hk_common.cuh"
 
+#ifndef HK_GENERIC_MIN_CTAS
+#define HK_GENERIC_MIN_CTAS 4  // resident CTAs of 8 warps the register budget is sized for (tools/time_c5.py)
+#endif
+
 namespace hk {
 
 template <typename T>
@@ -57,7 +61,7 @@ __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2)
 // RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
 // guards become predication) or 0 for any N (run-time loops).
 template <typename T, int D, bool OBS, int RT, int DEPTH>
-__global__ void __launch_bounds__(256, 4) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
+__global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
     constexpr int NBUF = DEPTH + 1;
     constexpr int UNR = RT > 0 ? RT : 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];

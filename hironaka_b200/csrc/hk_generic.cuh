@@ -51,6 +51,9 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+constexpr uint32_t GENERIC_HOT_OPS = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON;
+constexpr uint32_t GENERIC_HOT_FLAGS = HK_F_ACT_DISCRETE;
+
 // words per row of the compact live-row list: D coordinates + the slot number, rounded up to an even
 // count so that a pair of rows is a whole number of 16-byte words
 __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2) & ~1; }
@@ -60,9 +63,15 @@ __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2)
 // 4 words), then the compact list of live rows, (N + 1) * generic_compact_stride(D) words
 // RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
 // guards become predication) or 0 for any N (run-time loops).
-template <typename T, int D, bool OBS, int RT, int DEPTH>
+template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT>
 __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
     constexpr int NBUF = DEPTH + 1;
+    // HOT: the plain random-play step (shift + reposition + newton, discrete host ids, int32 action arrays,
+    // one step, no observation) with its op and flag words known at compile time, so that the dozens of
+    // run-time tests of them fold away; every other call takes the general instantiation.
+    const uint32_t kops = HOT ? GENERIC_HOT_OPS : p.ops;
+    const uint32_t kflags = HOT ? GENERIC_HOT_FLAGS : p.flags;
+    const int kT = HOT ? 1 : p.T;
     constexpr int UNR = RT > 0 ? RT : 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,14 +91,14 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
     const bool vec_out = aligned16(p.out) && ((W & 3) == 0);
     const T padv = Elem<T>::pad(p.pad);
     const int OW = W + (p.obs_coord ? D : 0);
-    const bool inplace = (gout == gin) && !(p.flags & HK_F_STORE_ALL);
+    const bool inplace = (gout == gin) && !(kflags & HK_F_STORE_ALL);
     // the short path for ended games covers plain single steps only
     const bool ended_fast_path =
-        p.T == 1 && !(OBS && p.obs) && !p.host_out && !(p.ops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON)) &&
-        !(p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
+        kT == 1 && !(OBS && p.obs) && !p.host_out && !(kops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON)) &&
+        !(kflags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
     const bool compact_path =
-        p.T == 1 && !(OBS && p.obs) && !p.host_out && !(p.ops & HK_OP_DEDUPE) &&
-        !(p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
+        kT == 1 && !(OBS && p.obs) && !p.host_out && !(kops & HK_OP_DEDUPE) &&
+        !(kflags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
     const long long nw = (long long)gridDim.x * warps_per_cta;
@@ -122,8 +131,8 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
 
     int b = 0;
     int32_t ha_nx = 3, ax_nx = 0;
-    if ((p.ops & HK_OP_SHIFT) && gw < p.B) {
-        load_actions(p, gw, ha_nx, ax_nx);
+    if ((kops & HK_OP_SHIFT) && gw < p.B) {
+        load_actions(p, kflags, gw, ha_nx, ax_nx);
     }
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) {
@@ -139,8 +148,8 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         // this game's actions were requested one iteration ago (a dependent global load per game would
         // otherwise sit on the critical path of the short iterations); request the next game's now
         int32_t ha = ha_nx, ax = ax_nx;
-        if ((p.ops & HK_OP_SHIFT) && g + nw < p.B) {
-            load_actions(p, g + nw, ha_nx, ax_nx);
+        if ((kops & HK_OP_SHIFT) && g + nw < p.B) {
+            load_actions(p, kflags, g + nw, ha_nx, ax_nx);
         }
         cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
@@ -186,17 +195,17 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     T v[D];
 #pragma unroll
                     for (int k = 0; k < D; ++k) v[k] = x[i * D + k];
-                    if (p.ops & HK_OP_SHIFT) {
-                        const uint32_t cm = action_mask(ha, p.flags);
-                        bool apply = (ax >= 0) && (ax < D) && !(p.flags & HK_F_FREEZE_ENDED);
-                        if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                    if (kops & HK_OP_SHIFT) {
+                        const uint32_t cm = action_mask(ha, kflags);
+                        bool apply = (ax >= 0) && (ax < D) && !(kflags & HK_F_FREEZE_ENDED);
+                        if (kflags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
                         T s = Elem<T>::zero();
 #pragma unroll
                         for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + v[k] : s;
 #pragma unroll
                         for (int k = 0; k < D; ++k) v[k] = (apply && k == ax) ? s : v[k];
                     }
-                    if (p.ops & HK_OP_REPOSITION) {  // a lone point minus its own coordinates
+                    if (kops & HK_OP_REPOSITION) {  // a lone point minus its own coordinates
 #pragma unroll
                         for (int k = 0; k < D; ++k) v[k] = Elem<T>::zero();
                     }
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
 #pragma unroll
                         for (int k = 0; k < D; ++k) exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
                     }
-                } else if (p.ops) {
+                } else if (kops) {
                     uint32_t bad = 0;
 #pragma unroll
                     for (int k = 0; k < D; ++k) bad |= (uint32_t)Elem<T>::bits(x[i * D + k]) ^ (uint32_t)Elem<T>::bits(padv);
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             }
             if (lane == 0) {
                 if (p.done) p.done[g] = 1;
-                if (p.reward) p.reward[g] = (p.flags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
+                if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
                 if (p.done_count) atomicAdd(p.done_count, 1);
                 if (p.num_points) p.num_points[g] = cnt;
                 if (p.length) p.length[g] = 0;
@@ -272,10 +281,10 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             for (int k = 0; k < D; ++k) v[k] = act ? Elem<T>::from_bits(comp[lane * CSTRIDE + k]) : Elem<T>::big();
             const int myslot = act ? (int)comp[lane * CSTRIDE + D] : 0;
             bool rowchg = false;
-            if (p.ops & HK_OP_SHIFT) {
-                const uint32_t cm = action_mask(ha, p.flags);
+            if (kops & HK_OP_SHIFT) {
+                const uint32_t cm = action_mask(ha, kflags);
                 bool apply = (ax >= 0) && (ax < D);
-                if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                if (kflags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
                 if (apply && act) {  // (HK_F_FREEZE_ENDED: this game has two or more live rows)
                     T s = Elem<T>::zero();
 #pragma unroll
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     }
                 }
             }
-            if (p.ops & HK_OP_REPOSITION) {
+            if (kops & HK_OP_REPOSITION) {
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const T mn = warp_min<T>(v[k]);  // idle lanes hold +BIG
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
             }
             uint32_t live = (cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-            if (p.ops & HK_OP_NEWTON) {
+            if (kops & HK_OP_NEWTON) {
                 __syncwarp();
                 if (act) {
 #pragma unroll
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             }
             const bool alive = (live >> lane) & 1u;
             if constexpr (Elem<T>::is_float) {
-                if (p.ops & HK_OP_RESCALE) {
+                if (kops & HK_OP_RESCALE) {
                     float mx = -1.0f;
 #pragma unroll
                     for (int k = 0; k < D; ++k) mx = alive ? fmaxf(mx, v[k]) : mx;
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
 #pragma unroll
                 for (int k = 0; k < D; ++k) exceed = exceed || (Elem<T>::to_float(v[k]) >= p.threshold);
             }
-            if (p.ops) {  // dead rows that do not hold the padding value are normalised, as every reference op does
+            if (kops) {  // dead rows that do not hold the padding value are normalised, as every reference op does
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 if (p.done) p.done[g] = dn ? 1 : 0;
                 if (p.reward) {
                     const float rw = dn ? 1.0f : 0.0f;  // the game was not done before this step
-                    p.reward[g] = (p.flags & HK_F_ROLE_AGENT) ? -rw : rw;
+                    p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
                 }
                 if (p.done_count && dn) atomicAdd(p.done_count, 1);
                 if (p.num_points) p.num_points[g] = ncnt;
@@ -402,21 +411,21 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
             continue;
         }
-        int32_t len = (cnt < 2) ? 0 : p.T + 1;
-        for (int st = 0; st < p.T; ++st) {
+        int32_t len = (cnt < 2) ? 0 : kT + 1;
+        for (int st = 0; st < kT; ++st) {
             int32_t ha_n = 3, ax_n = 0;
-            if ((p.ops & HK_OP_SHIFT) && st + 1 < p.T) {
-                load_actions(p, (long long)(st + 1) * p.B + g, ha_n, ax_n);
+            if ((kops & HK_OP_SHIFT) && st + 1 < kT) {
+                load_actions(p, kflags, (long long)(st + 1) * p.B + g, ha_n, ax_n);
             }
             const bool prev_done = cnt < 2;
 
             // ---- shift ----
-            if ((p.ops & HK_OP_SHIFT) && cnt == 0 && p.host_out && lane == 0) p.host_out[g] = 0;
-            if ((p.ops & HK_OP_SHIFT) && cnt > 0) {
+            if ((kops & HK_OP_SHIFT) && cnt == 0 && p.host_out && lane == 0) p.host_out[g] = 0;
+            if ((kops & HK_OP_SHIFT) && cnt > 0) {
                 uint32_t cm;
-                if (p.flags & HK_F_HOST_ALL_COORD) {
+                if (kflags & HK_F_HOST_ALL_COORD) {
                     cm = (1u << D) - 1u;
-                } else if (p.flags & HK_F_HOST_ZEILLINGER) {
+                } else if (kflags & HK_F_HOST_ZEILLINGER) {
                     // Zeillinger's host, lane-parallel: every lane scans the pairs (i, j) of its own rows i,
                     // then a lexicographic (L, S, flat index) minimum is reduced over the warp
                     _Pragma("unroll UNR")
@@ -472,16 +481,16 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     cm = zeillinger_mask_from_diff<D>(vi, vj, found);
                     __syncwarp();
                 } else {
-                    cm = action_mask(ha, p.flags);
+                    cm = action_mask(ha, kflags);
                 }
-                ax = agent_policy_axis(cm, ax, p.flags, D);
+                ax = agent_policy_axis(cm, ax, kflags, D);
                 bool apply = (ax >= 0) && (ax < D);
                 if (p.host_out) {  // hk_host_policy: report the host's choice, move nothing
                     if (lane == 0) p.host_out[g] = (int32_t)cm;
                     apply = false;
                 }
-                if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
-                if (p.flags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
+                if (kflags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                if (kflags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
                 if (apply) {
                     _Pragma("unroll UNR")
                     for (int r = 0; r < R; ++r) {
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
             }
             // ---- reposition ----
-            if ((p.ops & HK_OP_REPOSITION) && cnt == 1) {
+            if ((kops & HK_OP_REPOSITION) && cnt == 1) {
                 // a lone point minus its own coordinates: the origin (most games of a long rollout are here)
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                         x[i * D + k] = Elem<T>::zero();
                     }
                 }
-            } else if ((p.ops & HK_OP_REPOSITION) && cnt > 1) {
+            } else if ((kops & HK_OP_REPOSITION) && cnt > 1) {
                 T mn[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) mn[k] = Elem<T>::big();
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
             }
             // ---- dedupe alone (remove_repeated _fn.py:192-213) ----
-            if ((p.ops & HK_OP_DEDUPE) && cnt >= 2) {
+            if ((kops & HK_OP_DEDUPE) && cnt >= 2) {
                 __syncwarp();
                 uint32_t kill = 0;
                 _Pragma("unroll UNR")
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 mylive &= ~kill;
             }
             // ---- newton: dedupe + dominance, reading the pre-removal state ----
-            if ((p.ops & HK_OP_NEWTON) && cnt >= 2) {
+            if ((kops & HK_OP_NEWTON) && cnt >= 2) {
                 // The live rows are first copied, in slot order, into a COMPACT list in shared memory (row k at
                 // k*CSTRIDE: D coordinates, then the slot number), so that the dominator loop walks it linearly
                 // with 16-byte broadcast loads, two dominators per trip, instead of decoding ballot words into row
@@ -657,7 +666,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             }
             // ---- rescale (float state) ----
             if constexpr (Elem<T>::is_float) {
-                if (p.ops & HK_OP_RESCALE) {
+                if (kops & HK_OP_RESCALE) {
                     float mx = -1.0f;
                     _Pragma("unroll UNR")
                     for (int r = 0; r < R; ++r) {
@@ -693,7 +702,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 if (p.done) p.done[(long long)st * p.B + g] = dn ? 1 : 0;
                 if (p.reward) {
                     float rw = (dn && !prev_done) ? 1.0f : 0.0f;
-                    p.reward[(long long)st * p.B + g] = (p.flags & HK_F_ROLE_AGENT) ? -rw : rw;
+                    p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
                 }
                 if (p.done_count && dn) atomicAdd(p.done_count + st, 1);
             }
@@ -714,7 +723,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
 #pragma unroll
                         for (int k = 0; k < D; ++k) exceed |= Elem<T>::to_float(x[i * D + k]) >= p.threshold;
                     }
-                } else if (p.ops) {  // every reference op rewrites dead rows with the padding value: usually they hold it
+                } else if (kops) {  // every reference op rewrites dead rows with the padding value: usually they hold it
                     uint32_t bad = 0;
 #pragma unroll
                     for (int k = 0; k < D; ++k) bad |= (uint32_t)Elem<T>::bits(x[i * D + k]) ^ (uint32_t)Elem<T>::bits(padv);
@@ -757,7 +766,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
                 mx = warp_maxf(mx);
                 if (mx == 0.0f) mx = 1.0f;
-                const bool resc = (p.flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
+                const bool resc = (kflags & HK_F_OBS_RESCALE) && (mx > 0.0f);
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
@@ -772,9 +781,9 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
                 __syncwarp();
                 float* gobs = p.obs + g * (long long)OW;
-                const bool sorted = p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
-                const bool lex = p.flags & HK_F_OBS_SORT_LEX;
-                const bool lexf = p.flags & HK_F_OBS_SORT_LEX_FIRST;
+                const bool sorted = kflags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST);
+                const bool lex = kflags & HK_F_OBS_SORT_LEX;
+                const bool lexf = kflags & HK_F_OBS_SORT_LEX_FIRST;
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {
                     const int i = lane + 32 * r;
@@ -812,7 +821,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     for (int k = 0; k < D; ++k) gobs[rank * D + k] = fi[k];
                 }
                 if (p.obs_coord && lane < D) {
-                    const uint32_t ocm = action_mask(load_action(p.obs_coord, g, p.flags), p.flags);
+                    const uint32_t ocm = action_mask(load_action(p.obs_coord, g, kflags), kflags);
                     gobs[W + lane] = (float)((ocm >> lane) & 1u);
                 }
             }

@@ -1,13 +1,15 @@
 // hk_generic_launch.inl — launch code of the warp-per-game kernel, included by hk_generic_*.cu
+#include <type_traits>
+
 #include "hk_generic.cuh"
 #include "hk_launch.cuh"
 
 namespace hk {
 namespace {
 
-template <typename T, int D, bool OBS, int RT, int DEPTH>
-int launch_generic_depth(const StepParams& p, int dev, cudaStream_t stream) {
-    auto kernel = hk_generic_kernel<T, D, OBS, RT, DEPTH>;
+template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT>
+int launch_generic_hot(const StepParams& p, int dev, cudaStream_t stream) {
+    auto kernel = hk_generic_kernel<T, D, OBS, RT, DEPTH, HOT>;
     const int W = p.N * D;
     const int Wpad = (W + 3) & ~3;
     const int R = (p.N + 31) / 32;
@@ -52,7 +54,13 @@ int launch_generic_depth(const StepParams& p, int dev, cudaStream_t stream) {
 // the latency of its loads.
 template <typename T, int D, bool OBS, int RT>
 int launch_generic_rt(const StepParams& p, int dev, cudaStream_t stream) {
-    return launch_generic_depth<T, D, OBS, RT, 1>(p, dev, stream);
+    // the plain random-play step of an int32 state has an instantiation with its op / flag words folded in
+    if constexpr (!OBS && RT > 0 && std::is_same<T, int32_t>::value) {
+        const bool hot = p.T == 1 && p.ops == GENERIC_HOT_OPS && p.flags == GENERIC_HOT_FLAGS && !p.host_out &&
+                         p.host_action && p.axis;
+        if (hot) return launch_generic_hot<T, D, OBS, RT, 1, true>(p, dev, stream);
+    }
+    return launch_generic_hot<T, D, OBS, RT, 1, false>(p, dev, stream);
 }
 
 // rows-per-lane specialisations exist for the common dimensions; everything else takes run-time loops

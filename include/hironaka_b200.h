@@ -100,7 +100,7 @@ int hk_kernel_class(int N, int d);
  * warp-per-game kernel too (so both kernel families are parity-tested on every shape). */
 int hk_debug_force_generic(int on);
 /* Tuning hook: programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) of
- * the thread-per-game kernel, on by default; results do not depend on it. */
+ * the thread-per-game kernel, off by default (measured: no gain); results do not depend on it. */
 int hk_debug_set_pdl(int on);
 
 /* ---- the fused step ------------------------------------------------------------------
@@ -113,7 +113,9 @@ int hk_debug_set_pdl(int on);
  *
  *   state_in / state_out  [B,N,d] dtype; may be the same pointer (in place = the reference's
  *                         inplace=True) or disjoint (inplace=False).  Dead rows are negative in
- *                         coordinate 0 and are rewritten with padding_value.
+ *                         coordinate 0 and are rewritten with padding_value.  In place, only the games
+ *                         the step changed are written back (same result, fewer bytes; HK_F_STORE_ALL
+ *                         rewrites every game).
  *   host_action [B] int32 coordinate bitmask or discrete id (HK_F_ACT_DISCRETE); required with HK_OP_SHIFT
  *   axis        [B] int32 agent's coordinate; required with HK_OP_SHIFT
  *   done        [B] uint8  (#live rows <= 1 after the step), nullable        (util.py:34-35)

@@ -184,3 +184,20 @@ def test_policy_glue_of_functional():
     assert not F.rollout_sanity_tests((obs, policy(obs)[0], torch.zeros(2)), (n, d))  # mask not applied
     soft = torch.softmax(torch.randn(2, 3), dim=-1)
     assert not F.rollout_sanity_tests((torch.zeros(2, n * d), soft, torch.zeros(2)), (n, d))  # already a softmax
+
+
+@pytest.mark.parametrize("n", [5, 10, 20])
+def test_committed_sorting_networks_sort(n):
+    """hk_sortnet.inc (generated by tools/gen_sortnet.py) is what the features kernel sorts row keys
+    with: the comparator lists of the instantiated sizes must sort every 0/1 input (0-1 principle)."""
+    import re
+    src = open(os.path.join(ROOT, "hironaka_b200", "csrc", "hk_sortnet.inc")).read()
+    m = re.search(r"if constexpr \(N == %d\) \{(.*?)\n\}" % n, src, re.S)
+    assert m, f"no network for n = {n}"
+    ces = [(int(a), int(b)) for a, b in re.findall(r"HK_CE\((\d+), (\d+)\)", m.group(1))]
+    assert ces and all(0 <= a < b < n for a, b in ces)
+    x = np.arange(1 << n, dtype=np.uint32)
+    bits = [(x >> i) & 1 for i in range(n)]
+    for a, b in ces:  # HK_CE(i, j): k[i] = max, k[j] = min (descending)
+        bits[a], bits[b] = np.maximum(bits[a], bits[b]), np.minimum(bits[a], bits[b])
+    assert all(bool(np.all(bits[i] >= bits[i + 1])) for i in range(n - 1))

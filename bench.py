@@ -524,6 +524,23 @@ def measure_secondary(torch, lib, C, dev):
                  "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
                  "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
                          "dense count; the dense count is what the root filter (64 live points) executes"}
+    # the same 20 steps as ONE launch (hk_rollout on the warp-per-game family: compact rows stay in registers)
+    try:
+        dcount5 = torch.zeros(T, dtype=torch.int32, device=dev)
+
+        def roll5(i):
+            x.copy_(pristine)
+            rc = lib.hk_rollout(x.data_ptr(), x.data_ptr(), ha.data_ptr(), ax.data_ptr(), None, None, dcount5.data_ptr(),
+                                None, B, N, d, T, C.HK_DTYPE_I32, C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON,
+                                C.HK_F_ACT_DISCRETE, -1.0, stream)
+            assert rc == 0
+
+        def copy5(i):
+            x.copy_(pristine)
+        ms5 = timed(roll5, 6) - timed(copy5, 6)
+        out["C5"]["rollout_fused_T20"] = {"ms_per_rollout": ms5, "game_steps_per_s": B * T / (ms5 * 1e-3)}
+    except Exception as e:
+        out["C5"]["rollout_fused_T20"] = {"error": repr(e)}
 
     # C2 with HK_F_STORE_ALL: every game written back every step (what the roofline's algorithmic bytes assume)
     try:

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         kT == 1 && !(OBS && p.obs) && !p.host_out && !(kops & ~(HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON)) &&
         !(kflags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
     const bool compact_path =
-        kT == 1 && !(OBS && p.obs) && !p.host_out && !(kops & HK_OP_DEDUPE) &&
+        !(OBS && p.obs) && !p.host_out && !(kops & HK_OP_DEDUPE) &&
         !(kflags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
@@ -253,12 +253,13 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
             continue;
         }
-        // ---- games with 2 .. 32 live rows, single step: one COMPACT row per lane ----
+        // ---- games with 2 .. 32 live rows: one COMPACT row per lane, for one step or a whole rollout ----
         // The general path below keeps the padded layout (lane l owns rows l, l+32, ...) and pays for it
         // with ballot rounds and row loops in every op: ~1 200 warp-instructions for a three-point
         // game.  Here the live rows are compacted first (the list the filter needs anyway), lane v
-        // takes compact row v, the whole step runs on one row per lane, and the survivors go back to
-        // their slots: ~150 + 12 per live row.
+        // takes compact row v and keeps it in registers for all T steps, and the survivors go back to
+        // their slots at the end: ~150 + 12 per live row and step.  Rows that die stay parked at +BIG
+        // in the compact list, so the list is built once per game.
         if (cnt >= 2 && cnt <= 32 && compact_path) {
             int base = 0;
             _Pragma("unroll UNR")
@@ -275,93 +276,144 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 base += __popc(bal);
             }
             __syncwarp();
-            const bool act = lane < cnt;
-            T v[D];
+            int ccnt = cnt;  // rows in the compact list (a long rollout rebuilds it as rows die)
+            bool act = lane < ccnt;
+            T v[D], v0[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) v[k] = act ? Elem<T>::from_bits(comp[lane * CSTRIDE + k]) : Elem<T>::big();
-            const int myslot = act ? (int)comp[lane * CSTRIDE + D] : 0;
-            bool rowchg = false;
-            if (kops & HK_OP_SHIFT) {
-                const uint32_t cm = action_mask(ha, kflags);
-                bool apply = (ax >= 0) && (ax < D);
-                if (kflags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
-                if (apply && act) {  // (HK_F_FREEZE_ENDED: this game has two or more live rows)
-                    T s = Elem<T>::zero();
+            for (int k = 0; k < D; ++k) {
+                v[k] = act ? Elem<T>::from_bits(comp[lane * CSTRIDE + k]) : Elem<T>::big();
+                v0[k] = v[k];
+            }
+            int myslot = act ? (int)comp[lane * CSTRIDE + D] : 0;
+            bool rebuilt = false;  // after a rebuild v0 no longer belongs to this lane's row: rows are written back regardless
+            if ((ccnt & 1) && lane <= D) comp[ccnt * CSTRIDE + lane] = (uint32_t)Elem<T>::bits(Elem<T>::big());  // pad row: dominates nothing
+            uint32_t live = (ccnt >= 32) ? 0xffffffffu : ((1u << ccnt) - 1u);
+            int cur = cnt;
+            int32_t len = kT + 1;
+            int npairs = (ccnt + 1) >> 1;
+            for (int st = 0; st < kT; ++st) {
+                if (st > 0 && cur >= 2 && 2 * cur <= ccnt) {
+                    // Half of the listed rows have died: rebuild the list from the survivors so that the
+                    // filter's cost keeps following the live count.  Rows that died go back to their slots
+                    // as padding now; survivors move to the lanes below `cur`.
+                    const bool alive_now = (live >> lane) & 1u;
+                    __syncwarp();
+                    if (act && !alive_now) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + v[k] : s;
+                        for (int k = 0; k < D; ++k) x[myslot * D + k] = padv;
+                    }
+                    if (alive_now) {
+                        uint32_t* dst = comp + __popc(live & ((1u << lane) - 1u)) * CSTRIDE;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) dst[k] = (uint32_t)Elem<T>::bits(v[k]);
+                        dst[D] = (uint32_t)myslot;
+                    }
+                    __syncwarp();
+                    ccnt = cur;
+                    act = lane < ccnt;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) v[k] = act ? Elem<T>::from_bits(comp[lane * CSTRIDE + k]) : Elem<T>::big();
+                    myslot = act ? (int)comp[lane * CSTRIDE + D] : 0;
+                    __syncwarp();
+                    if ((ccnt & 1) && lane <= D) comp[ccnt * CSTRIDE + lane] = (uint32_t)Elem<T>::bits(Elem<T>::big());
+                    live = (1u << ccnt) - 1u;  // (ccnt <= 16 here)
+                    npairs = (ccnt + 1) >> 1;
+                    rebuilt = true;
+                    chg = true;
+                }
+                int32_t ha_n = 3, ax_n = 0;
+                if ((kops & HK_OP_SHIFT) && st + 1 < kT) load_actions(p, kflags, (long long)(st + 1) * p.B + g, ha_n, ax_n);
+                const bool prev_done = cur < 2;
+                const bool alive0 = (live >> lane) & 1u;
+                if ((kops & HK_OP_SHIFT) && cur > 0) {
+                    const uint32_t cm = action_mask(ha, kflags);
+                    bool apply = (ax >= 0) && (ax < D);
+                    if (kflags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+                    if (kflags & HK_F_FREEZE_ENDED) apply = apply && !prev_done;
+                    if (apply && alive0) {
+                        T s = Elem<T>::zero();
+#pragma unroll
+                        for (int k = 0; k < D; ++k) s = ((cm >> k) & 1u) ? s + v[k] : s;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) v[k] = (k == ax) ? s : v[k];
+                    }
+                }
+                if ((kops & HK_OP_REPOSITION) && cur > 0) {
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        if (k == ax) {
-                            rowchg = rowchg || (v[k] != s);
-                            v[k] = s;
+                        const T mn = warp_min<T>(alive0 ? v[k] : Elem<T>::big());
+                        v[k] = alive0 ? v[k] - mn : v[k];
+                    }
+                }
+                if ((kops & HK_OP_NEWTON) && cur >= 2) {
+                    __syncwarp();
+                    if (act) {  // rows that have died are parked at +BIG: they dominate nothing
+#pragma unroll
+                        for (int k = 0; k < D; ++k)
+                            comp[lane * CSTRIDE + k] = (uint32_t)Elem<T>::bits(alive0 ? v[k] : Elem<T>::big());
+                    }
+                    __syncwarp();
+                    int32_t acc = (int32_t)0x80000000;
+                    for (int pr = 0; pr < npairs; ++pr) {  // two dominators per trip, 16-byte broadcast loads
+                        uint32_t w[2 * CSTRIDE];
+                        const uint4* src = reinterpret_cast<const uint4*>(comp + pr * 2 * CSTRIDE);
+#pragma unroll
+                        for (int q = 0; q < CSTRIDE / 2; ++q) {
+                            const uint4 u = src[q];
+                            w[4 * q] = u.x, w[4 * q + 1] = u.y, w[4 * q + 2] = u.z, w[4 * q + 3] = u.w;
                         }
-                    }
-                }
-            }
-            if (kops & HK_OP_REPOSITION) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    const T mn = warp_min<T>(v[k]);  // idle lanes hold +BIG
-                    rowchg = rowchg || (mn != Elem<T>::zero());
-                    v[k] = act ? v[k] - mn : v[k];
-                }
-            }
-            uint32_t live = (cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-            if (kops & HK_OP_NEWTON) {
-                __syncwarp();
-                if (act) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) comp[lane * CSTRIDE + k] = (uint32_t)Elem<T>::bits(v[k]);
-                }
-                __syncwarp();
-                if ((cnt & 1) && lane <= D) comp[cnt * CSTRIDE + lane] = comp[(cnt - 1) * CSTRIDE + lane];
-                __syncwarp();
-                int32_t acc = (int32_t)0x80000000;
-                const int npairs = (cnt + 1) >> 1;
-                for (int pr = 0; pr < npairs; ++pr) {  // two dominators per trip, 16-byte broadcast loads
-                    uint32_t w[2 * CSTRIDE];
-                    const uint4* src = reinterpret_cast<const uint4*>(comp + pr * 2 * CSTRIDE);
-#pragma unroll
-                    for (int q = 0; q < CSTRIDE / 2; ++q) {
-                        const uint4 u = src[q];
-                        w[4 * q] = u.x, w[4 * q + 1] = u.y, w[4 * q + 2] = u.z, w[4 * q + 3] = u.w;
-                    }
-                    int32_t ta = 0, tb = 0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        ta |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[k]));
-                        tb |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[CSTRIDE + k]));
-                    }
-                    // compact order is slot order: ties only kill from a lower position (also neutralises the
-                    // self pair; the padding copy of the last row sits at position cnt >= every lane)
-                    acc &= (ta - ((2 * pr >= lane) ? 1 : 0)) & (tb - ((2 * pr + 1 >= lane) ? 1 : 0));
-                }
-                live = __ballot_sync(0xffffffffu, act && (acc < 0));
-            }
-            const bool alive = (live >> lane) & 1u;
-            if constexpr (Elem<T>::is_float) {
-                if (kops & HK_OP_RESCALE) {
-                    float mx = -1.0f;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) mx = alive ? fmaxf(mx, v[k]) : mx;
-                    mx = warp_maxf(mx);
-                    if (mx == 0.0f) mx = 1.0f;
-                    if (mx > 0.0f && alive) {
+                        int32_t ta = 0, tb = 0;
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            const float q = (v[k] != 0.0f) ? __fdiv_rn(v[k], mx) : v[k];
-                            rowchg = rowchg || (q != v[k]);
-                            v[k] = q;
+                            ta |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[k]));
+                            tb |= Elem<T>::bits(v[k] - Elem<T>::from_bits(w[CSTRIDE + k]));
+                        }
+                        // compact order is slot order: ties only kill from a lower position (also neutralises the
+                        // self pair)
+                        acc &= (ta - ((2 * pr >= lane) ? 1 : 0)) & (tb - ((2 * pr + 1 >= lane) ? 1 : 0));
+                    }
+                    live = __ballot_sync(0xffffffffu, alive0 && (acc < 0));
+                }
+                const bool alive = (live >> lane) & 1u;
+                if constexpr (Elem<T>::is_float) {
+                    if (kops & HK_OP_RESCALE) {
+                        float mx = -1.0f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) mx = alive ? fmaxf(mx, v[k]) : mx;
+                        mx = warp_maxf(mx);
+                        if (mx == 0.0f) mx = 1.0f;
+                        if (mx > 0.0f && alive) {
+#pragma unroll
+                            for (int k = 0; k < D; ++k) v[k] = (v[k] != 0.0f) ? __fdiv_rn(v[k], mx) : v[k];
                         }
                     }
                 }
+                cur = __popc(live);
+                const bool dn = cur < 2;
+                if (lane == 0) {
+                    if (p.done) p.done[(long long)st * p.B + g] = dn ? 1 : 0;
+                    if (p.reward) {
+                        const float rw = (dn && !prev_done) ? 1.0f : 0.0f;
+                        p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
+                    }
+                    if (p.done_count && dn) atomicAdd(p.done_count + st, 1);
+                }
+                if (dn && !prev_done) len = st + 1;
+                ha = ha_n;
+                ax = ax_n;
             }
             // survivors and killed rows go back to their slots of the padded game
+            const bool alive = (live >> lane) & 1u;
             bool exceed = false;
-            if (act && (rowchg || !alive)) {
-                chg = true;
+            if (act) {
+                bool rowchg = !alive || rebuilt;
 #pragma unroll
-                for (int k = 0; k < D; ++k) x[myslot * D + k] = alive ? v[k] : padv;
+                for (int k = 0; k < D; ++k) rowchg = rowchg || (Elem<T>::bits(v[k]) != Elem<T>::bits(v0[k]));
+                if (rowchg) {
+                    chg = true;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[myslot * D + k] = alive ? v[k] : padv;
+                }
             }
             if (alive && p.exceed_flag) {
 #pragma unroll
@@ -382,17 +434,9 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     }
                 }
             }
-            const int ncnt = __popc(live);
-            const bool dn = ncnt < 2;
             if (lane == 0) {
-                if (p.done) p.done[g] = dn ? 1 : 0;
-                if (p.reward) {
-                    const float rw = dn ? 1.0f : 0.0f;  // the game was not done before this step
-                    p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
-                }
-                if (p.done_count && dn) atomicAdd(p.done_count, 1);
-                if (p.num_points) p.num_points[g] = ncnt;
-                if (p.length) p.length[g] = dn ? 1 : 2;
+                if (p.num_points) p.num_points[g] = cur;
+                if (p.length) p.length[g] = len;
             }
             if (p.exceed_flag) {
                 if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;

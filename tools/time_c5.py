@@ -39,3 +39,21 @@ per = np.mean(np.array(per), axis=0)
 print("flags", extra, "root filter %.3f ms | mean step %.4f ms = %.3e game-steps/s | hbm frac %.3f" % (
     np.mean(root), per.mean(), B / (per.mean() * 1e-3), B * 2573 / (per.mean() * 1e-3) / 6543.7e9))
 print(" per step:", " ".join("%.3f" % v for v in per), "| done", int(done.sum()), "checksum", int(x.sum()))
+
+# one-launch rollout (hk_rollout): the 20 steps in a single launch, state read and written once
+dcount = torch.zeros(T, dtype=torch.int32, device=dev)
+ms = []
+for rep in range(4):
+    x = x0.clone()
+    assert L.hk_step(x.data_ptr(), x.data_ptr(), None, None, None, None, None, None, None, None, B, N, d, 0,
+                     C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0, -1.0, 1e8, stream) == 0
+    dcount.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    assert L.hk_rollout(x.data_ptr(), x.data_ptr(), ha.data_ptr(), ax.data_ptr(), None, None, dcount.data_ptr(), None,
+                        B, N, d, T, 0, C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, C.HK_F_ACT_DISCRETE | extra,
+                        -1.0, stream) == 0
+    e1.record(); torch.cuda.synchronize()
+    if rep: ms.append(e0.elapsed_time(e1))
+print("one-launch rollout of %d steps: %.3f ms = %.3e game-steps/s | finished per step %s | checksum %d" % (
+    T, np.mean(ms), B * T / (np.mean(ms) * 1e-3), dcount.tolist()[-3:], int(x.sum())))

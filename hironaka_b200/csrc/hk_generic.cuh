@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
 #pragma unroll
                         for (int k = 0; k < D; ++k) mx = alive ? fmaxf(mx, v[k]) : mx;
                         mx = warp_maxf(mx);
-                        if (mx == 0.0f) mx = 1.0f;
+                        if (mx == 0.0f || ((kflags & HK_F_RESCALE_EPS) && mx > 0.0f && mx <= 1e-8f)) mx = 1.0f;
                         if (mx > 0.0f && alive) {
 #pragma unroll
                             for (int k = 0; k < D; ++k) v[k] = (v[k] != 0.0f) ? __fdiv_rn(v[k], mx) : v[k];
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                         for (int k = 0; k < D; ++k) mx = fmaxf(mx, x[i * D + k]);
                     }
                     mx = warp_maxf(mx);
-                    if (mx == 0.0f) mx = 1.0f;
+                    if (mx == 0.0f || ((kflags & HK_F_RESCALE_EPS) && mx > 0.0f && mx <= 1e-8f)) mx = 1.0f;
                     if (mx > 0.0f) {
                         _Pragma("unroll UNR")
                         for (int r = 0; r < R; ++r) {
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     for (int k = 0; k < D; ++k) mx = fmaxf(mx, Elem<T>::to_float(x[i * D + k]));
                 }
                 mx = warp_maxf(mx);
-                if (mx == 0.0f) mx = 1.0f;
+                if (mx == 0.0f || ((kflags & HK_F_RESCALE_EPS) && mx > 0.0f && mx <= 1e-8f)) mx = 1.0f;
                 const bool resc = (kflags & HK_F_OBS_RESCALE) && (mx > 0.0f);
                 _Pragma("unroll UNR")
                 for (int r = 0; r < R; ++r) {

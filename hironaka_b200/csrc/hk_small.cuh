@@ -213,9 +213,10 @@ __device__ __forceinline__ uint32_t op_newton_rolled(T (&y)[K * D], uint32_t clm
     return clm & ~kill;
 }
 
-// rescale (float state): live entries / game max, max == 0 -> 1 (rescale_torch _torch_ops.py:136-146)
+// rescale (float state): live entries / game max, max == 0 -> 1 (rescale_torch _torch_ops.py:136-146);
+// `eps`: a maximum <= 1e-8 leaves the game unchanged (calculate_rescale _jax_ops.py:93-98; x / 1 == x)
 template <int N, int D>
-__device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm) {
+__device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm, bool eps) {
     float mx = -1.0f, mnpos = 3.0e38f;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -227,7 +228,7 @@ __device__ __forceinline__ void op_rescale(float (&x)[N * D], uint32_t lm) {
             mnpos = (lv && v > 0.0f) ? fminf(mnpos, v) : mnpos;
         }
     }
-    if (mx == 0.0f) mx = 1.0f;
+    if (mx == 0.0f || (eps && mx > 0.0f && mx <= 1e-8f)) mx = 1.0f;
     // Dead rows are parked at +BIG and zeros are common after reposition; neither goes through
     // the divider (0 / mx = 0 exactly, dead rows are rewritten with the padding value).
     // The choice of the division routine is warp-uniform; the vote is taken by ALL lanes, outside
@@ -356,7 +357,7 @@ __device__ __forceinline__ uint32_t game_step(T (&x)[N * D], uint32_t lm, uint32
         }
     }
     if constexpr (Elem<T>::is_float) {
-        if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm);
+        if (ops & HK_OP_RESCALE) op_rescale<N, D>(x, lm, flags & HK_F_RESCALE_EPS);
     }
     return lm;
 }
@@ -716,7 +717,7 @@ __device__ __noinline__ void features_rolled(const uint32_t* row, uint32_t lm, i
             }
         }
     }
-    if (mx == 0.0f) mx = 1.0f;
+    if (mx == 0.0f || ((flags & HK_F_RESCALE_EPS) && mx > 0.0f && mx <= 1e-8f)) mx = 1.0f;
     // both votes are taken by ALL lanes, outside any per-game condition
     const bool act = (flags & HK_F_OBS_RESCALE) && (mx > 0.0f);
     const GameDivider g = make_divider(act ? mx : 1.0f, mnpos);

@@ -86,7 +86,7 @@ def get_take_actions(role: str, spec: Tuple[int, int], rescale_points: bool = Fa
         points = _state_of(obs_preprocess(observations))
         coords = coords_preprocess(observations, actions)
         mask = _ops.coords_to_mask(coords, d, points.device)
-        r = _ops.step(points, mask, axis, ops=op_bits, flags=C.JAX_SEMANTICS, inplace=False)
+        r = _ops.step(points, mask, axis, ops=op_bits, flags=C.JAX_SEMANTICS | C.HK_F_RESCALE_EPS, inplace=False)
         return r.state.reshape(-1, n * d)
 
     return take_actions
@@ -111,7 +111,7 @@ def get_feature_fn(role: str, spec: Tuple, scale_observation: bool = True) -> Ca
     the agent keeps its d coordinates appended unchanged (util.py:172-214)."""
     assert len(spec) == 2
     n, d = spec
-    flags = C.HK_F_OBS_SORT_LEX | (C.HK_F_OBS_RESCALE if scale_observation else 0)
+    flags = C.HK_F_OBS_SORT_LEX | C.HK_F_RESCALE_EPS | (C.HK_F_OBS_RESCALE if scale_observation else 0)
     if role == "host":
         def feature_fn(observations: torch.Tensor) -> torch.Tensor:
             pts = _state_of(observations.reshape(-1, n, d))
@@ -133,7 +133,7 @@ def generate_pts(generator: Optional[torch.Generator], shape: Tuple[int, int, in
     The random draw is torch's (the reference uses jax.random); everything after it is one launch."""
     pts = torch.randint(0, max_value, shape, generator=generator, device=device).to(dtype)
     op_bits = C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | (C.HK_OP_RESCALE if rescale else 0)
-    _ops.step(pts, ops=op_bits, flags=0, inplace=True)
+    _ops.step(pts, ops=op_bits, flags=C.HK_F_RESCALE_EPS, inplace=True)
     return pts
 
 
@@ -153,7 +153,7 @@ def get_env_step(role: str, spec: Tuple[int, int], rescale_points: bool = False,
     op_bits = C.HK_OP_SHIFT | C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | \
         (C.HK_OP_RESCALE if rescale_points else 0)
     flags = (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
-        C.HK_F_OBS_SORT_LEX | (C.HK_F_OBS_RESCALE if scale_observation else 0)
+        C.HK_F_OBS_SORT_LEX | C.HK_F_RESCALE_EPS | (C.HK_F_OBS_RESCALE if scale_observation else 0)
 
     def env_step(points: torch.Tensor, host_action: torch.Tensor, axis: torch.Tensor, next_coord=None,
                  inplace: bool = False):
@@ -192,7 +192,7 @@ class GraphedEnvStep:
         self._ops = C.HK_OP_SHIFT | C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0) | \
             (C.HK_OP_RESCALE if rescale_points else 0)
         self._flags = (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
-            C.HK_F_OBS_SORT_LEX | (C.HK_F_OBS_RESCALE if scale_observation else 0)
+            C.HK_F_OBS_SORT_LEX | C.HK_F_RESCALE_EPS | (C.HK_F_OBS_RESCALE if scale_observation else 0)
         self._dt = C.HK_DTYPE_I32 if dtype == torch.int32 else C.HK_DTYPE_F32
         from ._lib import check, lib
         self._lib, self._check = lib(), check
@@ -288,6 +288,49 @@ def action_wrapper(policy_value_fn: Callable, dimension: Optional[int] = None) -
 
     wrapped_action_fn.__name__ = getattr(policy_value_fn, "__name__", type(policy_value_fn).__name__)
     return wrapped_action_fn
+
+
+def get_dynamic_policy_fn(spec: Tuple[int, int], host_fn: Callable, agent_fn: Callable) -> Callable:
+    """One policy function for a unified MC tree (get_dynamic_policy_fn, util.py:218-258): the input is
+    always [B, (N+1)*d]; a host state has its last d entries padded with 0, an agent state carries the
+    host's coordinate set there.  Like the reference (`lax.cond` on ONE predicate for the whole batch,
+    :231-233) the batch is a host batch iff SOME row has an all-zero coordinate block; the agent's
+    logits are padded with -inf to the host's 2^d - d - 1 actions (:235-238)."""
+    n, d = spec
+    extra_action_dim = 2 ** d - 2 * d - 1
+
+    def dynamic_policy_fn(state: torch.Tensor, host_and_agent_args, *args, **kwargs):
+        host_args, agent_args = host_and_agent_args
+        coord = state[:, n * d: n * d + d]
+        use_host = bool(torch.isclose(coord, torch.zeros((), dtype=coord.dtype, device=coord.device)).all(dim=-1).any())
+        if use_host:
+            return host_fn(state, *host_args, *args, **kwargs)
+        policy, value = agent_fn(state, *agent_args, *args, **kwargs)
+        pad = torch.full((policy.shape[0], extra_action_dim), float("-inf"), dtype=policy.dtype, device=policy.device)
+        return torch.cat([policy, pad], dim=1), value
+
+    return dynamic_policy_fn
+
+
+def select_sample_after_sim(role: str, rollout, dimension: int, mix_random_terminal_states: bool = True,
+                            generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Mask of the rollout states kept for training (select_sample_after_sim, util.py:351-382): every
+    state of an unfinished game (more than d, resp. 2d for the agent, non-negative entries), plus —
+    with `mix_random_terminal_states` — the states whose value in a uniform random permutation of
+    0..size-1 is below the number of unfinished states (:375-377), i.e. about as many random extra states
+    as there are unfinished ones.
+    RNG contract: the permutation comes from torch (``torch.randperm`` with `generator`), not from
+    jax.random's threefry stream, so the random part has the reference's distribution but not its bits;
+    the deterministic part (`mix_random_terminal_states=False`) is identical."""
+    obs = rollout[0]
+    size = obs.shape[0]
+    offset = dimension if role == "agent" else 0
+    undone = (obs >= 0).sum(dim=-1) > (dimension + offset)
+    if not mix_random_terminal_states:
+        return undone
+    random_idx = torch.randperm(size, generator=generator, device=obs.device if generator is None or
+                                generator.device.type != "cpu" else "cpu").to(obs.device)
+    return undone | (random_idx < undone.sum())
 
 
 def rollout_sanity_tests(rollout, spec: Tuple[int, int]) -> bool:

@@ -87,14 +87,17 @@ class FusedGame:
                                      exploration_rate=exploration_rate if sample_for == "agent" else 0.0)
         next_done = points.ended_batch_in_tensor
         next_observations = points.get_features()
-        sign = 1.0 if sample_for == "host" else -1.0
-        reward = next_done.to(torch.float32) * sign  # _default_reward (fused_game.py:175-182)
+        # the reward function sees the UNFILTERED per-game tensors (a custom `reward_func` must be row-wise,
+        # as the default is: fused_game.py:175-182); rows of games that were over are dropped by the writer
         if sample_for == "host":
+            reward = self._rewards(sample_for, observations, next_observations, next_done)
             buffer.add_masked(done, observations, chosen_actions, reward, next_done, next_observations)
         else:
             next_host_move, _ = self.host_move(points, exploration_rate=exploration_rate)
-            buffer.add_masked(done, {"points": observations, "coords": host_move}, agent_move, reward, next_done,
-                              {"points": next_observations, "coords": next_host_move})
+            obs_d = {"points": observations, "coords": host_move}
+            next_d = {"points": next_observations, "coords": next_host_move}
+            reward = self._rewards(sample_for, obs_d, next_d, next_done)
+            buffer.add_masked(done, obs_d, agent_move, reward, next_done, next_d)
 
     def graphed_step_into(self, buffer, points: TensorPoints, sample_for: str, masked=True, scale_observation=True,
                           exploration_rate=0.2, warmup: int = 2) -> "torch.cuda.CUDAGraph":

@@ -1,126 +1,84 @@
-"""Abstract batched point-set interface, same contract as ``hironaka.core.PointsBase``
-(hironaka/core/points_base.py:7-279): points are [batch, max_num_points, dimension]; removed
-slots are padded with a negative number; ``shift / reposition / get_newton_polytope / rescale``
-mutate in place and return ``self`` (or return a copy when ``inplace=False``)."""
+"""The part of the reference's ``PointsBase`` contract (hironaka/core/points_base.py:7-279) that the
+``point_cls=`` seam needs, written for one concrete storage: a ``[batch, max_num_points, dimension]``
+CUDA tensor whose removed slots hold a non-positive padding value.
+
+What callers of the reference rely on and this keeps: ``config`` (the constructor keywords that
+``copy()`` replays, listed by the subclass in ``subcls_config_keys`` plus ``max_num_points``),
+``running_attributes`` (carried over by ``copy()``), the four game operations mutating in place and
+returning ``self`` — or a fresh object when ``inplace=False`` (:90-140) — and ``ended`` /
+``ended_batch`` / ``__getitem__``.  The list-of-lists storage variants of the reference are not
+rebuilt; a subclass supplies ``_apply(op, ...)`` for its storage.
+"""
 from __future__ import annotations
 
-import abc
+import copy as _copy
 import logging
-from copy import deepcopy
-from typing import Any, List, Optional, Tuple
+from typing import Any, List
 
 
-class PointsBase(abc.ABC):
-    base_config_keys = ["max_num_points"]
-    subcls_config_keys: List[str]
-    running_attributes: List[str]
+class PointsBase:
+    subcls_config_keys: List[str] = []
+    running_attributes: List[str] = []
+    _GAME_OPS = ("shift", "reposition", "get_newton_polytope", "rescale")
 
-    def __init__(self, points: Any, **kwargs):
-        self.logger = logging.getLogger(__class__.__name__)
-        for key in ("subcls_config_keys", "running_attributes"):
-            if not hasattr(self, key):
-                raise NotImplementedError(f"{key} must be initialized when subclassing.")
+    def __init__(self, points: Any, max_num_points: int | None = None, **_ignored):
+        self.logger = logging.getLogger(type(self).__name__)
+        if points.dim() == 2:  # a single game: the reference adds the batch axis with a warning
+            self.logger.warning("Points are 3-dimensional: batch, max_num_points, coordinates. "
+                                "A batch dimension is automatically added.")
+            points = points.unsqueeze(0)
+        if points.dim() != 3:
+            raise ValueError("Input dimension must be 2 or 3.")
         self.points = points
-        shape = self._check_points_shape()
-        self.batch_size, _, self.dimension = shape
-        self.max_num_points = self._get_max_num_points()
-        if "max_num_points" in kwargs:
-            if kwargs["max_num_points"] < self.max_num_points:
+        self.batch_size, self.max_num_points, self.dimension = points.shape
+        if max_num_points is not None:
+            if max_num_points < self.max_num_points:
                 self.logger.warning("Specified max_num_points is smaller than the one in input. Ignored.")
             else:
-                self.max_num_points = kwargs["max_num_points"]
-        self.config = {}
-        for key in self.subcls_config_keys + self.base_config_keys:
-            if not hasattr(self, key):
-                raise Exception("Must initialize keys in 'subcls_config_keys' before calling super().__init__.")
-            self.config[key] = getattr(self, key)
+                self.max_num_points = max_num_points
+        missing = [k for k in self.subcls_config_keys if not hasattr(self, k)]
+        if missing:
+            raise Exception(f"Must initialize keys in 'subcls_config_keys' before calling super().__init__: {missing}")
+        self.config = {k: getattr(self, k) for k in (*self.subcls_config_keys, "max_num_points")}
 
-    # ---- copying -----------------------------------------------------------------------
     def copy(self, points=None) -> "PointsBase":
-        src = self._points_copy(self.points) if points is None else points
-        new = self.__class__(src, **self.config)
-        for key in self.running_attributes:
-            if not hasattr(self, key):
-                raise Exception(f"Attribute {key} is not initialized.")
-            setattr(new, key, deepcopy(getattr(self, key)))
-        return new
+        """A new object on a clone of the points (or on `points`), same config, running attributes deep-copied."""
+        twin = type(self)(self.points.clone().detach() if points is None else points, **self.config)
+        for name in self.running_attributes:
+            if not hasattr(self, name):
+                raise Exception(f"Attribute {name} is not initialized.")
+            setattr(twin, name, _copy.deepcopy(getattr(self, name)))
+        return twin
 
-    def _wrap(self, result, inplace: bool) -> "PointsBase":
+    def _run(self, op: str, *args, inplace: bool = True, **kwargs) -> "PointsBase":
+        result = self._apply(op, *args, inplace=inplace, **kwargs)
         return self if inplace else self.copy(points=result)
 
-    # ---- the four game operations ---------------------------------------------------------
-    def shift(self, coords, axis, inplace=True, **kwargs) -> "PointsBase":
-        return self._wrap(self._shift(self.points, coords, axis, inplace=inplace, **kwargs), inplace)
+    def shift(self, coords, axis, inplace=True, **kwargs):
+        return self._run("shift", coords, axis, inplace=inplace, **kwargs)
 
-    def reposition(self, inplace=True, **kwargs) -> "PointsBase":
-        return self._wrap(self._reposition(self.points, inplace=inplace, **kwargs), inplace)
+    def reposition(self, inplace=True, **kwargs):
+        return self._run("reposition", inplace=inplace, **kwargs)
 
-    def get_newton_polytope(self, inplace=True, **kwargs) -> "PointsBase":
-        return self._wrap(self._get_newton_polytope(self.points, inplace=inplace, **kwargs), inplace)
+    def get_newton_polytope(self, inplace=True, **kwargs):
+        return self._run("get_newton_polytope", inplace=inplace, **kwargs)
 
-    def rescale(self, inplace=True, **kwargs) -> "PointsBase":
-        return self._wrap(self._rescale(self.points, inplace=inplace, **kwargs), inplace)
+    def rescale(self, inplace=True, **kwargs):
+        return self._run("rescale", inplace=inplace, **kwargs)
 
-    # ---- status ----------------------------------------------------------------------------
+    def _apply(self, op: str, *args, inplace: bool, **kwargs):
+        raise NotImplementedError("a storage-specific subclass runs the game operations")
+
+    @property
+    def ended_batch(self):
+        raise NotImplementedError
+
     @property
     def ended(self) -> bool:
-        return all(self._get_batch_ended(self.points))
-
-    @property
-    def ended_batch(self) -> Any:
-        return self._get_batch_ended(self.points)
+        return bool(self.ended_batch.all())
 
     def get_features(self):
         return self.points
 
     def __getitem__(self, item: int):
         return self.points[item]
-
-    # ---- hooks -----------------------------------------------------------------------------
-    @staticmethod
-    def _points_copy(points):
-        return deepcopy(points)
-
-    @abc.abstractmethod
-    def _get_shape(self, points: Any):
-        ...
-
-    @abc.abstractmethod
-    def _get_newton_polytope(self, points: Any, inplace: Optional[bool] = True, **kwargs):
-        ...
-
-    @abc.abstractmethod
-    def _shift(self, points: Any, coords, axis, inplace: Optional[bool] = True, **kwargs):
-        ...
-
-    @abc.abstractmethod
-    def _reposition(self, points: Any, inplace: Optional[bool] = True, **kwargs):
-        ...
-
-    @abc.abstractmethod
-    def _rescale(self, points: Any, inplace: Optional[bool] = True, **kwargs):
-        ...
-
-    @abc.abstractmethod
-    def _get_batch_ended(self, points: Any):
-        ...
-
-    def _add_batch_axis(self, points: Any):
-        raise NotImplementedError
-
-    def _get_max_num_points(self) -> int:
-        return max((len(self[b]) for b in range(self.batch_size)), default=0)
-
-    def _check_points_shape(self) -> Tuple[int, int, int]:
-        shape = self._get_shape(self.points)
-        if len(shape) == 2:
-            try:
-                self.points = self._add_batch_axis(self.points)
-                self.logger.warning("Points are 3-dimensional: batch, max_num_points, coordinates. "
-                                    "A batch dimension is automatically added.")
-                shape = (1, *shape)
-            except NotImplementedError:
-                raise ValueError("Points must be 3-dimensional: batch, max_num_points, coordinates.")
-        if len(shape) != 3:
-            raise ValueError("Input dimension must be 2 or 3.")
-        return tuple(shape)

@@ -72,6 +72,10 @@ class ReplayBuffer:
         obs / next_obs: [B, ...] float32 tensor, or dict {"points": [B, N, d], "coords": [B, d]};
         action [B] or [B,1] int32, reward [B] or [B,1] float32, done [B] or [B,1] bool."""
         B = skip.shape[0]
+        # B is a host-known upper bound of the rows kept: the reference asserts buffer_size > length
+        # (replay_buffer.py:75); more kept rows than slots would make several rows race for one slot
+        if B >= self.buffer_size:
+            raise ValueError(f"{B} samples are more than the buffer size ({self.buffer_size}).")
         skip_u8 = skip.contiguous().view(torch.uint8) if skip.dtype == torch.bool else skip.to(torch.uint8).contiguous()
         act = action.reshape(B).to(torch.int32).contiguous()
         rew = reward.reshape(B).to(torch.float32).contiguous()
@@ -112,8 +116,13 @@ class ReplayBuffer:
         self.add_masked(keep_all, obs, action, reward, done, next_obs)
 
     # ---- reads ----------------------------------------------------------------------------------
-    def sample(self, batch_size: int, device: torch.device = None, clone: bool = True) -> Tuple:
-        """Uniform sample over the filled part; the bound is read on the device (no sync)."""
+    def sample(self, batch_size: int, device: torch.device = None, clone: bool = True, check_empty: bool = True) -> Tuple:
+        """Uniform sample over the filled part.  Like the reference (replay_buffer.py:139) an empty buffer is
+        an error; that check reads the write position back (one device->host sync).  Pass
+        `check_empty=False` inside a CUDA graph or a sync-free loop: the bound is then used on the device
+        only, and an empty buffer yields row 0 (zeros)."""
+        if check_empty and not self.full and self.pos == 0:
+            raise AssertionError("cannot sample from an empty replay buffer")
         bound = torch.where(self._full > 0, torch.full_like(self._pos, self.buffer_size), self._pos)
         u = torch.rand(batch_size, device=self.device, dtype=torch.float64)
         idx = torch.clamp((u * bound.to(torch.float64)).to(torch.int64), max=self.buffer_size - 1)

@@ -44,8 +44,13 @@ class HostSession:
              done: Optional[np.ndarray] = None, reward: Optional[np.ndarray] = None, want_done_count: bool = True):
         """H2D(actions) -> one fused step -> D2H(done, reward, done_count); blocking.
         `done` (uint8 [B]) / `reward` (float32 [B]) are caller-provided output buffers or None."""
-        ha = None if host_action is None else np.ascontiguousarray(host_action, dtype=np.int32)
-        ax = None if axis is None else np.ascontiguousarray(axis, dtype=np.int32)
+        packed = bool(flags & C.HK_F_ACT_PACKED)  # the element size of the action arrays follows the flags, as in rollout()
+        want = np.uint8 if flags & (C.HK_F_ACT_U8 | C.HK_F_ACT_PACKED) else np.int32
+        ha = None if host_action is None else np.ascontiguousarray(host_action, dtype=want)
+        ax = None if (axis is None or packed) else np.ascontiguousarray(axis, dtype=want)
+        for a in (ha, ax):
+            if a is not None and a.shape != (self.B,):
+                raise ValueError(f"actions must have shape ({self.B},)")
         cnt = ctypes.c_int32(0)
         rc = lib().hk_session_step(self._h, None if ha is None else ha.ctypes.data,
                                    None if ax is None else ax.ctypes.data,

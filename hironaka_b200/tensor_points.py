@@ -62,7 +62,6 @@ class TensorPoints(PointsBase):
         if points.dim() == 3 and not points.is_contiguous():
             points = points.contiguous()
 
-        self.batch_size, self.max_num_points, self.dimension = points.shape[-3:] if points.dim() == 3 else (1, *points.shape)
         self.padding_value = padding_value
         self.distinguished_points = distinguished_points
         super().__init__(points, **kwargs)
@@ -104,35 +103,20 @@ class TensorPoints(PointsBase):
     def ended_batch_in_tensor(self) -> torch.Tensor:
         return _ops.dones(self.points)[0]
 
-    # ---- PointsBase hooks ---------------------------------------------------------------
-    def _shift(self, points, coords, axis, inplace=True, ignore_ended_games=True, **kwargs):
-        return _src.shift_torch(points, coords, axis, inplace=inplace, padding_value=self.padding_value,
-                                ignore_ended_games=ignore_ended_games)
+    # ---- the four game operations: one launch each through hironaka_b200.src ----------------
+    def _apply(self, op: str, *args, inplace: bool = True, ignore_ended_games: bool = True, **kwargs):
+        pad = self.padding_value
+        if op == "shift":
+            coords, axis = args
+            return _src.shift_torch(self.points, coords, axis, inplace=inplace, padding_value=pad,
+                                    ignore_ended_games=ignore_ended_games)
+        fn = {"get_newton_polytope": _src.get_newton_polytope_torch, "reposition": _src.reposition_torch,
+              "rescale": _src.rescale_torch}[op]
+        return fn(self.points, inplace=inplace, padding_value=pad)
 
-    def _get_newton_polytope(self, points, inplace=True, **kwargs):
-        return _src.get_newton_polytope_torch(points, inplace=inplace, padding_value=self.padding_value)
-
-    def _reposition(self, points, inplace=True, **kwargs):
-        return _src.reposition_torch(points, inplace=inplace, padding_value=self.padding_value)
-
-    def _rescale(self, points, inplace=True, **kwargs):
-        return _src.rescale_torch(points, inplace=inplace, padding_value=self.padding_value)
-
-    def _get_shape(self, points: torch.Tensor) -> torch.Size:
-        return points.shape
-
-    def _get_max_num_points(self) -> int:
-        return self.points.shape[1]
-
-    @staticmethod
-    def _points_copy(points: torch.Tensor) -> torch.Tensor:
-        return points.clone().detach()
-
-    def _add_batch_axis(self, points: torch.Tensor) -> torch.Tensor:
-        return points.unsqueeze(0)
-
-    def _get_batch_ended(self, points: torch.Tensor) -> torch.Tensor:
-        return _ops.dones(points)[0]
+    @property
+    def ended_batch(self) -> torch.Tensor:
+        return _ops.dones(self.points)[0]
 
     @property
     def ended(self) -> bool:

@@ -90,6 +90,10 @@ extern "C" {
                                       axis (< 8) in the high 3 bits; axis[] is ignored.  Halves the bytes of an action stream
                                       again (1 instead of 2 per game-step).  Needs d <= 5; not with the fixed players. */
 
+#define HK_F_RESCALE_EPS (1u << 15) /* rescale (the op and the rescaled observation) leaves a game whose maximum is <= 1e-8
+                                       unchanged: calculate_rescale of the JAX flavour (hironaka/src/_jax_ops.py:93-98).
+                                       Unset = rescale_torch: only a maximum of exactly 0 is replaced by 1 (_torch_ops.py:139) */
+
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
 const char* hk_error_string(int code);

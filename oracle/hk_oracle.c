@@ -132,10 +132,11 @@ static uint32_t oracle_zeillinger(const float* pts, int N, int d) {
 
 #define NO_RESCALE(x, N, d, pad) (void)0
 #define F32_RESCALE(x, N, d, pad)                                                                       \
-    do { /* rescale_torch hironaka/src/_torch_ops.py:136-146 */                                         \
+    do { /* rescale_torch hironaka/src/_torch_ops.py:136-146; with HK_F_RESCALE_EPS the rule of     \
+            calculate_rescale hironaka/src/_jax_ops.py:93-98: a maximum <= 1e-8 leaves the game alone */ \
         float mx_ = x[0];                                                                               \
         for (int t = 1; t < N * d; ++t) mx_ = x[t] > mx_ ? x[t] : mx_;                                  \
-        if (mx_ == 0.0f) mx_ = 1.0f;                                                                    \
+        if (mx_ == 0.0f || ((flags & HK_F_RESCALE_EPS) && mx_ <= 1e-8f)) mx_ = 1.0f;                    \
         for (int i = 0; i < N; ++i) {                                                                   \
             int lv_ = x[i * d] >= 0;                                                                    \
             for (int k = 0; k < d; ++k) x[i * d + k] = lv_ ? x[i * d + k] / mx_ : pad;                  \
@@ -372,7 +373,7 @@ static void features_one(const float* f, float* o, int N, int d, uint32_t flags)
             const T* x = c->state + b * N * d;                                                         \
             float mx = (float)x[0];                                                                    \
             for (int t = 1; t < N * d; ++t) mx = (float)x[t] > mx ? (float)x[t] : mx;                  \
-            if (mx == 0.0f) mx = 1.0f;                                                                 \
+            if (mx == 0.0f || ((flags & HK_F_RESCALE_EPS) && mx <= 1e-8f)) mx = 1.0f;                  \
             for (int i = 0; i < N; ++i)                                                                \
                 for (int k = 0; k < d; ++k) {                                                          \
                     float v = (float)x[i * d + k];                                                     \

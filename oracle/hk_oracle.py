@@ -10,12 +10,13 @@ reference root) in NumPy, keeping the reference's order of operations so that fl
 results are bit-identical, and keeping the two flavours of the reference apart:
 
   * ``*_torch``  follow hironaka/src/_torch_ops.py + hironaka/src/_fn.py (TensorPoints path)
-  * ``*_jax``    follow hironaka/src/_jax_ops.py + hironaka/jax/util.py   (JAX path; JAX is not
-                 installable here, so this restatement is pinned against the golden vectors of
-                 test/testJAX.py, see tests/test_oracle_golden.py)
+  * ``*_jax``    follow hironaka/src/_jax_ops.py + hironaka/jax/util.py   (JAX path)
 
-Parity pinning: the torch flavour is additionally checked against outputs of the real
-reference imported in the build container (tests/golden/*.npz, made by oracle/gen_golden.py).
+Parity pinning: both flavours reproduce the reference's known-answer vectors (tests/kat.py) and
+outputs of the reference's OWN code run in the build container: the torch flavour imported as is
+(tests/golden/ref_*.npz, oracle/gen_golden.py), the JAX flavour by executing the reference's JAX
+source files unmodified over a NumPy stand-in for jax.numpy / vmap / jit, since jax is not
+installed here (tests/golden/ref_jax_*.npz, oracle/gen_golden_jax.py + oracle/jax_numpy_shim.py).
 
 The [B,N,N,d] temporaries of the reference are kept on purpose (this is the restatement, not
 the fast path); use oracle/hk_oracle.c through ``oracle.cport`` for large batches.
@@ -425,6 +426,7 @@ def zeillinger_fn(pts: np.ndarray) -> np.ndarray:
 OP_SHIFT, OP_REPOSITION, OP_NEWTON, OP_RESCALE, OP_DEDUPE = 1, 2, 4, 8, 16
 F_NOOP_INVALID, F_FREEZE_ENDED, F_ACT_DISCRETE, F_ROLE_AGENT = 1, 2, 4, 8
 F_OBS_RESCALE, F_OBS_SORT_COORD0, F_OBS_SORT_LEX = 16, 32, 64
+F_RESCALE_EPS = 1 << 15
 
 
 def masks_to_binary(mask: np.ndarray, d: int) -> np.ndarray:
@@ -434,7 +436,9 @@ def masks_to_binary(mask: np.ndarray, d: int) -> np.ndarray:
 def step(points: np.ndarray, host_action, axis, ops: int, flags: int, padding_value: float = -1.0,
          obs_coord=None, want_obs: bool = False):
     """One game-step with the C-ABI's op/flag vocabulary, composed from the restated reference
-    functions above: torch flavour when NOOP_INVALID/FREEZE_ENDED are set, JAX flavour otherwise.
+    functions above: torch flavour when NOOP_INVALID/FREEZE_ENDED are set, JAX flavour (the `_jax`
+    restatements throughout) otherwise; F_RESCALE_EPS selects calculate_rescale's `max <= 1e-8 ->
+    unchanged` rule (_jax_ops.py:93-98) for the rescale op and the rescaled observation.
     Works on a float32 copy (the reference's storage) and returns
     (new_points[f32], done, reward, num_points, obs or None)."""
     p = np.asarray(points).astype(np.float32)
@@ -455,21 +459,32 @@ def step(points: np.ndarray, host_action, axis, ops: int, flags: int, padding_va
                 p = np.where(prev_done[:, None, None], np.where(p >= 0, p, np.float32(padding_value)), q)
         else:
             p = shift_jax(p, coord, ax, padding_value)
-    if ops & OP_REPOSITION:
-        p = reposition_torch(p, padding_value)
-    if ops & OP_DEDUPE:
-        p = remove_repeated(p, padding_value)
-    if ops & OP_NEWTON:
-        p = get_newton_polytope_torch(p, padding_value)
+    jax_flavour = not (flags & (F_NOOP_INVALID | F_FREEZE_ENDED))
+    rescale = (lambda q: rescale_jax(q, padding_value)) if flags & F_RESCALE_EPS else \
+        (lambda q: rescale_torch(q, padding_value))
+    if jax_flavour and padding_value == -1.0:
+        if ops & OP_REPOSITION:
+            p = reposition_jax(p)
+        if ops & OP_DEDUPE:
+            p = remove_repeated_jax(p)
+        if ops & OP_NEWTON:
+            p = get_newton_polytope_jax(p)
+    else:
+        if ops & OP_REPOSITION:
+            p = reposition_torch(p, padding_value)
+        if ops & OP_DEDUPE:
+            p = remove_repeated(p, padding_value)
+        if ops & OP_NEWTON:
+            p = get_newton_polytope_torch(p, padding_value)
     if ops & OP_RESCALE:
-        p = rescale_torch(p, padding_value)
+        p = rescale(p)
     done = get_dones(p)
     rew = reward_fn("agent" if flags & F_ROLE_AGENT else "host", done, prev_done)
     obs = None
     if want_obs:
         f = p
         if flags & F_OBS_RESCALE:
-            f = rescale_torch(f, padding_value)
+            f = rescale(f)
         if flags & F_OBS_SORT_COORD0:
             f = get_features_torch(f)
         elif flags & F_OBS_SORT_LEX:

@@ -524,12 +524,19 @@ def test_config4_ade_starts_dqn_replay(hb):
 @pytest.mark.parametrize("cfg", [
     dict(name="C2", B=1 << 20, N=20, d=3, T=20, mv=20, ops=O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
     dict(name="C1", B=1024, N=10, d=3, T=10, mv=21, ops=O.OP_SHIFT | O.OP_NEWTON, flags=TORCH_FLAGS | O.F_ACT_DISCRETE),
-    dict(name="C5", B=1 << 16, N=64, d=5, T=6, mv=20, ops=O.OP_SHIFT | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
+    # exactly the configuration bench.py times for C5: the HOT instantiation of the warp-per-game kernel
+    # (shift + reposition + newton, discrete ids), every resident warp playing ~55 games in a row
+    dict(name="C5", B=1 << 18, N=64, d=5, T=20, mv=20, ops=O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
+    dict(name="C5-norepos", B=1 << 16, N=64, d=5, T=6, mv=20, ops=O.OP_SHIFT | O.OP_NEWTON, flags=O.F_ACT_DISCRETE),
+    # the warp-per-game family on the (20,3) shape at a size where its game loop iterates many times
+    dict(name="C2-generic", B=1 << 16, N=20, d=3, T=20, mv=20, ops=O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON,
+         flags=O.F_ACT_DISCRETE, generic=True),
 ], ids=lambda c: c["name"])
 def test_baseline_sizes_bit_exact(hb, cfg):
     """Full-size parity against the C port on identical seeded inputs."""
     from hironaka_b200 import ops
     B, N, d, T = cfg["B"], cfg["N"], cfg["d"], cfg["T"]
+    ops.force_generic(bool(cfg.get("generic")))
     rng = np.random.default_rng(2024)
     x = rng.integers(0, cfg["mv"], size=(B, N, d)).astype(np.int32)
     ncls = 2 ** d - d - 1
@@ -549,7 +556,7 @@ def test_baseline_sizes_bit_exact(hb, cfg):
         odones.append(od.astype(bool))
         assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)), t
         assert np.array_equal(r.reward.cpu().numpy(), orw), t
-        if t in (0, 1, T - 1):
+        if t in (0, 1, T - 1) or t % 5 == 4:
             assert np.array_equal(g.cpu().numpy(), o), t
     # one-launch rollout ends in the same state with the same per-step finished counts
     _, _, _, dcount, _ = ops.rollout(g_roll, dev(ha), dev(ax), ops=cfg["ops"], flags=cfg["flags"], inplace=True)
@@ -559,3 +566,140 @@ def test_baseline_sizes_bit_exact(hb, cfg):
     g2 = g.clone()
     ops.step(g2, ops=O.OP_NEWTON, inplace=True)
     assert torch.equal(g2, g)
+    ops.force_generic(False)
+
+
+# ---------------------------------------------------------------- the reference's own JAX sources
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_jax_golden_rollouts(hb, family, golden_dir, dtype):
+    """Rollouts produced by EXECUTING the reference's JAX sources (hironaka/src/_jax_ops.py,
+    hironaka/jax/util.py; oracle/gen_golden_jax.py): take_actions -> get_dones -> reward_fn -> feature_fn,
+    host and agent roles, with / without reposition, rescaled float states, step by step and as one launch."""
+    from hironaka_b200 import ops
+    files = sorted(glob.glob(os.path.join(golden_dir, "ref_jax_rollout_*.npz")))
+    assert len(files) >= 8
+    for path in files:
+        g = np.load(path)
+        seed, B, N, d, T, mv, agent, repos, resc = g["meta"].tolist()
+        if resc and dtype == np.int32:
+            continue
+        ops_bits = O.OP_SHIFT | O.OP_NEWTON | (O.OP_REPOSITION if repos else 0) | (O.OP_RESCALE if resc else 0)
+        flags = O.F_ACT_DISCRETE | O.F_RESCALE_EPS | (O.F_ROLE_AGENT if agent else 0)
+        root = O.OP_NEWTON | (O.OP_REPOSITION if repos else 0) | (O.OP_RESCALE if resc else 0)
+        x, done, _, _, _ = run_step(hb, g["raw"].astype(dtype), None, None, root, flags)
+        assert np.array_equal(x.astype(np.float32), g["states"][0]), path
+        assert np.array_equal(done, g["dones"][0]), path
+        x0 = x
+        for t in range(T):
+            hid, ax = g["host_ids"][t], g["axes"][t]
+            x, done, rew, npts, obs = run_step(hb, x, hid, ax, ops_bits, flags | O.F_OBS_SORT_LEX | O.F_OBS_RESCALE,
+                                               want_obs=True)
+            assert np.array_equal(x.astype(np.float32), g["states"][t + 1]), (path, t)
+            assert np.array_equal(done, g["dones"][t + 1]), (path, t)
+            assert np.array_equal(rew, g["rewards"][t]), (path, t)
+            assert np.array_equal(obs, g["feat_host"][t]), (path, t)
+            raw = run_step(hb, x, None, None, 0, flags | O.F_OBS_SORT_LEX, want_obs=True)[4]
+            assert np.array_equal(raw, g["feat_host_raw"][t]), (path, t)
+            fa = run_step(hb, x, None, None, 0, flags | O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, want_obs=True, obs_coord=hid)[4]
+            assert np.array_equal(fa, g["feat_agent"][t]), (path, t)
+        out, dn, rw, dcount, _ = ops.rollout(dev(x0), dev(g["host_ids"]), dev(g["axes"]), ops=ops_bits, flags=flags,
+                                             inplace=False, want_done=True, want_reward=True)
+        assert np.array_equal(out.cpu().numpy().astype(np.float32), g["states"][T]), path
+        assert np.array_equal(dn.cpu().numpy(), g["dones"][1:]), path
+        assert np.array_equal(rw.cpu().numpy(), g["rewards"]), path
+        assert np.array_equal(dcount.cpu().numpy(), g["dones"][1:].sum(1)), path
+
+
+def test_jax_golden_functional_api(hb, golden_dir):
+    """The same goldens through the drop-in functional API (hironaka_b200.functional = hironaka/jax/util.py)."""
+    from hironaka_b200 import functional as F
+    g = np.load(os.path.join(golden_dir, "ref_jax_rollout_c2_20x3.npz"))
+    seed, B, N, d, T, *_ = g["meta"].tolist()
+    take = F.get_take_actions("host", (N, d), False, True)
+    feat = F.get_feature_fn("host", (N, d), True)
+    afeat = F.get_feature_fn("agent", (N, d), True)
+    rewf = F.get_reward_fn("host")
+    decode = F.get_batch_decode(d)
+    x = dev(g["states"][0])
+    prev = F.get_dones(x)
+    for t in range(T):
+        coords = decode(dev(g["host_ids"][t]))
+        nxt = take(F.flatten(x), coords, dev(g["axes"][t]))
+        assert np.array_equal(nxt.cpu().numpy(), g["states"][t + 1].reshape(B, -1)), t
+        x = nxt.reshape(B, N, d)
+        dn = F.get_dones(x)
+        assert np.array_equal(dn.cpu().numpy(), g["dones"][t + 1]), t
+        assert np.array_equal(rewf(dn, prev).cpu().numpy(), g["rewards"][t]), t
+        assert np.array_equal(feat(nxt).cpu().numpy(), g["feat_host"][t]), t
+        aobs = F.make_agent_obs(x, coords)
+        assert np.array_equal(afeat(aobs).cpu().numpy(), g["feat_agent"][t]), t
+        assert np.array_equal(F.get_done_from_flatten(aobs, "agent", d).cpu().numpy(), g["done_from_flatten"][t][1]), t
+        prev = dn
+    # the agent role reads its coordinates from the observation (util.py:66-75)
+    ga = np.load(os.path.join(golden_dir, "ref_jax_rollout_c2_20x3_agent.npz"))
+    _, B, N, d, T, *_ = ga["meta"].tolist()
+    take_a = F.get_take_actions("agent", (N, d), False, True)
+    x = dev(ga["states"][0])
+    for t in range(T):
+        coords = decode(dev(ga["host_ids"][t]))
+        ax = dev(ga["axes"][t])
+        nxt = take_a(F.make_agent_obs(x, coords), ax, ax)
+        assert np.array_equal(nxt.cpu().numpy(), ga["states"][t + 1].reshape(B, -1)), t
+        x = nxt.reshape(B, N, d)
+    # select_sample_after_sim: the deterministic part is the reference's, the random part keeps its contract
+    gs = np.load(os.path.join(golden_dir, "ref_jax_select_after_sim.npz"))
+    for role, key in (("host", "host_obs"), ("agent", "agent_obs")):
+        ro = (dev(gs[key]), None, None)
+        und = F.select_sample_after_sim(role, ro, 3, mix_random_terminal_states=False)
+        assert np.array_equal(und.cpu().numpy(), gs[f"undone_{role}"])
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        sel = F.select_sample_after_sim(role, ro, 3, mix_random_terminal_states=True, generator=gen)
+        assert bool((sel | ~und).all()) and int(sel.sum()) <= 2 * int(und.sum())
+        assert int(sel.sum()) >= int(und.sum())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_jax_golden_ops(hb, family, golden_dir, dtype):
+    for path in sorted(glob.glob(os.path.join(golden_dir, "ref_jax_ops_*.npz"))):
+        g = np.load(path)
+        x = g["points"].astype(dtype)
+        B, N, d = x.shape
+        cm = (g["coord"].astype(np.int64) * (1 << np.arange(d))).sum(1).astype(np.int32)
+        c = lambda a: a.astype(np.float32)
+        assert np.array_equal(c(run_step(hb, x, cm, g["axes"], O.OP_SHIFT, 0)[0]), g["shift"]), path
+        assert np.array_equal(c(run_step(hb, x, None, None, O.OP_REPOSITION, 0)[0]), g["reposition"]), path
+        assert np.array_equal(c(run_step(hb, x, None, None, O.OP_DEDUPE, 0)[0]), g["remove_repeated"]), path
+        assert np.array_equal(c(run_step(hb, x, None, None, O.OP_NEWTON, 0)[0]), g["newton"]), path
+        if dtype == np.float32:
+            assert np.array_equal(run_step(hb, x, None, None, O.OP_RESCALE, O.F_RESCALE_EPS)[0], g["rescale"]), path
+            # calculate_rescale's eps rule (_jax_ops.py:93-98): maxima <= 1e-8 leave the game alone
+            tiny = g["tiny_points"]
+            assert np.array_equal(run_step(hb, tiny, None, None, O.OP_RESCALE, O.F_RESCALE_EPS)[0], g["tiny_rescale"]), path
+            obs = run_step(hb, tiny, None, None, 0, O.F_OBS_RESCALE | O.F_RESCALE_EPS, want_obs=True)[4]
+            assert np.array_equal(obs.reshape(B, N, d), g["tiny_rescale"]), path
+            assert np.array_equal(run_step(hb, tiny, None, None, O.OP_RESCALE, 0)[0],
+                                  cport.step(tiny, None, None, O.OP_RESCALE, 0)[0]), path
+
+
+@pytest.mark.parametrize("N", [5, 10, 20])
+def test_features_pack_borders(hb, family, N):
+    """The observation kernel packs a whole row into one 32-bit key while every live value is an integer
+    below 2^9 (d = 3), into a 64-bit key below 2^19, and compares floats beyond: values that straddle
+    511/512 and 2^19 - 1 / 2^19, alone and mixed inside one warp tile, with ties on every coordinate."""
+    rng = np.random.default_rng(N)
+    B, d = 96, 3
+    for lo, hi in ((509, 514), (0, 513), ((1 << 19) - 3, (1 << 19) + 3), (510, (1 << 19) + 2)):
+        base = rng.integers(lo, hi, size=(B, N, d))
+        pick = rng.random((B, N, d)) < 0.5
+        x = np.where(pick, base, rng.integers(0, 4, size=(B, N, d))).astype(np.int32)
+        x[rng.random((B, N)) < 0.3] = -1
+        x[::7] = np.where(x[::7] >= 0, np.minimum(x[::7], 511), -1)       # games that stay packable next to ones that do not
+        x[3::11, :, 2] = np.where(x[3::11, :, 0] >= 0, 512, -1)           # the border value in the primary sort column
+        for dtype in (np.int32, np.float32):
+            xv = x.astype(dtype)
+            for flags in (O.F_OBS_SORT_LEX, O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, O.F_OBS_SORT_COORD0, 1 << 12,
+                          O.F_OBS_SORT_COORD0 | O.F_OBS_RESCALE):
+                got = run_step(hb, xv, None, None, 0, flags, want_obs=True)[4]
+                assert np.array_equal(got, cport.features(xv, flags)), (lo, hi, dtype, flags)

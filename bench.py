@@ -2,7 +2,7 @@
 """bench.py — game-steps/sec of the batched Hironaka env step on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this engine
-    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm (oracle C port)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm: the unmodified reference (baseline/_ref)
     torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU
 
 Workload (config.workload = "C2"): BASELINE.json configs[1] — dim=3, max_num_points=20
@@ -11,9 +11,10 @@ then per step a uniform random host action id and a uniform random agent axis ov
 (invalid actions occur; JAX semantics apply them), step = shift -> reposition -> newton ->
 done/reward.  All inputs are generated on the CPU from a seed and copied (never device RNG).
 1 Mi games per GPU (weak scaling; the state, 252 MB, exceeds the 126 MB L2, so every step
-streams from HBM).  A "step" is one game-step of all B slots = one hk_step launch; consecutive
-steps walk through independent 20-step rollouts, each on its own pre-generated batch, so the
-live-point dynamics are those of real play and nothing but steps sits in the timed region.
+streams from HBM).  A "step" is one game-step of all B slots = one launch of the in-place step with a
+census (hk_step_census: games at rest are answered from their census byte, games in play are ordered by
+live count); consecutive steps walk through independent 20-step rollouts, each on its own pre-generated
+batch, so the live-point dynamics are those of real play and nothing but steps sits in the timed region.
 
 One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
@@ -36,7 +37,8 @@ METRIC = "game_steps_per_sec"
 UNIT = "game-steps/s"
 N_POINTS, DIM, T_ROLLOUT, MAX_VALUE = 20, 3, 20, 20
 GAMES_PER_GPU = 1 << 20
-CPU_SAMPLE_GAMES = int(os.environ.get("HK_BENCH_CPU_SAMPLE", 1 << 19))  # bounded sample of the C2 workload for the CPU arm (state 126 MB, ~1 s per 40 steps)
+CPU_SAMPLE_GAMES = int(os.environ.get("HK_BENCH_CPU_SAMPLE", 1 << 19))  # bounded sample of the C2 workload for the C port (state 126 MB, ~1 s per 40 steps)
+REF_SAMPLE_GAMES = int(os.environ.get("HK_BENCH_REF_SAMPLE", 1 << 14))  # games per step of the real reference (its [B,N,N,d] temporaries: 79 MB each)
 MAX_RESIDENT_ROLLOUTS = 10  # distinct pre-generated batches; beyond K = 200 they are restored from pristine copies
 BYTES_PER_GAME_STEP = 8 * N_POINTS * DIM + 13  # int32 state r+w, 2 x int32 action, u8 done, f32 reward
 OPS_PER_GAME_STEP = N_POINTS * (N_POINTS - 1) * (DIM + 1) + 3 * N_POINTS * DIM + N_POINTS
@@ -77,7 +79,7 @@ def traffic_per_launch():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get("hk_small_kernel_i32_20x3_bytes_per_launch_1Mi")
+            return json.load(f).get("hk_sched_kernel_i32_20x3_bytes_per_launch_1Mi")
     except Exception:
         return None
 
@@ -179,20 +181,39 @@ def reference_style_rate(games: int = 4096, steps: int = 10, seed: int = 77):
     return games * steps / (time.perf_counter() - t0)
 
 
+def reference_baseline(steps: int, warmup: int):
+    """The unmodified reference (baseline/_ref, hironaka.core.TensorPoints over hironaka/src/_torch_ops.py) on a
+    bounded sample of the C2 workload, all host threads.  Returns the cpu_baseline dict, or None when
+    baseline/_ref did not travel."""
+    from baseline import reference_arm as R
+    if not R.available():
+        return None
+    rate, cores, threads, dt = R.rate(make_inputs, REF_SAMPLE_GAMES, steps, warmup, T_ROLLOUT)
+    return {"value": rate, "unit": UNIT, "cores": cores, "torch_threads": threads, "kind": "reference",
+            "seconds": dt,
+            "sample": f"{REF_SAMPLE_GAMES} games x {steps} steps of the C2 workload through the UNMODIFIED reference "
+                      f"(honglu2875/hironaka 0.0.1 in baseline/_ref): HostActionEncoder.decode_tensor -> TensorPoints.shift "
+                      f"-> reposition -> get_newton_polytope -> ended_batch_in_tensor -> reward, torch on {threads} threads of "
+                      f"{cores} cores, time.perf_counter (the reference's Timer).  The reference's JAX step cannot be timed: "
+                      f"jax is not installed in this image"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = CPU_SAMPLE_GAMES
-    rate, cores, dt = cpu_rate(sample, args.steps, args.warmup)
+    cpu = reference_baseline(args.steps, args.warmup)
+    if cpu is None:  # baseline/_ref did not travel: the oracle's C port stands in (kind "port")
+        rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, args.steps, args.warmup)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+               "sample": f"{CPU_SAMPLE_GAMES} games x {args.steps} steps of the C2 workload, oracle/hk_oracle.c over "
+                         f"{cores} pthreads (baseline/_ref is missing)"}
+    rate, dt = cpu["value"], cpu["seconds"]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} games x {args.steps} steps of the C2 workload, oracle/hk_oracle.c over "
-                                   f"{cores} pthreads (the reference itself is Python/torch and cannot travel; "
-                                   f"JAX-CPU cannot be timed: jax is not installed)"},
+        "vs_baseline": None, "dtype": "float32" if cpu["kind"] == "reference" else "int32", "data": "synthetic",
+        "config": workload_config(args.gpus), "cpu_baseline": cpu,
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,7 +252,7 @@ def run_gpu_arm(args):
         gb = GameBatch(torch.from_numpy(pts[r]).to(dev), semantics="jax", reposition=True, initial_filter=True)
         batches.append(gb)
     wraps = K > n_roll * T_ROLLOUT
-    pristine = [b.points.clone() for b in batches[:n_roll]] if wraps else None
+    pristine = [(b.points.clone(), b.census.clone()) for b in batches[:n_roll]] if wraps else None
     ha_d = torch.from_numpy(ha).to(dev)
     ax_d = torch.from_numpy(ax).to(dev)
     done = torch.empty(B, dtype=torch.uint8, device=dev)
@@ -243,11 +264,11 @@ def run_gpu_arm(args):
 
     def launch_step(r, t):
         st = batches[r].points
-        rc = lib.hk_step(st.data_ptr(), st.data_ptr(), ha_d[r, t].data_ptr(), ax_d[r, t].data_ptr(), done.data_ptr(),
-                         reward.data_ptr(), None, None, None, None, B, N_POINTS, DIM, C.HK_DTYPE_I32, op_step, flags,
-                         -1.0, 1e8, stream)
+        rc = lib.hk_step_census(st.data_ptr(), ha_d[r, t].data_ptr(), ax_d[r, t].data_ptr(), done.data_ptr(),
+                                reward.data_ptr(), None, batches[r].census.data_ptr(), None, None, B, N_POINTS, DIM,
+                                C.HK_DTYPE_I32, op_step, flags, -1.0, 1e8, stream)
         if rc != 0:
-            raise RuntimeError(f"hk_step failed: {rc}")
+            raise RuntimeError(f"hk_step_census failed: {rc}")
 
     def barrier():
         if world > 1:
@@ -264,13 +285,18 @@ def run_gpu_arm(args):
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
+    # Gate: the device spins for a moment while the host enqueues the K launches behind it, so that the timed
+    # region (events on the launching stream, after the gate) holds K back-to-back steps and no host launch gap
+    # (the first launch after a barrier + synchronize used to cost 0.1-0.15 ms more than the others).
+    torch.cuda._sleep(int(min(K, 400) * 60000 + 400000))
     ev[0].record()
     for i in range(K):
         r, t = divmod(i, T_ROLLOUT)
-        if r >= n_roll:  # K > 200: reuse a batch; its restore (one D2D copy) is charged to the timed region
+        if r >= n_roll:  # K > 200: reuse a batch; its restore (two D2D copies) is charged to the timed region
             r %= n_roll
             if t == 0:
-                batches[r].points.copy_(pristine[r])
+                batches[r].points.copy_(pristine[r][0])
+                batches[r].census.copy_(pristine[r][1])
         launch_step(r, t)
         ev[i + 1].record()
     barrier()
@@ -296,13 +322,19 @@ def run_gpu_arm(args):
     value = B * world * K / (total_ms_max * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None if args.no_e2e else measure_e2e(torch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
+    collective = None
+    if world > 1 and not args.no_collective:
+        try:
+            collective = measure_collective(torch, dist, lib, C, dev, world, rank)
+        except Exception as e:
+            collective = {"error": repr(e)}
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         try:
             secondary = measure_secondary(torch, lib, C, dev)
         except Exception as e:  # context numbers must never take the headline down
             secondary = {"error": repr(e)}
-    e2e = None if args.no_e2e else measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -314,12 +346,13 @@ def run_gpu_arm(args):
     achieved = B * BYTES_PER_GAME_STEP / avg_launch_s / 1e9
     traffic = traffic_per_launch()
     roofline = {
-        "bound": "hbm", "kernel": "hk::hk_small_kernel<int,20,3,false>", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "hk::hk_sched_kernel<int,20,3>", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        # `achieved` uses SURVEY 8d's algorithmic bytes (every game read AND written every step).  In-place steps
-        # write back only the games that changed, so the bytes that really move (`traffic`, ncu) are fewer and
-        # `frac` can exceed 1; `physical` is the same launch counted in moved bytes, and
-        # secondary.C2_write_back.store_all is the kernel made to write every game (HK_F_STORE_ALL).
+        # `achieved` uses SURVEY 8d's algorithmic bytes (every game read AND written every step).  The census step
+        # neither reads the games at rest nor writes back unchanged games, so the bytes that really move
+        # (`traffic`, ncu, mean over a rollout) are far fewer and `frac` exceeds 1; `physical` is the same launch
+        # counted in moved bytes, and secondary.C2_write_back.store_all is the tile-ring kernel made to read and
+        # write every game (HK_F_STORE_ALL), the like-for-like number for the algorithmic byte model.
         "physical": None if not traffic else {"bytes_per_launch": traffic, "gbps": traffic / avg_launch_s / 1e9,
                                               "frac": traffic / avg_launch_s / 1e9 / peak},
         "store_all_frac": None if not secondary or "store_all" not in secondary.get("C2_write_back", {}) else
@@ -339,12 +372,13 @@ def run_gpu_arm(args):
     if not args.no_cpu and world == 1:
         try:
             rate, cores, dt = cpu_rate(CPU_SAMPLE_GAMES, 80, 5)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "reference_style_numpy": {"value": reference_style_rate(), "cores": 1,
-                                             "sample": "4096 games x 10 steps, oracle/hk_oracle.py (array-op restatement "
-                                                       "with the reference's [B,N,N,d] temporaries)"},
-                   "sample": f"{CPU_SAMPLE_GAMES} games x 80 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
-                             f"(C port of the reference step) over {cores} pthreads"}
+            port = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{CPU_SAMPLE_GAMES} games x 80 steps of the C2 workload in {dt:.2f} s, oracle/hk_oracle.c "
+                              f"(C port of the reference step) over {cores} pthreads"}
+            cpu = reference_baseline(40, 2)  # ~10-30 s of the real reference
+            if cpu is None:
+                cpu = dict(port)
+            cpu["port"] = port
         except Exception as e:  # the CPU baseline must never take the GPU line down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     line = {
@@ -352,7 +386,7 @@ def run_gpu_arm(args):
         "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
-        "library": os.path.relpath(hb.LIB_PATH, ROOT), "secondary": secondary,
+        "library": os.path.relpath(hb.LIB_PATH, ROOT), "collective": collective, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -662,50 +696,143 @@ def measure_secondary(torch, lib, C, dev):
     return out
 
 
-def measure_e2e(torch, GameBatch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist):
-    """The same K steps through the host-buffer C-ABI (hk_session_rollout via HostSession.rollout):
-    the state of each rollout batch is resident; EVERY step copies that step's actions from
-    pinned host memory (one packed byte per game-step) and copies the step's finished-game count
-    back to the host.  Uploads of step t+1 overlap step t (two streams inside the session)."""
+def measure_e2e(torch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist, repeats: int = 5):
+    """The same K steps through the host-buffer C-ABI (hk_session_rollout_ex via HostSession.rollout): the state
+    of each rollout batch is resident; EVERY step copies that step's actions from pinned host memory (one
+    packed byte per game-step) and brings back the step's per-game done flags (one byte per game, pinned) and
+    the finished-game count.  Three streams inside the session: uploads, steps, read-backs.  The K steps are
+    repeated `repeats` times from the same start and the MEDIAN is reported (a single ~1-2 ms window is noisy)."""
     from hironaka_b200 import HostSession, constants as C
     op_step = C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON
+    root_ops = C.HK_OP_NEWTON | C.HK_OP_REPOSITION
     flags = C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED
     # one byte per game-step: host-action id | axis << 5 (HK_F_ACT_PACKED), prepared like the other synthetic inputs
     ha_pin = torch.from_numpy(HostSession.pack_actions(ha[:n_roll], ax[:n_roll])).pin_memory()
-    sessions = []
+    done_pin = torch.empty((n_roll, T_ROLLOUT, B), dtype=torch.uint8).pin_memory()
+    sessions, starts = [], []
     for r in range(n_roll):
         s = HostSession(pts[r], device=dev.index)
-        s.step(None, None, C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0)  # root filter (generate_pts), untimed
+        s.step(None, None, root_ops, 0)  # root filter (generate_pts), untimed
         sessions.append(s)
-    pristine = [s.get_state() for s in sessions] if K > n_roll * T_ROLLOUT else None
+        starts.append(s.get_state())
     warm = HostSession(pts[0], device=dev.index)
-    warm.rollout(ha_pin[0, :3].numpy(), None, op_step, flags)
+    warm.rollout(ha_pin[0, :3].numpy(), None, op_step, flags, done=done_pin[0, :3].numpy())
     warm.close()
-    barrier()
-    t0 = time.perf_counter()
-    total_done, done_steps, i = 0, 0, 0
-    while done_steps < K:
-        r = i % n_roll
-        if i >= n_roll:
-            sessions[r].set_state(pristine[r])  # reuse of a batch beyond K = 200 (charged to the timed region)
-        T = min(T_ROLLOUT, K - done_steps)
-        counts = sessions[r].rollout(ha_pin[r, :T].numpy(), None, op_step, flags)
-        total_done += int(counts.sum())
-        done_steps += T
-        i += 1
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3  # host-blocking API: wall clock is the device time plus the copies
+
+    def one_pass():
+        barrier()
+        t0 = time.perf_counter()
+        total_done, done_steps, i = 0, 0, 0
+        while done_steps < K:
+            r = i % n_roll
+            if i >= n_roll:  # reuse of a batch beyond K = 200 (charged to the timed region)
+                sessions[r].set_state(starts[r])
+            T = min(T_ROLLOUT, K - done_steps)
+            counts = sessions[r].rollout(ha_pin[r, :T].numpy(), None, op_step, flags, done=done_pin[r, :T].numpy())
+            total_done += int(counts.sum())
+            done_steps += T
+            i += 1
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3  # host-blocking API: wall clock is the device time plus the copies
+        check = int(done_pin[(i - 1) % n_roll, T - 1].sum())  # the flags of the last step did reach the host
+        return ms, total_done, check, int(counts[-1])
+
+    times, total_done = [], 0
+    for rep in range(repeats):
+        if rep:  # back to the same start; the root filter is replayed (idempotent) so that the census is filled again
+            for r in range(n_roll):
+                sessions[r].set_state(starts[r])
+                sessions[r].step(None, None, root_ops, 0)
+        ms, total_done, check, last = one_pass()
+        assert check == last, (check, last)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        times.append(ms)
     for s in sessions:
         s.close()
-    if world > 1:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    return {"value": B * world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B, "d2h_bytes_per_step": 4,
-            "ms_per_step": ms / K,
-            "api": "hk_session_rollout (HostSession.rollout): per step H2D of one packed byte per game (host-action id | "
-                   "axis << 5, HK_F_ACT_PACKED) from pinned memory, one hk_step launch, D2H of the finished-game count",
+    ms = float(np.median(times))
+    return {"value": B * world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B, "d2h_bytes_per_step": B + 4,
+            "ms_per_step": ms / K, "repeats": repeats, "ms_per_step_all": [round(t / K, 5) for t in times],
+            "api": "hk_session_rollout_ex (HostSession.rollout): per step H2D of one packed byte per game (host-action id | "
+                   "axis << 5, HK_F_ACT_PACKED) from pinned memory, one hk_step_census launch, D2H of the per-game done "
+                   "flags (1 byte per game, pinned) and of the finished-game count; median of the repeats",
             "checksum_done": int(total_done)}
+
+
+def measure_collective(torch, dist, lib, C, dev, world, rank, games: int = 1 << 16):
+    """The one collective of the path: the all-gather (NCCL over NVLink) that assembles per-rank rollout buffers
+    for training, hironaka_b200.engine.gather_rollout — the analogue of the leading device axis pmap returns in
+    JAXTrainer.simulate (hironaka/jax/jax_trainer.py:316-320,558-592).  Each rank plays a real T-step rollout of
+    `games` games with the fused observation, producing obs [games*T, N*d] f32, policy logits [games*T, A] f32
+    and values [games*T] f32 (the last two are placeholders of the right size: the nets are out of scope), then
+    all ranks gather them.  Timed three ways on the device: the gather alone, the next rollout alone, and both
+    together (gather on a side stream) — the overlap fraction says how much of the gather hides behind play."""
+    from hironaka_b200.engine import gather_rollout
+    N, d, T = N_POINTS, DIM, T_ROLLOUT
+    A = 2 ** d - d - 1
+    rng = np.random.default_rng(500 + rank)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    x0 = torch.from_numpy(rng.integers(0, MAX_VALUE, size=(games, N, d), dtype=np.int32)).to(dev)
+    ha = torch.from_numpy(rng.integers(0, A, size=(T, games), dtype=np.int32)).to(dev)
+    ax = torch.from_numpy(rng.integers(0, d, size=(T, games), dtype=np.int32)).to(dev)
+    obs = torch.empty((T, games, N * d), dtype=torch.float32, device=dev)
+    policy = torch.zeros((games * T, A), dtype=torch.float32, device=dev)
+    value = torch.zeros(games * T, dtype=torch.float32, device=dev)
+    oflags = C.HK_F_ACT_DISCRETE | C.HK_F_OBS_SORT_LEX | C.HK_F_OBS_RESCALE | C.HK_F_RESCALE_EPS
+    x = x0.clone()
+
+    def rollout():
+        x.copy_(x0)
+        rc = lib.hk_step(x.data_ptr(), x.data_ptr(), None, None, None, None, None, None, None, None, games, N, d,
+                         C.HK_DTYPE_I32, C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0, -1.0, 1e8, stream)
+        for t in range(T):
+            rc |= lib.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), None, None, None,
+                              obs[t].data_ptr(), None, None, games, N, d, C.HK_DTYPE_I32,
+                              C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, oflags, -1.0, 1e8, stream)
+        assert rc == 0
+
+    def gather():
+        return gather_rollout((obs.view(games * T, N * d), policy, value))
+
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rollout()
+    out = gather()
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(out[0][rank], obs.view(games * T, N * d)))  # this rank's slice came back intact
+    side = torch.cuda.Stream(dev)
+
+    def both():
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            gather()
+        rollout()
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    ms_g, ms_r, ms_b = timed(gather), timed(rollout), timed(both)
+    sent = obs.numel() * 4 + policy.numel() * 4 + value.numel() * 4
+    recv = sent * (world - 1)
+    return {"what": "all_gather_into_tensor of one rollout's obs/policy/value per rank (engine.gather_rollout, NCCL)",
+            "games_per_rank": games, "steps": T, "bytes_sent_per_rank": sent, "bytes_received_per_rank": recv,
+            "gather_ms": ms_g, "bus_gbps": recv / (ms_g * 1e-3) / 1e9,
+            "nvlink_ref_gbps": 770.0, "bus_frac_of_measured_peer_copy": recv / (ms_g * 1e-3) / 1e9 / 770.0,
+            "rollout_with_features_ms": ms_r, "overlapped_ms": ms_b,
+            "overlap_fraction": max(0.0, min(1.0, (ms_g + ms_r - ms_b) / max(1e-9, min(ms_g, ms_r)))),
+            "own_slice_intact": ok}
 
 
 def main():
@@ -718,6 +845,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (profiling runs)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B tuning)")
+    ap.add_argument("--no-collective", action="store_true", help="skip the rollout all-gather leg (N > 1)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

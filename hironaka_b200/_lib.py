@@ -25,6 +25,8 @@ SIGNATURES = {
     "hk_debug_force_generic": (ctypes.c_int, [ctypes.c_int]),
     "hk_debug_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "hk_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
+    "hk_step_census": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
+    "hk_debug_set_sched_geometry": (ctypes.c_int, [ctypes.c_int]),
     "hk_shift": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_reposition": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "hk_newton_polytope": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
@@ -44,6 +46,7 @@ SIGNATURES = {
     "hk_session_get_state": (ctypes.c_int, [_p, _p]),
     "hk_session_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _u32, _u32]),
     "hk_session_rollout": (ctypes.c_int, [_p, _p, _p, _i32, _p, _u32, _u32]),
+    "hk_session_rollout_ex": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _u32, _u32]),
     "hk_session_state_ptr": (_p, [_p]),
     "hk_session_stream": (_p, [_p]),
 }

@@ -32,6 +32,7 @@ int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream
 
 namespace {
 
+std::atomic<int> g_sched_geometry{0};  // tuning hook (hk_debug_set_sched_geometry)
 std::atomic<int> g_use_pdl{0};  // programmatic dependent launch of the thread-per-game kernel (hk_debug_set_pdl)
 
 struct DevInfo {
@@ -88,6 +89,14 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     const bool obs = p.obs != nullptr;
+    if (p.census) {
+        // the census path: in-place single steps without fused observation or in-kernel players
+        const bool policy = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
+        if (p.out != p.in || p.T != 1 || obs || policy || p.host_out || p.ops == 0) return HK_ERR_UNSUPPORTED;
+        if (hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE))
+            return dtype == HK_DTYPE_I32 ? hk::launch_sched_i32(p, dev, stream) : hk::launch_sched_f32(p, dev, stream);
+        return dtype == HK_DTYPE_I32 ? hk::launch_generic_i32(p, false, dev, stream) : hk::launch_generic_f32(p, false, dev, stream);
+    }
     // remove_repeated alone is not on the step path: it runs on the warp-per-game kernel for every shape
     const bool small = hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE);
     if (dtype == HK_DTYPE_I32)
@@ -116,6 +125,7 @@ std::atomic<int> g_force_generic{0};
 namespace hk {
 int device_sms(int dev) { return device_sms_impl(dev); }
 bool use_pdl() { return g_use_pdl.load(std::memory_order_relaxed) != 0; }
+int sched_geometry() { return g_sched_geometry.load(std::memory_order_relaxed); }
 }  // namespace hk
 
 extern "C" {
@@ -143,6 +153,12 @@ int hk_debug_set_pdl(int on) {
     return HK_OK;
 }
 
+// tuning hook: geometry of the census-scheduled kernel (0 = 4 warps x 2 stages, 1 = 8 warps x 1 stage)
+int hk_debug_set_sched_geometry(int which) {
+    g_sched_geometry.store(which);
+    return HK_OK;
+}
+
 // test hook: route small shapes through the generic warp-per-game kernel as well
 int hk_debug_force_generic(int on) {
     g_force_generic.store(on ? 1 : 0);
@@ -161,6 +177,26 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
     p.num_points = num_points;
     p.obs = obs;
     p.obs_coord = obs_coord;
+    p.exceed_flag = exceed_flag;
+    p.ops = ops;
+    p.flags = flags;
+    p.threshold = value_threshold;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, float* reward,
+                   int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
+                   int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,
+                   void* stream) {
+    if (census == nullptr || state == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state, state, B, N, d, padding_value);
+    p.host_action = host_action;
+    p.axis = axis;
+    p.done = done;
+    p.reward = reward;
+    p.num_points = num_points;
+    p.census = census;
+    p.done_count = done_count;
     p.exceed_flag = exceed_flag;
     p.ops = ops;
     p.flags = flags;
@@ -353,18 +389,25 @@ struct hk_session {
     int N, d, dtype;
     float pad;
     cudaStream_t stream;
-    cudaStream_t copy_stream;
-    cudaEvent_t ready[2], freed[2];
+    cudaStream_t copy_stream;  // host -> device (actions)
+    cudaStream_t back_stream;  // device -> host (per-step results), so that the two directions overlap
+    cudaEvent_t ready[2], freed[2], drained[2];
     void* state;
     int32_t* host_action;  // two slots of B int32 each (double buffer for hk_session_rollout)
     int32_t* axis;
     int32_t* counts;       // per-step finished-game counts of a rollout (device)
     int32_t* counts_pinned; // pinned host mirror: a D2H copy into pageable memory would block the host every step
     int counts_cap;
-    uint8_t* done;
+    uint8_t* done;         // two slots of B bytes (double buffer for the per-step read-back of hk_session_rollout_ex)
     float* reward;
     int32_t* done_count;
+    uint8_t* census;       // [B] census of the resident state (hk_step_census); zeroed whenever the state is set
 };
+
+// the census step serves in-place single steps without fused observation or in-kernel players
+static bool census_eligible(uint32_t ops, uint32_t flags) {
+    return ops != 0 && !(flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST));
+}
 
 // sessions switch to their device for the duration of a call and restore the caller's device
 struct DeviceGuard {
@@ -402,14 +445,18 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
     s->pad = padding_value;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->back_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&s->ready[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->freed[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->drained[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaMalloc(&s->state, (size_t)B * N * d * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->host_action, (size_t)B * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4 * 2);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->census, (size_t)B);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->census, 0, (size_t)B, s->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->reward, (size_t)B * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_count, 4);
     // per-step count buffers of hk_session_rollout are sized here (allocating later would put a
@@ -433,6 +480,7 @@ int hk_session_destroy(hk_session* s) {
     cudaFree(s->host_action);
     cudaFree(s->axis);
     cudaFree(s->done);
+    cudaFree(s->census);
     cudaFree(s->reward);
     cudaFree(s->done_count);
     cudaFree(s->counts);
@@ -440,8 +488,10 @@ int hk_session_destroy(hk_session* s) {
     for (int i = 0; i < 2; ++i) {
         if (s->ready[i]) cudaEventDestroy(s->ready[i]);
         if (s->freed[i]) cudaEventDestroy(s->freed[i]);
+        if (s->drained[i]) cudaEventDestroy(s->drained[i]);
     }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->back_stream) cudaStreamDestroy(s->back_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HK_OK;
@@ -451,6 +501,7 @@ int hk_session_set_state(hk_session* s, const void* state_host) {
     if (!s || !state_host) return HK_ERR_BAD_ARG;
     DeviceGuard guard_(s->device);
     HK_CUDA(cudaMemcpyAsync(s->state, state_host, (size_t)s->B * s->N * s->d * 4, cudaMemcpyHostToDevice, s->stream));
+    HK_CUDA(cudaMemsetAsync(s->census, 0, (size_t)s->B, s->stream));  // every game unknown again
     HK_CUDA(cudaStreamSynchronize(s->stream));
     return HK_OK;
 }
@@ -484,8 +535,10 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
         HK_CUDA(cudaMemsetAsync(s->done_count, 0, 4, s->stream));
         p.done_count = s->done_count;
     }
+    if (census_eligible(ops, flags)) p.census = s->census;
     int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
     if (rc != HK_OK) return rc;
+    if (!p.census && ops != 0) HK_CUDA(cudaMemsetAsync(s->census, 0, (size_t)s->B, s->stream));  // stepped without it: stale
     if (done_host) HK_CUDA(cudaMemcpyAsync(done_host, s->done, (size_t)s->B, cudaMemcpyDeviceToHost, s->stream));
     if (reward_host) HK_CUDA(cudaMemcpyAsync(reward_host, s->reward, (size_t)s->B * 4, cudaMemcpyDeviceToHost, s->stream));
     if (done_count_host) HK_CUDA(cudaMemcpyAsync(done_count_host, s->done_count, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -493,8 +546,8 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
     return HK_OK;
 }
 
-int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
-                       int32_t* done_count_host, uint32_t ops, uint32_t flags) {
+int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                          int32_t* done_count_host, uint8_t* done_host, uint32_t ops, uint32_t flags) {
     const bool packed = flags & HK_F_ACT_PACKED;
     if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || (!axis_host && !packed)) return HK_ERR_BAD_ARG;
     DeviceGuard guard_(s->device);
@@ -510,19 +563,30 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
     }
     const size_t esz = (flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4;
     const size_t abytes = (size_t)s->B * esz;
+    const bool use_census = census_eligible(ops, flags);
     HK_CUDA(cudaMemsetAsync(s->counts, 0, (size_t)T * 4, s->stream));
+    // Three streams: uploads (copy_stream), steps (stream), read-backs (back_stream).  Step t uses slot t & 1 of
+    // the action and done buffers; the upload of step t waits until step t - 2 has run (freed), the read-back of
+    // step t waits for step t, and step t + 2 waits until that read-back has drained the slot (drained).
+    auto read_back = [&](int t) -> int {
+        const int slot = t & 1;
+        HK_CUDA(cudaStreamWaitEvent(s->back_stream, s->freed[slot], 0));
+        if (done_count_host)
+            HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->back_stream));
+        if (done_host)
+            HK_CUDA(cudaMemcpyAsync(done_host + (size_t)t * s->B, s->done + (size_t)slot * s->B, (size_t)s->B,
+                                    cudaMemcpyDeviceToHost, s->back_stream));
+        HK_CUDA(cudaEventRecord(s->drained[slot], s->back_stream));
+        return HK_OK;
+    };
     for (int t = 0; t < T; ++t) {
         const int slot = t & 1;
         int32_t* ha = s->host_action + (size_t)slot * s->B;
         int32_t* ax = s->axis + (size_t)slot * s->B;
-        // copy stream: wait until the step that last used this slot has run, bring that step's result
-        // back to the host (on this stream, so that the 4-byte read does not sit between two kernels of
-        // the compute stream), then upload step t
         if (t >= 2) {
             HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[slot], 0));
-            if (done_count_host)
-                HK_CUDA(cudaMemcpyAsync(s->counts_pinned + (t - 2), s->counts + (t - 2), 4, cudaMemcpyDeviceToHost,
-                                        s->copy_stream));
+            int rb = read_back(t - 2);
+            if (rb != HK_OK) return rb;
         }
         HK_CUDA(cudaMemcpyAsync(ha, (const char*)host_action_host + (size_t)t * abytes, abytes, cudaMemcpyHostToDevice,
                                 s->copy_stream));
@@ -531,26 +595,34 @@ int hk_session_rollout(hk_session* s, const void* host_action_host, const void* 
                                     s->copy_stream));
         HK_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
         HK_CUDA(cudaStreamWaitEvent(s->stream, s->ready[slot], 0));
+        if (t >= 2 && done_host) HK_CUDA(cudaStreamWaitEvent(s->stream, s->drained[slot], 0));
         StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
         p.host_action = ha;
         p.axis = packed ? nullptr : ax;
         p.done_count = s->counts + t;
+        p.done = done_host ? s->done + (size_t)slot * s->B : nullptr;
+        p.census = use_census ? s->census : nullptr;
         p.ops = ops;
         p.flags = flags;
         int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
         if (rc != HK_OK) return rc;
         HK_CUDA(cudaEventRecord(s->freed[slot], s->stream));
     }
-    if (done_count_host) {  // the results of the last two steps
-        for (int t = (T >= 2 ? T - 2 : 0); t < T; ++t) {
-            HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->freed[t & 1], 0));
-            HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->copy_stream));
-        }
+    if (!use_census) HK_CUDA(cudaMemsetAsync(s->census, 0, (size_t)s->B, s->stream));
+    for (int t = (T >= 2 ? T - 2 : 0); t < T; ++t) {  // the results of the last two steps
+        int rb = read_back(t);
+        if (rb != HK_OK) return rb;
     }
     HK_CUDA(cudaStreamSynchronize(s->stream));
     HK_CUDA(cudaStreamSynchronize(s->copy_stream));
+    HK_CUDA(cudaStreamSynchronize(s->back_stream));
     if (done_count_host) memcpy(done_count_host, s->counts_pinned, (size_t)T * 4);
     return HK_OK;
+}
+
+int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                       int32_t* done_count_host, uint32_t ops, uint32_t flags) {
+    return hk_session_rollout_ex(s, host_action_host, axis_host, T, done_count_host, nullptr, ops, flags);
 }
 
 void* hk_session_state_ptr(hk_session* s) { return s ? s->state : nullptr; }

@@ -39,18 +39,6 @@ __device__ __forceinline__ float warp_maxf(float v) {
     return v;
 }
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 constexpr uint32_t GENERIC_HOT_OPS = HK_OP_SHIFT | HK_OP_REPOSITION | HK_OP_NEWTON;
 constexpr uint32_t GENERIC_HOT_FLAGS = HK_F_ACT_DISCRETE;
 
@@ -63,7 +51,9 @@ __host__ __device__ constexpr int generic_compact_stride(int D) { return (D + 2)
 // 4 words), then the compact list of live rows, (N + 1) * generic_compact_stride(D) words
 // RT = rows per lane known at compile time (1: N <= 32, 2: N <= 64; the r-loops unroll and their
 // guards become predication) or 0 for any N (run-time loops).
-template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT>
+// CENSUS: the instantiation that serves hk_step_census (plain in-place single steps); it is separate so that
+// the census bookkeeping costs the other calls nothing (the kernel is bound by instruction issue).
+template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT, bool CENSUS = false>
 __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(const StepParams p, int warps_per_cta, int slot_words) {
     constexpr int NBUF = DEPTH + 1;
     // HOT: the plain random-play step (shift + reposition + newton, discrete host ids, int32 action arrays,
@@ -129,6 +119,31 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         }
     };
 
+    // ---- census (hk_step_census): games at rest are answered from their census byte and never loaded.
+    // Lane l holds the byte of the game this warp visits l iterations after `cbase` (two batches of 32, so that
+    // the look-ahead of the prefetch never waits on a load).
+    const bool use_census = CENSUS && (p.census != nullptr);
+    const bool frozen_rest = (kflags & HK_F_FREEZE_ENDED) && !(kops & (HK_OP_REPOSITION | HK_OP_RESCALE));
+    auto census_fetch = [&](long long it0) -> uint32_t {
+        const long long gg = gw + (it0 + lane) * nw;
+        return (use_census && gg < p.B) ? (uint32_t)__ldg(p.census + gg) : 0u;
+    };
+    long long cbase = 0;
+    uint32_t cv_cur = census_fetch(0), cv_nxt = census_fetch(32);
+    auto census_of = [&](long long it) -> uint32_t {  // it in [cbase, cbase + 64), warp-uniform
+        const int o = (int)(it - cbase);
+        return __shfl_sync(0xffffffffu, (o < 32) ? cv_cur : cv_nxt, o & 31);
+    };
+    auto at_rest = [&](uint32_t v) -> bool { return (v & 0x80u) && ((v & 2u) || frozen_rest); };
+    // finished-game counts: lane l accumulates the games finished after steps l and l + 32 and flushes them
+    // once, instead of one same-address atomic per game and step
+    int dc0 = 0, dc1 = 0;
+    auto count_done = [&](int st) {
+        if (st < 32) dc0 += (lane == st) ? 1 : 0;
+        else if (st < 64) dc1 += (lane == st - 32) ? 1 : 0;
+        else if (lane == 0) atomicAdd(p.done_count + st, 1);
+    };
+
     int b = 0;
     int32_t ha_nx = 3, ax_nx = 0;
     if ((kops & HK_OP_SHIFT) && gw < p.B) {
@@ -136,13 +151,19 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
     }
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) {
-        if (gw + k * nw < p.B) prefetch(gw + k * nw, k);
+        if (gw + k * nw < p.B && !(use_census && at_rest(census_of(k)))) prefetch(gw + k * nw, k);
         cp_async_commit();
     }
-    for (long long g = gw; g < p.B; g += nw, b = (b + 1 == NBUF) ? 0 : b + 1) {
+    long long it = 0;
+    for (long long g = gw; g < p.B; g += nw, ++it, b = (b + 1 == NBUF) ? 0 : b + 1) {
+        if (use_census && it - cbase == 32) {
+            cbase += 32;
+            cv_cur = cv_nxt;
+            cv_nxt = census_fetch(cbase + 32);
+        }
         {   // the buffer that held the previous game is free: the game DEPTH iterations ahead goes there
             const int bn = (b + DEPTH >= NBUF) ? b + DEPTH - NBUF : b + DEPTH;
-            if (g + DEPTH * nw < p.B) prefetch(g + DEPTH * nw, bn);
+            if (g + DEPTH * nw < p.B && !(use_census && at_rest(census_of(it + DEPTH)))) prefetch(g + DEPTH * nw, bn);
         }
         cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
         // this game's actions were requested one iteration ago (a dependent global load per game would
@@ -150,6 +171,18 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         int32_t ha = ha_nx, ax = ax_nx;
         if ((kops & HK_OP_SHIFT) && g + nw < p.B) {
             load_actions(p, kflags, g + nw, ha_nx, ax_nx);
+        }
+        if (use_census) {
+            const uint32_t cvg = census_of(it);
+            if (at_rest(cvg)) {  // nothing to load, nothing to do: the outputs of a game at rest are constants
+                if (lane == 0) {
+                    if (p.done) p.done[g] = 1;
+                    if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
+                    if (p.num_points) p.num_points[g] = (int32_t)(cvg & 1u);
+                }
+                if (p.done_count) count_done(0);
+                continue;
+            }
         }
         cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
@@ -232,9 +265,22 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             if (lane == 0) {
                 if (p.done) p.done[g] = 1;
                 if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
-                if (p.done_count) atomicAdd(p.done_count, 1);
                 if (p.num_points) p.num_points[g] = cnt;
                 if (p.length) p.length[g] = 0;
+            }
+            if (p.done_count) count_done(0);
+            if (use_census) {  // (dead rows are normalised by now: kops != 0 on the census path)
+                bool moving = false;  // a live row away from the origin
+                _Pragma("unroll UNR")
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i < N && ((mylive >> r) & 1u)) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) moving = moving || (Elem<T>::bits(x[i * D + k]) != 0);
+                    }
+                }
+                const bool org = !__any_sync(0xffffffffu, moving);
+                if (lane == 0) p.census[g] = (uint8_t)(0x80u | (org ? 2u : 0u) | (uint32_t)cnt);
             }
             if (p.exceed_flag) {
                 if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
@@ -396,11 +442,21 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                         const float rw = (dn && !prev_done) ? 1.0f : 0.0f;
                         p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
                     }
-                    if (p.done_count && dn) atomicAdd(p.done_count + st, 1);
                 }
+                if (p.done_count && dn) count_done(st);
                 if (dn && !prev_done) len = st + 1;
                 ha = ha_n;
                 ax = ax_n;
+            }
+            if (use_census) {
+                bool moving = false;
+                if ((live >> lane) & 1u) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) moving = moving || (Elem<T>::bits(v[k]) != 0);
+                }
+                const bool org = !__any_sync(0xffffffffu, moving);
+                if (lane == 0)
+                    p.census[g] = (uint8_t)((cur <= 1) ? (0x80u | (org ? 2u : 0u) | (uint32_t)cur) : (uint32_t)(cur > 127 ? 127 : cur));
             }
             // survivors and killed rows go back to their slots of the padded game
             const bool alive = (live >> lane) & 1u;
@@ -748,12 +804,28 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     float rw = (dn && !prev_done) ? 1.0f : 0.0f;
                     p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
                 }
-                if (p.done_count && dn) atomicAdd(p.done_count + st, 1);
             }
+            if (p.done_count && dn) count_done(st);
             if (dn && !prev_done) len = st + 1;
             ha = ha_n;
             ax = ax_n;
             __syncwarp();
+        }
+        if (use_census) {
+            bool moving = false;
+            if (cnt <= 1) {
+                _Pragma("unroll UNR")
+                for (int r = 0; r < R; ++r) {
+                    const int i = lane + 32 * r;
+                    if (i < N && ((mylive >> r) & 1u)) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) moving = moving || (Elem<T>::bits(x[i * D + k]) != 0);
+                    }
+                }
+            }
+            const bool org = !__any_sync(0xffffffffu, moving);
+            if (lane == 0)
+                p.census[g] = (uint8_t)((cnt <= 1) ? (0x80u | (org ? 2u : 0u) | (uint32_t)cnt) : (uint32_t)(cnt > 127 ? 127 : cnt));
         }
         // ---- outputs ----
         bool exceed = false;
@@ -873,6 +945,10 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         __syncwarp();  // every lane is done with buffer b before the next prefetch may overwrite it
     }
     cp_async_wait<0>();
+    if (p.done_count) {
+        if (dc0) atomicAdd(p.done_count + lane, dc0);
+        if (dc1) atomicAdd(p.done_count + 32 + lane, dc1);
+    }
 }
 
 }  // namespace hk

@@ -7,9 +7,9 @@
 namespace hk {
 namespace {
 
-template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT>
+template <typename T, int D, bool OBS, int RT, int DEPTH, bool HOT, bool CENSUS = false>
 int launch_generic_hot(const StepParams& p, int dev, cudaStream_t stream) {
-    auto kernel = hk_generic_kernel<T, D, OBS, RT, DEPTH, HOT>;
+    auto kernel = hk_generic_kernel<T, D, OBS, RT, DEPTH, HOT, CENSUS>;
     const int W = p.N * D;
     const int Wpad = (W + 3) & ~3;
     const int R = (p.N + 31) / 32;
@@ -58,7 +58,11 @@ int launch_generic_rt(const StepParams& p, int dev, cudaStream_t stream) {
     if constexpr (!OBS && RT > 0 && std::is_same<T, int32_t>::value) {
         const bool hot = p.T == 1 && p.ops == GENERIC_HOT_OPS && p.flags == GENERIC_HOT_FLAGS && !p.host_out &&
                          p.host_action && p.axis;
-        if (hot) return launch_generic_hot<T, D, OBS, RT, 1, true>(p, dev, stream);
+        if (hot) return p.census ? launch_generic_hot<T, D, OBS, RT, 1, true, true>(p, dev, stream)
+                                 : launch_generic_hot<T, D, OBS, RT, 1, true>(p, dev, stream);
+    }
+    if constexpr (!OBS) {
+        if (p.census) return launch_generic_hot<T, D, OBS, RT, 1, false, true>(p, dev, stream);
     }
     return launch_generic_hot<T, D, OBS, RT, 1, false>(p, dev, stream);
 }

@@ -16,6 +16,7 @@ constexpr int kMaxDevices = 64;
 
 int device_sms(int dev);  // hk_capi.cu
 bool use_pdl();           // hk_capi.cu (hk_debug_set_pdl)
+int sched_geometry();     // hk_capi.cu (hk_debug_set_sched_geometry)
 
 // per-kernel, per-device launch facts (dynamic smem opt-in + resident CTAs per SM), computed once
 struct KernelFacts {
@@ -49,6 +50,9 @@ inline bool is_small_shape(int N, int d) { return d == 3 && (N == 20 || N == 10 
 // thread-per-game family (hk_small.cuh); `obs` selects the instantiation that builds features
 int launch_small_i32(const StepParams& p, bool obs, int dev, cudaStream_t stream);
 int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream);
+// census-scheduled thread-per-game kernel (hk_sched.cuh): in-place single steps with p.census
+int launch_sched_i32(const StepParams& p, int dev, cudaStream_t stream);
+int launch_sched_f32(const StepParams& p, int dev, cudaStream_t stream);
 // warp-per-game family (hk_generic.cuh)
 int launch_generic_i32(const StepParams& p, bool obs, int dev, cudaStream_t stream);
 int launch_generic_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream);

@@ -1,0 +1,341 @@
+// hk_sched.cuh — census-scheduled thread-per-game step kernel (in-place single steps of small games).
+//
+// The tile-ring kernel (hk_small.cuh) reads every game every step and lets a tile's BUSIEST game pick the
+// tier for all 32.  In a rollout that wastes most of the work: a game that has ended sits at a fixed point
+// (a lone point at the origin: 52 % of the games after 5 random-play steps at (20,3), 95 % after 10), and the
+// live counts inside a tile are heavy-tailed (mean 6 rows, tile maximum 11 at the root).  This kernel keeps
+// a CENSUS — one byte per game, written by the previous step — and schedules by it:
+//   * games at rest are not loaded at all: their done = 1 / reward = 0 come from the census byte;
+//   * the other games of a warp's tiles are ordered by live count (counting sort over six tier classes)
+//     and cut into chunks of 32, so that a chunk's tier fits all of its games;
+//   * each chunk is gathered game by game: where a game is a whole number of 16-byte words ((20,3): 240 B)
+//     every lane issues ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) for its own game onto the stage's
+//     mbarrier, and a changed game goes back with one bulk store per lane; the other shapes ((10,3), (5,3),
+//     unaligned pointers) are copied with cp.async in 8/4-byte pieces, 15 lanes per game.  The chunk is
+//     processed by the same per-game code as the tile-ring kernel (small_process_tile).
+// Work and DRAM traffic follow the number of games still in play instead of the batch size.
+//
+// Census byte (HK census, include/hironaka_b200.h): 0 = unknown (the game is read and counted);
+// 1..127 = live rows of a game in play; 0x80 | c | (o ? 2 : 0) = ended game with c <= 1 live rows, dead rows
+// normalised, o = at rest for every op (no row, or the lone row at the origin).
+#pragma once
+#include "hk_small.cuh"
+
+namespace hk {
+
+constexpr int SCHED_ROUND_TILES = 32;  // tiles (of 32 games) a warp schedules together
+#ifndef SCHED_NATURAL_NUM
+#define SCHED_NATURAL_NUM 1  // a round is stepped tile by tile in natural order while at least NUM / DEN of
+#define SCHED_NATURAL_DEN 2  // its games are in play (tools/time_census.py)
+#endif
+
+template <int N, int D, int WARPS, int STAGES>
+struct SchedLayout {
+    static constexpr int W = N * D;
+    static constexpr int STAGE_WORDS = 32 * W;
+    // per warp: STAGES game stages, the class bytes of a round (one per game), the sorted order (u16 per game)
+    static constexpr int CLS_WORDS = SCHED_ROUND_TILES * 32 / 4;
+    static constexpr int ORDER_WORDS = SCHED_ROUND_TILES * 32 / 2;
+    static constexpr int WARP_WORDS = STAGES * STAGE_WORDS + CLS_WORDS + ORDER_WORDS;
+    static constexpr int BAR_BYTES = 256;  // mbarriers first (WARPS * STAGES of them), then the warps' areas
+    static_assert(WARPS * STAGES * 8 <= BAR_BYTES, "mbarrier area too small");
+    static constexpr size_t SMEM_BYTES = BAR_BYTES + (size_t)WARPS * WARP_WORDS * 4;
+};
+
+__device__ __forceinline__ int census_class(uint32_t v) {
+    if (v == 0) return 6;          // unknown: counted after the load
+    if (v & 0x80u) return 1;       // ended, but not at rest under this launch's ops
+    return v <= 2 ? 1 : (v <= 4 ? 2 : (v <= 8 ? 3 : (v <= 12 ? 4 : (v <= 16 ? 5 : 6))));
+}
+
+template <typename T, int N, int D, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p) {
+    using L = SchedLayout<N, D, WARPS, STAGES>;
+    constexpr int W = L::W;
+    constexpr int CHW = (W % 4 == 0) ? 4 : ((W % 2 == 0) ? 2 : 1);  // words per copy piece
+    constexpr int LPG = W / CHW;                                     // lanes per game
+    static_assert(LPG <= 32, "a game is copied by at most one warp instruction");
+    constexpr int GPI = 32 / LPG;                                    // games per copy instruction
+    constexpr int COPY_ITERS = (32 + GPI - 1) / GPI;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + warp * STAGES;
+    uint32_t* wbase = reinterpret_cast<uint32_t*>(smem_raw + L::BAR_BYTES) + (size_t)warp * L::WARP_WORDS;
+    uint32_t* stages = wbase;
+    uint8_t* clsb = reinterpret_cast<uint8_t*>(wbase + STAGES * L::STAGE_WORDS);
+    uint16_t* order = reinterpret_cast<uint16_t*>(wbase + STAGES * L::STAGE_WORDS + L::CLS_WORDS);
+
+    const long long B = p.B;
+    const long long ntiles = (B + 31) >> 5;
+    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    const long long nw = (long long)gridDim.x * WARPS;
+    uint32_t* gst = reinterpret_cast<uint32_t*>(p.out);  // in place: p.out == p.in
+    const bool piece_ok = ((reinterpret_cast<uintptr_t>(p.out)) & (CHW * 4 - 1)) == 0;
+    // one TMA bulk copy per game when a game is a whole number of 16-byte words and the state is 16-byte aligned
+    const bool bulk = ((W * 4) % 16 == 0) && aligned16(p.out);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+    const uint32_t lt = (1u << lane) - 1u;
+    // at rest under THIS launch: nothing to do for an origin / empty game; a frozen ended game also rests when
+    // neither reposition nor rescale would move its lone point
+    const bool frozen_rest = (p.flags & HK_F_FREEZE_ENDED) && !(p.ops & (HK_OP_REPOSITION | HK_OP_RESCALE));
+    const float rest_reward = (p.flags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
+    // piece lane -> (game slot within the instruction, piece within the game)
+    const int sub = lane / LPG, piece = lane - sub * LPG;
+    int settled_total = 0;
+
+    // A warp owns a CONTIGUOUS run of tiles (its games share DRAM pages when they are gathered one by one),
+    // scheduled in rounds of SCHED_ROUND_TILES.
+    const long long tpw = (ntiles + nw - 1) / nw;
+    const long long t_begin = gw * tpw;
+    const long long t_end = (t_begin + tpw < ntiles) ? (t_begin + tpw) : ntiles;
+    for (long long t0 = t_begin; t0 < t_end; t0 += SCHED_ROUND_TILES) {
+        // ---- census of this round's tiles: outputs of the games at rest, class bytes of the others ----
+        const int nk = (int)((t_end - t0 < SCHED_ROUND_TILES) ? (t_end - t0) : SCHED_ROUND_TILES);
+        uint32_t tilemask = 0, classes = 0;
+        int inplay = 0, ngames = 0;
+        // all census bytes of the round are requested before the first one is used (the stores below may alias
+        // them as far as the compiler knows, so a single loop would wait for every load in turn)
+        uint32_t cv[SCHED_ROUND_TILES];
+#pragma unroll
+        for (int k = 0; k < SCHED_ROUND_TILES; ++k) {
+            const long long g = ((t0 + k) << 5) + lane;
+            cv[k] = (k < nk && g < B) ? (uint32_t)__ldg(p.census + g) : 0x100u;  // 0x100: no such game
+        }
+#pragma unroll
+        for (int k = 0; k < SCHED_ROUND_TILES; ++k) {
+            if (k < nk) {
+                const long long g = ((t0 + k) << 5) + lane;
+                const uint32_t v = cv[k];
+                const bool valid = v != 0x100u;
+                const bool rest = valid && (v & 0x80u) && ((v & 2u) || frozen_rest);
+                if (rest) {
+                    if (p.done) p.done[g] = 1;
+                    if (p.reward) p.reward[g] = rest_reward;
+                    if (p.num_points) p.num_points[g] = (int32_t)(v & 1u);
+                }
+                const int c = (!valid || rest) ? 0 : census_class(v);
+                clsb[k * 32 + lane] = (uint8_t)c;
+                settled_total += __popc(__ballot_sync(0xffffffffu, rest));
+                const uint32_t play = __ballot_sync(0xffffffffu, c != 0);
+                if (play) tilemask |= 1u << k;
+                inplay += __popc(play);
+                ngames += __popc(__ballot_sync(0xffffffffu, valid));
+                classes |= 1u << c;
+            }
+        }
+        classes = __reduce_or_sync(0xffffffffu, classes) & ~1u;
+        __syncwarp();
+        if (inplay == 0) continue;
+        // While most games are still in play the tiles are stepped whole, in natural order: one bulk copy per
+        // tile and coalesced actions / outputs beat the per-game gather, and there is little to skip.  Later the
+        // games in play are sorted by class and gathered one by one.
+        const bool natural = inplay * SCHED_NATURAL_DEN >= ngames * SCHED_NATURAL_NUM;
+        // ---- counting sort of the games in play by class: order[] lists them (tile slot * 32 + lane) ----
+        int total = 0;
+        for (int q = 1; q <= 6 && !natural; ++q) {
+            if (!((classes >> q) & 1u)) continue;
+            for (int k = 0; k < nk; ++k) {
+                if (!((tilemask >> k) & 1u)) continue;
+                const bool m = clsb[k * 32 + lane] == q;
+                const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                if (m) order[total + __popc(bal & lt)] = (uint16_t)(k * 32 + lane);
+                total += __popc(bal);
+            }
+        }
+        __syncwarp();
+        const int nchunks = natural ? __popc(tilemask) : ((total + 31) >> 5);
+        uint32_t tiles_left = tilemask;  // natural order: the tiles still to be requested
+
+        // lane's game of chunk v (natural order: the next tile with a game in play; its games at rest ride along
+        // in the tile copy but are not stepped: their outputs were written above)
+        auto chunk_game = [&](int v, long long& g, bool& valid) {
+            if (natural) {
+                const int k = __ffs((int)tiles_left) - 1;
+                tiles_left &= tiles_left - 1;
+                g = ((t0 + k) << 5) + lane;
+                valid = (g < B) && (clsb[k * 32 + lane] != 0);
+                return;
+            }
+            const int idx = v * 32 + lane;
+            valid = idx < total;
+            const int lid = valid ? (int)order[idx] : 0;
+            g = ((t0 + (lid >> 5)) << 5) + (lid & 31);
+        };
+        // gather the chunk's games into a stage: game slot s at s * W words
+        auto gather = [&](long long g, bool valid, uint32_t* stage, int sidx) {
+            if (natural) {  // the whole tile: games g - lane .. of which (B - first) may be fewer than 32
+                const long long first = g - lane;
+                const int cnt = (int)((B - first < 32) ? (B - first) : 32);
+                if (bulk) {
+                    bulk_wait_read<0>();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(&bar[sidx], (uint32_t)cnt * (uint32_t)(W * 4));
+                        bulk_load(stage, gst + first * W, (uint32_t)cnt * (uint32_t)(W * 4), &bar[sidx]);
+                    }
+                    return;
+                }
+                if (piece_ok) {
+                    for (int w = lane * CHW; w < cnt * W; w += 32 * CHW) {
+                        if constexpr (CHW == 4) cp_async_16(stage + w, gst + first * W + w);
+                        else if constexpr (CHW == 2) cp_async_8(stage + w, gst + first * W + w);
+                        else cp_async_4(stage + w, gst + first * W + w);
+                    }
+                } else {
+                    for (int w = lane; w < cnt * W; w += 32) cp_async_4(stage + w, gst + first * W + w);
+                }
+                cp_async_commit();
+                return;
+            }
+            if (bulk) {
+                // the lane's own earlier bulk store from this stage must have finished READING it
+                bulk_wait_read<0>();
+                const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+                if (lane == 0) mbar_expect_tx(&bar[sidx], (uint32_t)nvalid * (uint32_t)(W * 4));
+                __syncwarp();
+                if (valid) bulk_load(stage + lane * W, gst + g * W, (uint32_t)(W * 4), &bar[sidx]);
+                return;
+            }
+            if (piece_ok) {
+#pragma unroll
+                for (int it = 0; it < COPY_ITERS; ++it) {
+                    const int s = it * GPI + sub;
+                    const long long gs = __shfl_sync(0xffffffffu, g, s & 31);
+                    const bool vs = __shfl_sync(0xffffffffu, valid ? 1 : 0, s & 31) != 0;
+                    if (sub < GPI && s < 32 && vs) {
+                        uint32_t* dst = stage + s * W + piece * CHW;
+                        const uint32_t* src = gst + gs * W + piece * CHW;
+                        if constexpr (CHW == 4) cp_async_16(dst, src);
+                        else if constexpr (CHW == 2) cp_async_8(dst, src);
+                        else cp_async_4(dst, src);
+                    }
+                }
+            } else {  // state pointer aligned to 4 bytes only: word copies
+                for (int s = 0; s < 32; ++s) {
+                    const long long gs = __shfl_sync(0xffffffffu, g, s);
+                    const bool vs = __shfl_sync(0xffffffffu, valid ? 1 : 0, s) != 0;
+                    if (vs) {
+                        for (int w = lane; w < W; w += 32) cp_async_4(stage + s * W + w, gst + gs * W + w);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+
+        long long g_cur, g_nxt = 0;
+        bool v_cur, v_nxt = false;
+        chunk_game(0, g_cur, v_cur);
+        gather(g_cur, v_cur, stages, 0);
+        for (int v = 0; v < nchunks; ++v) {
+            const int sidx = (STAGES == 1) ? 0 : (v & 1);
+            uint32_t* stage = stages + sidx * L::STAGE_WORDS;
+            LaneState ls;
+            ls.g = g_cur;
+            ls.valid = v_cur;
+            ls.shift = (p.ops & HK_OP_SHIFT) && ls.valid;
+            ls.ha = 3;
+            ls.ax = 0;
+            ls.origin = false;
+            if (ls.shift) load_actions(p, p.flags, ls.g, ls.ha, ls.ax);
+            if (bulk) {  // this chunk's games have landed (they were requested one chunk ago)
+                mbar_wait(&bar[sidx], (phase_bits >> sidx) & 1u);
+                phase_bits ^= (1u << sidx);
+            }
+            if constexpr (STAGES >= 2) {
+                // the next chunk streams into the other stage while this one is processed (its bulk stores of
+                // the chunk before have had the wait above to drain)
+                if (v + 1 < nchunks) {
+                    chunk_game(v + 1, g_nxt, v_nxt);
+                    gather(g_nxt, v_nxt, stages + ((v + 1) & 1) * L::STAGE_WORDS, (v + 1) & 1);
+                    if (!bulk) cp_async_wait<1>();
+                } else {
+                    if (!bulk) cp_async_wait<0>();
+                }
+            } else {
+                if (!bulk) cp_async_wait<0>();
+            }
+            __syncwarp();
+            uint32_t* row = stage + lane * W;
+            bool exceed = false;
+            bool chg = false;  // in place: only changed games go back
+            small_process_tile<T, N, D, false>(p, ls, row, exceed, chg);
+            if (ls.valid) {
+                if (p.num_points) p.num_points[ls.g] = ls.cnt;
+                const uint32_t nv = (ls.cnt <= 1) ? (0x80u | (ls.origin ? 2u : 0u) | (uint32_t)ls.cnt)
+                                                  : (uint32_t)(ls.cnt > 127 ? 127 : ls.cnt);
+                p.census[ls.g] = (uint8_t)nv;
+            }
+            if (p.exceed_flag) {
+                if (__any_sync(0xffffffffu, exceed && ls.valid) && lane == 0) *p.exceed_flag = 1;
+            }
+            // ---- write-back of the changed games, GPI games per instruction ----
+            uint32_t dirty = __ballot_sync(0xffffffffu, ls.valid && chg);
+            __syncwarp();
+            if (natural && __popc(dirty) > HK_SPARSE_STORE_MAX) {  // many changed games: the tile goes back whole
+                const long long first = ls.g - lane;
+                const int cnt = (int)((B - first < 32) ? (B - first) : 32);
+                if (bulk) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_store(gst + first * W, stage, (uint32_t)cnt * (uint32_t)(W * 4));
+                    bulk_commit();
+                } else {
+                    warp_copy_words(gst + first * W, stage, cnt * W, lane);
+                }
+            } else if (bulk) {
+                if (dirty) {
+                    fence_async_smem();  // the lanes' st.shared results before the async-proxy reads of the stores
+                    __syncwarp();
+                    if (ls.valid && chg) bulk_store(gst + ls.g * W, row, (uint32_t)(W * 4));
+                    bulk_commit();
+                }
+            } else if (piece_ok) {
+                while (dirty) {
+                    int s = -1;
+                    uint32_t m = dirty;
+#pragma unroll
+                    for (int q = 0; q < GPI; ++q) {  // the q-th dirty game goes to the lanes with sub == q
+                        const int b = m ? (__ffs((int)m) - 1) : -1;
+                        m &= m - 1;
+                        if (q == sub) s = b;
+                    }
+                    dirty = m;
+                    const long long gs = __shfl_sync(0xffffffffu, ls.g, s < 0 ? 0 : s);
+                    if (sub < GPI && s >= 0) {
+                        const uint32_t* src = stage + s * W + piece * CHW;
+                        uint32_t* dst = gst + gs * W + piece * CHW;
+                        if constexpr (CHW == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                        else if constexpr (CHW == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+                        else *dst = *src;
+                    }
+                }
+            } else {
+                while (dirty) {
+                    const int s = __ffs((int)dirty) - 1;
+                    dirty &= dirty - 1;
+                    const long long gs = __shfl_sync(0xffffffffu, ls.g, s);
+                    warp_copy_words(gst + gs * W, stage + s * W, W, lane);
+                }
+            }
+            __syncwarp();  // every lane is done with this stage before a later gather overwrites it
+            if constexpr (STAGES == 1) {
+                if (v + 1 < nchunks) {
+                    chunk_game(v + 1, g_nxt, v_nxt);
+                    gather(g_nxt, v_nxt, stages, 0);
+                }
+            }
+            g_cur = g_nxt;
+            v_cur = v_nxt;
+        }
+    }
+    if (bulk) bulk_wait_all<0>();  // this lane's bulk stores are globally complete before the warp retires
+    if (p.done_count && settled_total && lane == 0) atomicAdd(p.done_count, settled_total);
+}
+
+}  // namespace hk

@@ -1,0 +1,45 @@
+// hk_sched_launch.inl — launch code of the census-scheduled kernel, included by hk_sched_*.cu
+#include "hk_launch.cuh"
+#include "hk_sched.cuh"
+
+namespace hk {
+namespace {
+
+template <typename T, int N, int D, int WARPS, int STAGES>
+int launch_sched_geom(const StepParams& p, int dev, cudaStream_t stream) {
+    using L = SchedLayout<N, D, WARPS, STAGES>;
+    static KernelFacts facts;
+    auto kernel = hk_sched_kernel<T, N, D, WARPS, STAGES>;
+    cudaError_t err = cudaSuccess;
+    const int threads = WARPS * 32;
+    const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
+    if (err != cudaSuccess) return (int)err;
+    const long long ntiles = (p.B + 31) / 32;
+    long long ctas = (ntiles + WARPS - 1) / WARPS;
+    const long long cap = (long long)device_sms(dev) * per_sm;  // persistent: one wave
+    if (ctas > cap) ctas = cap;
+    kernel<<<(unsigned)ctas, threads, L::SMEM_BYTES, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int N, int D>
+int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
+    // geometry (warps per CTA x stages per warp): see DESIGN.md "K-sched"; hk_debug_set_sched_geometry switches it
+    switch (sched_geometry()) {
+        case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
+        default: return launch_sched_geom<T, N, D, 4, 2>(p, dev, stream);
+    }
+}
+
+template <typename T>
+int dispatch_sched(const StepParams& p, int dev, cudaStream_t stream) {
+    if (p.d == 3) {
+        if (p.N == 20) return launch_sched_shape<T, 20, 3>(p, dev, stream);
+        if (p.N == 10) return launch_sched_shape<T, 10, 3>(p, dev, stream);
+        if (p.N == 5) return launch_sched_shape<T, 5, 3>(p, dev, stream);
+    }
+    return HK_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+}  // namespace hk

@@ -384,6 +384,7 @@ struct LaneState {
     int32_t ha, ax;
     int cnt;
     int32_t len;
+    bool origin;  // census only: no live row, or the lone live row sits at the origin (a fixed point of every op)
 };
 
 __host__ __device__ constexpr int next_lower_tier(int K) {
@@ -472,6 +473,21 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
     chg = tchg;
     const bool last = st >= p.T;
     if (last && p.exceed_flag) exceed = exceeds<T, K, D>(y, clm, p.threshold);
+    if (p.census) {  // (warp-uniform) is the game at rest?  Only ended games can be.
+        if (K <= 4 || __any_sync(0xffffffffu, ls.cnt <= 1)) {
+            uint32_t nz = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) o |= (uint32_t)Elem<T>::bits(y[k * D + c]);
+                nz |= ((clm >> k) & 1u) ? o : 0u;
+            }
+            ls.origin = (nz == 0);
+        } else {
+            ls.origin = false;
+        }
+    }
     if (mutate) {
         if constexpr (K == N) {
 #pragma unroll
@@ -855,6 +871,100 @@ __device__ __noinline__ void features_rolled(const uint32_t* row, uint32_t lm, i
     }
 }
 
+// One tile (the lane's game sits in `row`, its shared-memory area) through all p.T steps: liveness pass and
+// dead-row check, the warp's tier by the largest live count, the steps on compact rows, per-step outputs.
+// On return `row` holds the new state, ls.cnt / ls.len / ls.origin describe it, `chg` says whether the
+// game must be written back.  Shared by the tile-ring kernel below and the census-scheduled kernel
+// (hk_sched.cuh).
+template <typename T, int N, int D, bool POLICY>
+__device__ __forceinline__ void small_process_tile(const StepParams& p, LaneState& ls, uint32_t* row, bool& exceed,
+                                                   bool& chg) {
+    constexpr int W = N * D;
+    const T padv = Elem<T>::pad(p.pad);
+    const bool mutate = p.ops != 0;
+    bool normalised = false;
+    ls.len = -1;
+    int st = 0;
+    do {
+        T x[W];
+        load_game<T, W>(row, x);
+        if constexpr (Elem<T>::is_float) {
+            uint32_t canon = 0;
+#pragma unroll
+            for (int q = 0; q < W; ++q) {  // canonicalise -0.0 (a game that held one counts as changed)
+                const float c = x[q] + 0.0f;
+                canon |= (uint32_t)__float_as_int(x[q]) ^ (uint32_t)__float_as_int(c);
+                x[q] = c;
+            }
+            chg = chg || (canon != 0);
+        }
+        // Every reference op rewrites dead rows with the padding value.  States produced by these
+        // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything
+        // else counts as a change of its game) and the rewrite below runs only if some game needs it.
+        // One pass yields the live mask (sign of coordinate 0) and the check.
+        bool any_junk = false;
+        uint32_t lm;
+        {
+            const bool check = mutate && !normalised;
+            const uint32_t pbits = (uint32_t)Elem<T>::bits(padv);
+            uint32_t dead = 0, diff = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const uint32_t sgn = (uint32_t)(Elem<T>::bits(x[i * D]) >> 31);  // all ones <=> dead row
+                dead |= sgn & (1u << i);
+                uint32_t dr = 0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) dr |= (uint32_t)Elem<T>::bits(x[i * D + c]) ^ pbits;
+                diff |= dr & sgn;
+            }
+            lm = ~dead & ((N == 32) ? 0xffffffffu : ((1u << N) - 1u));
+            if (check) {
+                chg = chg || (diff != 0);
+                any_junk = __any_sync(0xffffffffu, diff != 0);
+            }
+        }
+        ls.cnt = __popc(lm);
+        if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
+        const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
+        // the gathered tiers scatter only live rows: dead rows that need it are rewritten first
+        auto prestore = [&]() {
+            if (mutate && !normalised) {
+                if (any_junk) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
+                    }
+                    store_game<T, W>(row, x);
+                }
+                normalised = true;
+            }
+        };
+        if (N > 2 && p.T == 1 && lmax <= 2) {  // the tail of a rollout driven step by step: ended games and two-point games only
+            prestore();
+            st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+        } else if (N > 4 && lmax <= 4) {
+            prestore();
+            st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+        } else if (N > 8 && lmax <= 8) {
+            prestore();
+            st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+        } else if (N > 12 && lmax <= 12) {
+            if (W % 4 != 0) prestore();
+            st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            normalised = normalised || (W % 4 == 0);
+        } else if (N > 16 && lmax <= 16) {
+            if (W % 4 != 0) prestore();
+            st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            normalised = normalised || (W % 4 == 0);
+        } else {
+            st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            normalised = true;
+        }
+    } while (st < p.T);
+
+}
+
 // ---- tile movement -------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
@@ -941,89 +1051,10 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         }
 
         bool exceed = false;
-        bool normalised = false;
         // Did this lane's game change?  Unchanged games of an in-place call are not written back
         // (everything is when out != in).
         bool chg = !inplace;
-        ls.len = -1;
-        int st = 0;
-        do {
-            T x[W];
-            load_game<T, W>(row, x);
-            if constexpr (Elem<T>::is_float) {
-                uint32_t canon = 0;
-#pragma unroll
-                for (int q = 0; q < W; ++q) {  // canonicalise -0.0 (a game that held one counts as changed)
-                    const float c = x[q] + 0.0f;
-                    canon |= (uint32_t)__float_as_int(x[q]) ^ (uint32_t)__float_as_int(c);
-                    x[q] = c;
-                }
-                chg = chg || (canon != 0);
-            }
-            // Every reference op rewrites dead rows with the padding value.  States produced by these
-            // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything
-            // else counts as a change of its game) and the rewrite below runs only if some game needs it.
-            // One pass yields the live mask (sign of coordinate 0) and the check.
-            bool any_junk = false;
-            uint32_t lm;
-            {
-                const bool check = mutate && !normalised;
-                const uint32_t pbits = (uint32_t)Elem<T>::bits(padv);
-                uint32_t dead = 0, diff = 0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const uint32_t sgn = (uint32_t)(Elem<T>::bits(x[i * D]) >> 31);  // all ones <=> dead row
-                    dead |= sgn & (1u << i);
-                    uint32_t dr = 0;
-#pragma unroll
-                    for (int c = 0; c < D; ++c) dr |= (uint32_t)Elem<T>::bits(x[i * D + c]) ^ pbits;
-                    diff |= dr & sgn;
-                }
-                lm = ~dead & ((N == 32) ? 0xffffffffu : ((1u << N) - 1u));
-                if (check) {
-                    chg = chg || (diff != 0);
-                    any_junk = __any_sync(0xffffffffu, diff != 0);
-                }
-            }
-            ls.cnt = __popc(lm);
-            if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
-            const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
-            // the gathered tiers scatter only live rows: dead rows that need it are rewritten first
-            auto prestore = [&]() {
-                if (mutate && !normalised) {
-                    if (any_junk) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) {
-#pragma unroll
-                            for (int c = 0; c < D; ++c) x[i * D + c] = ((lm >> i) & 1u) ? x[i * D + c] : padv;
-                        }
-                        store_game<T, W>(row, x);
-                    }
-                    normalised = true;
-                }
-            };
-            if (N > 2 && p.T == 1 && lmax <= 2) {  // the tail of a rollout driven step by step: ended games and two-point games only
-                prestore();
-                st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
-            } else if (N > 4 && lmax <= 4) {
-                prestore();
-                st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
-            } else if (N > 8 && lmax <= 8) {
-                prestore();
-                st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
-            } else if (N > 12 && lmax <= 12) {
-                if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
-                normalised = normalised || (W % 4 == 0);
-            } else if (N > 16 && lmax <= 16) {
-                if (W % 4 != 0) prestore();
-                st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
-                normalised = normalised || (W % 4 == 0);
-            } else {
-                st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed, chg);
-                normalised = true;
-            }
-        } while (st < p.T);
+        small_process_tile<T, N, D, POLICY>(p, ls, row, exceed, chg);
 
         if (ls.valid) {
             if (p.num_points) p.num_points[ls.g] = ls.cnt;
@@ -1112,6 +1143,9 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                 }
             }
         }
+        // the lanes wrote this stage with st.shared (results, scratch); the refill below is an async-proxy
+        // write into the same bytes: order the two proxies before lane 0 issues it
+        fence_async_smem();
         __syncwarp();
         if (lane == 0) {
             if constexpr (DELAYED_REFILL) {

@@ -62,7 +62,7 @@ class GameBatch:
 
     def __init__(self, points: torch.Tensor, *, semantics: str = "jax", reposition: bool = True,
                  discrete_host_action: bool = True, role: str = "host", initial_filter: bool = False,
-                 host_policy: Optional[str] = None, agent_policy: Optional[str] = None):
+                 host_policy: Optional[str] = None, agent_policy: Optional[str] = None, census: bool = True):
         if semantics not in ("jax", "torch"):
             raise ValueError("semantics must be 'jax' or 'torch'")
         if not points.is_cuda:
@@ -77,8 +77,13 @@ class GameBatch:
             (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
             self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]
         self.reposition = reposition
+        # The census (one byte per game, hk_step_census) lets a step skip the games at rest and order the others
+        # by live count.  It describes `self.points`: call reset_census() after writing into the tensor yourself.
+        fixed = self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]
+        self.census = _ops.new_census(self.points) if (census and not fixed) else None
         if initial_filter:  # generate_pts: newton -> (reposition) on the root states (util.py:385-392)
-            _ops.step(self.points, ops=C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0), inplace=True)
+            _ops.step(self.points, ops=C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0), inplace=True,
+                      census=self.census)
 
     @property
     def device(self):
@@ -88,8 +93,13 @@ class GameBatch:
              want_reward: bool = True):
         """One game-step in place; returns (done [B] bool, reward [B] f32 | None)."""
         r = _ops.step(self.points, host_action, axis, ops=self.ops, flags=self.flags, inplace=True, want_done=True,
-                      want_reward=want_reward)
+                      want_reward=want_reward, census=self.census)
         return r.done, r.reward
+
+    def reset_census(self) -> None:
+        """Forget what is known about the games (after `points` was written from outside)."""
+        if self.census is not None:
+            self.census.zero_()
 
     def rollout(self, host_actions: Optional[torch.Tensor] = None, axes: Optional[torch.Tensor] = None,
                 want_done: bool = False, want_reward: bool = False, want_length: bool = True,
@@ -99,6 +109,7 @@ class GameBatch:
         _, done, reward, dcount, length = _ops.rollout(self.points, host_actions, axes, ops=self.ops, flags=self.flags,
                                                        inplace=True, want_done=want_done, want_reward=want_reward,
                                                        want_done_count=True, want_length=want_length, steps=steps)
+        self.reset_census()  # the one-launch rollout does not keep it
         return done, reward, dcount, length
 
     def step_host(self, host_action_host: torch.Tensor, axis_host: torch.Tensor) -> int:
@@ -113,6 +124,7 @@ class GameBatch:
         self._ax_dev[0].copy_(axis_host, non_blocking=True)
         _, _, _, dcount, _ = _ops.rollout(self.points, self._ha_dev, self._ax_dev, ops=self.ops, flags=self.flags,
                                           inplace=True, want_done_count=True)
+        self.reset_census()
         return int(dcount.item())
 
     def dones(self):

@@ -96,9 +96,15 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
          padding_value: float = -1.0, inplace: bool = True, out: Optional[torch.Tensor] = None,
          write_state: bool = True, want_done: bool = False, want_reward: bool = False,
          want_num_points: bool = False, want_obs: bool = False, obs_coord=None,
-         exceed_flag: Optional[torch.Tensor] = None, value_threshold: float = 1e8) -> StepResult:
+         exceed_flag: Optional[torch.Tensor] = None, value_threshold: float = 1e8,
+         census: Optional[torch.Tensor] = None, done_count: Optional[torch.Tensor] = None) -> StepResult:
     """One fused game-step (hk_step).  `host_action` is an int32 [B] tensor of coordinate
-    bitmasks, or discrete ids when HK_F_ACT_DISCRETE is set; `axis` an int [B] tensor."""
+    bitmasks, or discrete ids when HK_F_ACT_DISCRETE is set; `axis` an int [B] tensor.
+
+    `census` (uint8 [B], in/out; see `new_census`) selects hk_step_census: the in-place step whose work
+    follows the games still in play (games at rest are not read, the others are ordered by live count).
+    Zero the bytes of any game you rewrite between calls.  `done_count` (int32 [1]) is incremented by the
+    number of finished games."""
     dt = _require_state(state)
     B, N, d = state.shape
     dev = state.device
@@ -130,6 +136,18 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
         obs = torch.empty((B, N * d + (d if oc is not None else 0)), dtype=torch.float32, device=dev)
     if exceed_flag is not None and (exceed_flag.dtype != torch.int32 or exceed_flag.device != dev):
         raise ValueError("exceed_flag must be an int32 tensor on the state's device")
+    if census is not None:
+        if census.dtype != torch.uint8 or census.shape != (B,) or census.device != dev or not census.is_contiguous():
+            raise ValueError("census must be a contiguous uint8 [B] tensor on the state's device")
+        if not (write_state and inplace) or want_obs:
+            raise ValueError("the census step runs in place and has no fused observation")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib().hk_step_census(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(reward), _ptr(npts), _ptr(census),
+                                      _ptr(done_count), _ptr(exceed_flag), B, N, d, dt, ops, flags, float(padding_value),
+                                      float(value_threshold), stream)
+        check(rc, "hk_step_census")
+        return StepResult(dst, None if done is None else done.view(torch.bool), reward, npts, None)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib().hk_step(_ptr(state), _ptr(dst), _ptr(ha), _ptr(ax), _ptr(done), _ptr(reward), _ptr(npts),
@@ -137,6 +155,11 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
                            float(value_threshold), stream)
     check(rc, "hk_step")
     return StepResult(dst, None if done is None else done.view(torch.bool), reward, npts, obs)
+
+
+def new_census(state: torch.Tensor) -> torch.Tensor:
+    """A zeroed census for `state` (uint8 [B], every game unknown); pass it to `step(..., census=)`."""
+    return torch.zeros(state.shape[0], dtype=torch.uint8, device=state.device)
 
 
 def rollout(state: torch.Tensor, host_actions: Optional[torch.Tensor], axes: Optional[torch.Tensor], *, ops: int,

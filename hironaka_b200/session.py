@@ -60,11 +60,13 @@ class HostSession:
         check(rc, "hk_session_step")
         return cnt.value if want_done_count else None
 
-    def rollout(self, host_actions: np.ndarray, axes: np.ndarray, ops: int, flags: int) -> np.ndarray:
+    def rollout(self, host_actions: np.ndarray, axes: np.ndarray, ops: int, flags: int,
+                done: Optional[np.ndarray] = None) -> np.ndarray:
         """T steps from host action streams [T, B] (int32, or uint8 with HK_F_ACT_U8): uploads are
         double-buffered against the running step, the finished-game count of every step is read
-        back; returns int32 [T].  Pass pinned arrays (e.g. torch.empty(..., pin_memory=True).numpy())
-        for full PCIe speed."""
+        back; returns int32 [T].  `done` (uint8 [T, B], caller-provided, ideally pinned) also receives
+        every step's per-game done flags, read back on a third stream.  Pass pinned arrays
+        (e.g. torch.empty(..., pin_memory=True).numpy()) for full PCIe speed."""
         packed = bool(flags & C.HK_F_ACT_PACKED)  # one uint8 per game-step: host action | axis << 5; `axes` unused
         want = np.uint8 if flags & (C.HK_F_ACT_U8 | C.HK_F_ACT_PACKED) else np.int32
         ha = np.ascontiguousarray(host_actions, dtype=want)
@@ -72,8 +74,11 @@ class HostSession:
         if ha.ndim != 2 or ha.shape[1] != self.B or (ax is not None and ax.shape != ha.shape):
             raise ValueError("host_actions and axes must be [T, B]")
         counts = np.zeros(ha.shape[0], dtype=np.int32)
-        check(lib().hk_session_rollout(self._h, ha.ctypes.data, None if ax is None else ax.ctypes.data, ha.shape[0],
-                                       counts.ctypes.data, ops, flags), "hk_session_rollout")
+        if done is not None and (done.dtype != np.uint8 or done.shape != ha.shape or not done.flags.c_contiguous):
+            raise ValueError("done must be a contiguous uint8 [T, B] array")
+        check(lib().hk_session_rollout_ex(self._h, ha.ctypes.data, None if ax is None else ax.ctypes.data, ha.shape[0],
+                                          counts.ctypes.data, None if done is None else done.ctypes.data, ops, flags),
+              "hk_session_rollout_ex")
         return counts
 
     @staticmethod

@@ -107,6 +107,9 @@ int hk_debug_force_generic(int on);
  * the thread-per-game kernel, off by default (measured: no gain); results do not depend on it. */
 int hk_debug_set_pdl(int on);
 
+/* Tuning hook: geometry of the census-scheduled kernel (0 = 4 warps x 2 stages, 1 = 8 warps x 1 stage). */
+int hk_debug_set_sched_geometry(int which);
+
 /* ---- the fused step ------------------------------------------------------------------
  * One launch = one game-step for B independent games:
  *   prev_done -> [shift] -> [reposition] -> [dedupe] -> [newton] -> [rescale] -> done / reward / num_points
@@ -134,6 +137,26 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
             uint8_t* done, float* reward, int32_t* num_points, float* obs, const int32_t* obs_coord,
             int32_t* exceed_flag, int64_t B, int32_t N, int32_t d, int32_t dtype, uint32_t ops,
             uint32_t flags, float padding_value, float value_threshold, void* stream);
+
+/* ---- the in-place step with a census ------------------------------------------------------
+ * The same step as hk_step with state_out == state_in, plus `census`: one byte per game that the library
+ * writes after every step and reads before the next one, so that a rollout's work follows the games still in
+ * play instead of the batch size.  A game at rest (no live row, or a lone point at the origin: the fixed point
+ * every ended game of a reposition rollout reaches, hironaka/src/_jax_ops.py:76-90,114-123; or any ended game
+ * under HK_F_FREEZE_ENDED without reposition / rescale, _torch_ops.py:92-93) is NOT READ: its done = 1,
+ * reward = 0 and num_points come from its census byte.  Games in play are ordered by their live-row count
+ * before they are processed (thread-per-game shapes), so that the 32 games a warp steps together are alike.
+ * Results are identical to hk_step's, bit for bit.
+ *   census [B] uint8, in/out.  0 = unknown (the game is read and counted): zero-fill before the first call
+ *          and ZERO THE BYTE OF ANY GAME YOU REWRITE between calls.  Other values belong to the library
+ *          (1..127: live rows of a game in play; 0x80 | rows | 2 * at_rest: ended game, dead rows normalised).
+ *   done_count [1] int32, nullable: incremented by the number of finished games after the step.
+ * Not available with a fused observation, the in-kernel players, out-of-place states or ops == 0
+ * (HK_ERR_UNSUPPORTED). */
+int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, float* reward,
+                   int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
+                   int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,
+                   void* stream);
 
 /* ---- per-op entry points (the reference's hironaka.src op surface) ---------------------
  * Each is one launch of the same kernel family with a single op selected. */
@@ -228,6 +251,11 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
  * compute_rho, hironaka/jax/jax_trainer.py:533-534).  One synchronisation at the end. */
 int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                        int32_t* done_count_host, uint32_t ops, uint32_t flags);
+/* The same with the per-game results of every step: done_host [T,B] uint8 (pinned recommended; nullable) receives
+ * each step's done flags, read back on a third stream while the next steps run.  The session keeps a census
+ * of its resident state (hk_step_census), so the steps of a long rollout cost what the games still in play cost. */
+int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                          int32_t* done_count_host, uint8_t* done_host, uint32_t ops, uint32_t flags);
 void* hk_session_state_ptr(hk_session* s); /* device pointer of the resident state (zero-copy interop) */
 void* hk_session_stream(hk_session* s);
 

@@ -147,19 +147,50 @@ def test_rho_from_counts():
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    """`bench.py --impl reference` is the CPU arm (oracle C port on the host cores): it must run
-    without a GPU and print one JSON line with the contract's keys."""
+    """`bench.py --impl reference` is the CPU arm — the unmodified reference from baseline/_ref when it is there
+    (kind "reference"), the oracle's C port otherwise (kind "port"): it must run without a GPU and print one
+    JSON line with the contract's keys."""
     import json
-    env = dict(os.environ, HK_BENCH_CPU_SAMPLE="4096")
+    from baseline import reference_arm as R
+    env = dict(os.environ, HK_BENCH_CPU_SAMPLE="4096", HK_BENCH_REF_SAMPLE="512")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
                           "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "game_steps_per_sec" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == ("reference" if R.available() else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("C2")
     for k in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data"):
         assert k in line
+
+
+def test_reference_arm_matches_the_oracle():
+    """Parity gate of the reference arm: what bench.py times as "the reference" — the
+    unmodified hironaka.core.TensorPoints from baseline/_ref playing the bench's own C2 inputs — gives, step by
+    step, the states, done flags and rewards of the oracle's torch flavour on the same inputs (the GPU arm is
+    held to the same oracle by tests/test_gpu_parity.py, and to this arm directly by
+    test_reference_arm_matches_the_gpu)."""
+    from baseline import reference_arm as R
+    if not R.available():
+        pytest.skip("baseline/_ref is not installed (baseline/install_ref.sh needs /root/reference)")
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import cport, hk_oracle as O
+    torch, TensorPoints, HostActionEncoder = R.import_reference()
+    B, T = 1024, 12
+    pts, ha, ax = bench.make_inputs(99, B, 1)
+    tp = R.root_states(TensorPoints, torch, pts[0], True)
+    o = cport.step(pts[0], None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+    assert np.array_equal(tp.points.numpy(), o.astype(np.float32))
+    rec = []
+    counts = R.play(tp, HostActionEncoder(3), torch, ha[0, :T], ax[0, :T], True, record=rec)
+    flags = O.F_NOOP_INVALID | O.F_FREEZE_ENDED | O.F_ACT_DISCRETE
+    for t in range(T):
+        o, od, orw, _ = cport.step(o, ha[0, t], ax[0, t], O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, flags)
+        assert np.array_equal(rec[t][0], o.astype(np.float32)), t
+        assert np.array_equal(rec[t][1], od.astype(bool)) and np.array_equal(rec[t][2], orw), t
+        assert counts[t] == int(od.sum())
 
 
 def test_policy_glue_of_functional():

@@ -592,6 +592,22 @@ def test_uint8_actions_and_session_rollout():
                                 C.HK_F_ACT_DISCRETE | (C.HK_F_ACT_U8 if mode == "u8" else 0))
             assert got.tolist() == counts and np.array_equal(s.get_state(), o), mode
             s.close()
+        # per-game done flags of every step read back on the third stream, several rollouts on one session
+        # (the session's census carries over from call to call and is reset with the state)
+        s = HostSession(x)
+        oo = x
+        for rep in range(3):
+            done = torch.empty((Tn, B), dtype=torch.uint8).pin_memory().numpy()
+            got = s.rollout(packed, None, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED, done=done)
+            for t in range(Tn):
+                oo, od, _, _ = cport.step(oo, ha[t], ax[t], op_bits, O.F_ACT_DISCRETE)
+                assert np.array_equal(done[t], od), (rep, t)
+                assert got[t] == int(od.sum()), (rep, t)
+            assert np.array_equal(s.get_state(), oo), rep
+            if rep == 1:  # a fresh state resets the census
+                s.set_state(x)
+                oo = x
+        s.close()
 
 
 def test_cuda_graph_capture_of_step():
@@ -617,3 +633,32 @@ def test_cuda_graph_capture_of_step():
         o = cport.step(o, ha.cpu().numpy(), ax.cpu().numpy(), op_bits, C.HK_F_ACT_DISCRETE)[0]
     torch.cuda.synchronize()
     assert eq(state, o) and eq(r.done, O.get_dones(o.astype(np.float32)))
+
+
+def test_reference_arm_matches_the_gpu():
+    """The unmodified reference (baseline/_ref, what `bench.py --impl reference` times) against the CUDA path on
+    the bench's own C2 inputs, bit for bit: states, done flags, rewards after every step.  The reference's torch
+    ops treat an invalid action as a no-op and freeze ended games (hironaka/src/_torch_ops.py:90-93), so the
+    kernel runs with those two flags here; the headline's JAX flavour is pinned by the JAX-source goldens."""
+    import sys
+    from baseline import reference_arm as R
+    if not R.available():
+        pytest.skip("baseline/_ref did not travel")
+    import bench
+    from hironaka_b200 import constants as C, ops
+    rtorch, TensorPoints, HostActionEncoder = R.import_reference()
+    B, Tn = 4096, 20
+    pts, ha, ax = bench.make_inputs(7, B, 1)
+    tp = R.root_states(TensorPoints, rtorch, pts[0], True)
+    rec = []
+    R.play(tp, HostActionEncoder(3), rtorch, ha[0, :Tn], ax[0, :Tn], True, record=rec)
+    g = T(pts[0])
+    census = ops.new_census(g)
+    root = C.HK_OP_NEWTON | C.HK_OP_REPOSITION
+    ops.step(g, ops=root, inplace=True, census=census)
+    flags = C.TORCH_SEMANTICS | C.HK_F_ACT_DISCRETE
+    for t in range(Tn):
+        r = ops.step(g, T(ha[0, t]), T(ax[0, t]), ops=C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, flags=flags,
+                     inplace=True, want_done=True, want_reward=True, census=census)
+        assert np.array_equal(g.cpu().numpy().astype(np.float32), rec[t][0]), t
+        assert np.array_equal(r.done.cpu().numpy(), rec[t][1]) and np.array_equal(r.reward.cpu().numpy(), rec[t][2]), t

@@ -703,3 +703,91 @@ def test_features_pack_borders(hb, family, N):
                           O.F_OBS_SORT_COORD0 | O.F_OBS_RESCALE):
                 got = run_step(hb, xv, None, None, 0, flags, want_obs=True)[4]
                 assert np.array_equal(got, cport.features(xv, flags)), (lo, hi, dtype, flags)
+
+
+# ---------------------------------------------------------------- the census step
+
+
+@pytest.mark.parametrize("shape", [(40003, 20, 3), (2500, 10, 3), (1111, 5, 3), (31, 20, 3), (3000, 64, 5), (700, 16, 4)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+@pytest.mark.parametrize("geometry", [0, 1])
+def test_census_step_equals_oracle(hb, shape, dtype, geometry):
+    """hk_step_census over whole rollouts: games at rest are answered from their census byte, games in play
+    are reordered by live count — state, done, reward, num_points and the finished count must equal the
+    oracle's after EVERY step, for both flavours, from starts with junk in dead rows, empty games and
+    lone points, with the caller rewriting games (and zeroing their census bytes) along the way."""
+    from hironaka_b200 import ops
+    from hironaka_b200._lib import lib
+    lib().hk_debug_set_sched_geometry(geometry)
+    B, N, d = shape
+    rng = np.random.default_rng(B + N + geometry)
+    T = 14
+    x0 = random_state(rng, B, N, d, max_value=9, dead_frac=0.45, dup_frac=0.1).astype(dtype)
+    junk = rng.random((B, N)) < 0.3
+    x0[(x0[:, :, 0] < 0) & junk] = -7
+    x0[::5] = -1
+    x0[1::5, 1:] = -1
+    x0[1::5, 0] = np.abs(x0[1::5, 0])
+    ncls = 2 ** d - d - 1
+    for ops_bits, flags in ((O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE),
+                            (O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS | O.F_ACT_DISCRETE | O.F_ROLE_AGENT),
+                            (O.OP_SHIFT | O.OP_NEWTON, O.F_ACT_DISCRETE)):
+        o = x0.copy()
+        g = dev(x0)
+        census = ops.new_census(g)
+        for t in range(T):
+            ha = rng.integers(0, ncls, B).astype(np.int32)
+            ax = rng.integers(0, d, B).astype(np.int32)
+            o, od, orw, onp = cport.step(o, ha, ax, ops_bits, flags)
+            dc = torch.zeros(1, dtype=torch.int32, device="cuda")
+            r = ops.step(g, dev(ha), dev(ax), ops=ops_bits, flags=flags, inplace=True, want_done=True, want_reward=True,
+                         want_num_points=True, census=census, done_count=dc)
+            assert np.array_equal(g.cpu().numpy(), o), (ops_bits, flags, t)
+            assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)), (ops_bits, flags, t)
+            assert np.array_equal(r.reward.cpu().numpy().view(np.int32), orw.view(np.int32)), (ops_bits, flags, t)
+            assert np.array_equal(r.num_points.cpu().numpy(), onp), (ops_bits, flags, t)
+            assert int(dc.item()) == int(od.sum()), (ops_bits, flags, t)
+            if t % 4 == 2:  # the caller rewrites some games and zeroes their census bytes
+                idx = rng.permutation(B)[:max(1, B // 30)]
+                fresh = random_state(rng, len(idx), N, d, max_value=7, dead_frac=0.3).astype(dtype)
+                fresh[(fresh[:, :, 0] < 0) & (rng.random((len(idx), N)) < 0.5)] = -3
+                o[idx] = fresh
+                ti = torch.from_numpy(idx).cuda()
+                g[ti] = dev(fresh)
+                census[ti] = 0
+        c = census.cpu().numpy()
+        live = (o[:, :, 0] >= 0).sum(1)
+        known = c != 0
+        assert np.array_equal(np.where(c[known] & 0x80, c[known] & 1, c[known]), live[known]), "census counts"
+        if hb.ops.kernel_class(N, d) == 1:
+            assert known.all()
+    lib().hk_debug_set_sched_geometry(0)
+
+
+def test_census_step_baseline_size(hb):
+    """C2 at full size (1 Mi games, 20 steps) through hk_step_census against the C port, root filter included;
+    in a reposition rollout every finished game ends at rest, so the last steps read almost nothing."""
+    from hironaka_b200 import ops
+    B, N, d, T = 1 << 20, 20, 3, 20
+    rng = np.random.default_rng(77)
+    x = rng.integers(0, 20, size=(B, N, d)).astype(np.int32)
+    ha = rng.integers(0, 4, size=(T, B)).astype(np.int32)
+    ax = rng.integers(0, d, size=(T, B)).astype(np.int32)
+    step_ops = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    o = cport.step(x, None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+    g = dev(x)
+    census = ops.new_census(g)
+    ops.step(g, ops=O.OP_NEWTON | O.OP_REPOSITION, inplace=True, census=census)
+    assert np.array_equal(g.cpu().numpy(), o)
+    for t in range(T):
+        o, od, orw, _ = cport.step(o, ha[t], ax[t], step_ops, O.F_ACT_DISCRETE)
+        r = ops.step(g, dev(ha[t]), dev(ax[t]), ops=step_ops, flags=O.F_ACT_DISCRETE, inplace=True, want_done=True,
+                     want_reward=True, census=census)
+        assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)), t
+        assert np.array_equal(r.reward.cpu().numpy(), orw), t
+        if t in (0, 1, 7, T - 1):
+            assert np.array_equal(g.cpu().numpy(), o), t
+    c = census.cpu().numpy()
+    at_rest = (c & 0x82) == 0x82
+    assert np.array_equal(at_rest, od.astype(bool)) and at_rest.mean() > 0.99

@@ -264,7 +264,7 @@ def run_gpu_arm(args):
 
     def launch_step(r, t):
         st = batches[r].points
-        rc = lib.hk_step_census(st.data_ptr(), ha_d[r, t].data_ptr(), ax_d[r, t].data_ptr(), done.data_ptr(),
+        rc = lib.hk_step_census(st.data_ptr(), ha_d[r, t].data_ptr(), ax_d[r, t].data_ptr(), done.data_ptr(), None,
                                 reward.data_ptr(), None, batches[r].census.data_ptr(), None, None, B, N_POINTS, DIM,
                                 C.HK_DTYPE_I32, op_step, flags, -1.0, 1e8, stream)
         if rc != 0:
@@ -697,16 +697,19 @@ def measure_secondary(torch, lib, C, dev):
 
 
 def measure_e2e(torch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist, repeats: int = 5):
-    """The same K steps through the host-buffer C-ABI (hk_session_rollout_ex via HostSession.rollout): the state
-    of each rollout batch is resident; EVERY step copies that step's actions from pinned host memory (one
-    packed byte per game-step) and brings back the step's per-game done flags (one byte per game, pinned) and
-    the finished-game count.  Three streams inside the session: uploads, steps, read-backs.  The K steps are
-    repeated `repeats` times from the same start and the MEDIAN is reported (a single ~1-2 ms window is noisy)."""
+    """The same K steps through the host-buffer C-ABI (hk_session_rollout_bits / _ex via HostSession.rollout): the
+    state of each rollout batch is resident; EVERY step copies that step's actions from pinned host memory and
+    brings back the step's per-game done flags and the finished-game count.  Three streams inside the session
+    (uploads, steps, read-backs); a repeated call replays as one CUDA graph.  The K steps are repeated
+    `repeats` times from the same start and the MEDIAN is reported (a single ~1 ms window is noisy).
+    Headline: the compact transport — two games' actions per byte up (HK_F_ACT_NIBBLE), the done flags as a bit
+    mask down.  `bytes_variant`: one action byte per game up (HK_F_ACT_PACKED), one done byte per game down."""
     from hironaka_b200 import HostSession, constants as C
     op_step = C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON
     root_ops = C.HK_OP_NEWTON | C.HK_OP_REPOSITION
-    flags = C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED
-    # one byte per game-step: host-action id | axis << 5 (HK_F_ACT_PACKED), prepared like the other synthetic inputs
+    nwords = (B + 31) // 32
+    nib_pin = torch.from_numpy(HostSession.pack_actions_nibble(ha[:n_roll], ax[:n_roll])).pin_memory()
+    bits_pin = torch.empty((n_roll, T_ROLLOUT, nwords), dtype=torch.int32).pin_memory()
     ha_pin = torch.from_numpy(HostSession.pack_actions(ha[:n_roll], ax[:n_roll])).pin_memory()
     done_pin = torch.empty((n_roll, T_ROLLOUT, B), dtype=torch.uint8).pin_memory()
     sessions, starts = [], []
@@ -715,11 +718,15 @@ def measure_e2e(torch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist, rep
         s.step(None, None, root_ops, 0)  # root filter (generate_pts), untimed
         sessions.append(s)
         starts.append(s.get_state())
-    warm = HostSession(pts[0], device=dev.index)
-    warm.rollout(ha_pin[0, :3].numpy(), None, op_step, flags, done=done_pin[0, :3].numpy())
-    warm.close()
 
-    def one_pass():
+    def rollout(r, T, compact):
+        if compact:
+            return sessions[r].rollout(nib_pin[r, :T].numpy(), None, op_step, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_NIBBLE,
+                                       done_bits=bits_pin[r, :T].numpy().view(np.uint32))
+        return sessions[r].rollout(ha_pin[r, :T].numpy(), None, op_step, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED,
+                                   done=done_pin[r, :T].numpy())
+
+    def one_pass(compact):
         barrier()
         t0 = time.perf_counter()
         total_done, done_steps, i = 0, 0, 0
@@ -728,36 +735,48 @@ def measure_e2e(torch, dev, B, K, pts, ha, ax, n_roll, barrier, world, dist, rep
             if i >= n_roll:  # reuse of a batch beyond K = 200 (charged to the timed region)
                 sessions[r].set_state(starts[r])
             T = min(T_ROLLOUT, K - done_steps)
-            counts = sessions[r].rollout(ha_pin[r, :T].numpy(), None, op_step, flags, done=done_pin[r, :T].numpy())
+            counts = rollout(r, T, compact)
             total_done += int(counts.sum())
             done_steps += T
             i += 1
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3  # host-blocking API: wall clock is the device time plus the copies
-        check = int(done_pin[(i - 1) % n_roll, T - 1].sum())  # the flags of the last step did reach the host
+        r = (i - 1) % n_roll  # the flags of the last step did reach the host
+        check = int(HostSession.unpack_done_bits(bits_pin[r, T - 1].numpy().view(np.uint32), B).sum()) if compact \
+            else int(done_pin[r, T - 1].sum())
         return ms, total_done, check, int(counts[-1])
 
-    times, total_done = [], 0
-    for rep in range(repeats):
-        if rep:  # back to the same start; the root filter is replayed (idempotent) so that the census is filled again
-            for r in range(n_roll):
+    def measure(compact):
+        times, total_done = [], 0
+        for rep in range(repeats + 1):  # (the first pass runs eagerly and is not counted: graphs are captured on the second)
+            for r in range(n_roll):  # back to the same start; the root filter is replayed (idempotent) to fill the census
                 sessions[r].set_state(starts[r])
                 sessions[r].step(None, None, root_ops, 0)
-        ms, total_done, check, last = one_pass()
-        assert check == last, (check, last)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        times.append(ms)
+            ms, total_done, check, last = one_pass(compact)
+            assert check == last, (check, last)
+            if world > 1:
+                tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            if rep:
+                times.append(ms)
+        return float(np.median(times)), times, total_done
+
+    ms, times, total_done = measure(True)
+    ms_b, times_b, _ = measure(False)
     for s in sessions:
         s.close()
-    ms = float(np.median(times))
-    return {"value": B * world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B, "d2h_bytes_per_step": B + 4,
-            "ms_per_step": ms / K, "repeats": repeats, "ms_per_step_all": [round(t / K, 5) for t in times],
-            "api": "hk_session_rollout_ex (HostSession.rollout): per step H2D of one packed byte per game (host-action id | "
-                   "axis << 5, HK_F_ACT_PACKED) from pinned memory, one hk_step_census launch, D2H of the per-game done "
-                   "flags (1 byte per game, pinned) and of the finished-game count; median of the repeats",
+    return {"value": B * world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (B + 1) // 2,
+            "d2h_bytes_per_step": nwords * 4 + 4, "ms_per_step": ms / K, "repeats": repeats,
+            "ms_per_step_all": [round(t / K, 5) for t in times],
+            "api": "hk_session_rollout_bits (HostSession.rollout): per step H2D of half a byte per game (two games' discrete "
+                   "host id | axis << 2 per byte, HK_F_ACT_NIBBLE) from pinned memory, one hk_step_census launch, D2H of "
+                   "the per-game done flags as a bit mask (pinned) and of the finished-game count; CUDA-graph replay; "
+                   "median of the repeats after one untimed eager pass",
+            "bytes_variant": {"value": B * world * K / (ms_b * 1e-3), "ms_per_step": ms_b / K, "h2d_bytes_per_step": B,
+                              "d2h_bytes_per_step": B + 4, "ms_per_step_all": [round(t / K, 5) for t in times_b],
+                              "api": "hk_session_rollout_ex: one packed action byte per game up (HK_F_ACT_PACKED), one "
+                                     "done byte per game down"},
             "checksum_done": int(total_done)}
 
 

@@ -11,7 +11,8 @@ import os
 from . import constants as C
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libhironaka_b200.so")
+# HIRONAKA_B200_LIB points the binding at another build of the same library (tuning variants, tools/)
+LIB_PATH = os.environ.get("HIRONAKA_B200_LIB") or os.path.join(_HERE, "_lib", "libhironaka_b200.so")
 _lib = None
 
 _p = ctypes.c_void_p
@@ -25,8 +26,9 @@ SIGNATURES = {
     "hk_debug_force_generic": (ctypes.c_int, [ctypes.c_int]),
     "hk_debug_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "hk_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
-    "hk_step_census": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
+    "hk_step_census": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
     "hk_debug_set_sched_geometry": (ctypes.c_int, [ctypes.c_int]),
+    "hk_debug_set_session_graphs": (ctypes.c_int, [ctypes.c_int]),
     "hk_shift": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_reposition": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
     "hk_newton_polytope": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _p]),
@@ -47,6 +49,7 @@ SIGNATURES = {
     "hk_session_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _u32, _u32]),
     "hk_session_rollout": (ctypes.c_int, [_p, _p, _p, _i32, _p, _u32, _u32]),
     "hk_session_rollout_ex": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _u32, _u32]),
+    "hk_session_rollout_bits": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _u32, _u32]),
     "hk_session_state_ptr": (_p, [_p]),
     "hk_session_stream": (_p, [_p]),
 }

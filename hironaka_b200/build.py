@@ -81,5 +81,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_variant(name: str, defines, sources=None) -> str:
+    """A tuning variant of the library: every source compiled with extra -D macros into
+    hironaka_b200/_lib/variants/<name>/ (load it with HIRONAKA_B200_LIB=<path>)."""
+    vdir = os.path.join(OUT_DIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = nvcc_path()
+    flags = [f"-D{d}" for d in defines]
+
+    def one(src):
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc] + COMPILE_FLAGS + flags + ["-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        return obj
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+        objs = list(pool.map(one, SOURCES))
+    out = os.path.join(vdir, "libhironaka_b200.so")
+    r = subprocess.run([nvcc] + LINK_FLAGS + ["-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    for o in objs:
+        os.remove(o)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:  # python -m hironaka_b200.build --variant NAME MACRO=VALUE ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

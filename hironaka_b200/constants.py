@@ -37,6 +37,7 @@ HK_F_OBS_SORT_LEX_FIRST = 1 << 12
 HK_F_STORE_ALL = 1 << 13
 HK_F_ACT_PACKED = 1 << 14
 HK_F_RESCALE_EPS = 1 << 15
+HK_F_ACT_NIBBLE = 1 << 16
 
 # the two semantics of the reference
 TORCH_SEMANTICS = HK_F_NOOP_INVALID | HK_F_FREEZE_ENDED  # hironaka/src/_torch_ops.py:90-93

@@ -69,8 +69,11 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
         const bool agent_fixed = p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
         if ((p.flags & HK_F_HOST_ALL_COORD) && (p.flags & HK_F_HOST_ZEILLINGER)) return HK_ERR_BAD_ARG;
         if ((p.flags & HK_F_AGENT_FIRST) && (p.flags & HK_F_AGENT_LAST)) return HK_ERR_BAD_ARG;
-        const bool packed = p.flags & HK_F_ACT_PACKED;
+        const bool nibble = p.flags & HK_F_ACT_NIBBLE;
+        const bool packed = (p.flags & HK_F_ACT_PACKED) || nibble;
+        if ((p.flags & HK_F_ACT_PACKED) && nibble) return HK_ERR_BAD_ARG;
         if (packed && (host_fixed || agent_fixed || p.d > 5)) return HK_ERR_BAD_ARG;
+        if (nibble && (p.d > 3 || !(p.flags & HK_F_ACT_DISCRETE))) return HK_ERR_BAD_ARG;
         if (host_fixed) p.host_action = nullptr;
         if (agent_fixed || packed) p.axis = nullptr;
         if ((p.ops & HK_OP_SHIFT) &&
@@ -89,12 +92,17 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     const bool obs = p.obs != nullptr;
+    if (p.done_bits && !p.census) return HK_ERR_UNSUPPORTED;  // the bit mask is an output of the census path
     if (p.census) {
         // the census path: in-place single steps without fused observation or in-kernel players
         const bool policy = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
         if (p.out != p.in || p.T != 1 || obs || policy || p.host_out || p.ops == 0) return HK_ERR_UNSUPPORTED;
         if (hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE))
             return dtype == HK_DTYPE_I32 ? hk::launch_sched_i32(p, dev, stream) : hk::launch_sched_f32(p, dev, stream);
+        if (p.done_bits) {  // the warp-per-game kernel ORs the bits in, one game at a time
+            e = cudaMemsetAsync(p.done_bits, 0, (size_t)((p.B + 31) / 32) * 4, stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         return dtype == HK_DTYPE_I32 ? hk::launch_generic_i32(p, false, dev, stream) : hk::launch_generic_f32(p, false, dev, stream);
     }
     // remove_repeated alone is not on the step path: it runs on the warp-per-game kernel for every shape
@@ -119,6 +127,7 @@ StepParams make_params(const void* in, void* out, long long B, int N, int d, flo
 }
 
 std::atomic<int> g_force_generic{0};
+std::atomic<int> g_no_session_graphs{0};  // test / tuning hook (hk_debug_set_session_graphs)
 
 }  // namespace
 
@@ -159,6 +168,12 @@ int hk_debug_set_sched_geometry(int which) {
     return HK_OK;
 }
 
+// test / tuning hook: host-buffer rollouts replayed as CUDA graphs (on by default)
+int hk_debug_set_session_graphs(int on) {
+    g_no_session_graphs.store(on ? 0 : 1);
+    return HK_OK;
+}
+
 // test hook: route small shapes through the generic warp-per-game kernel as well
 int hk_debug_force_generic(int on) {
     g_force_generic.store(on ? 1 : 0);
@@ -184,8 +199,8 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
     return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
 }
 
-int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, float* reward,
-                   int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
+int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, uint32_t* done_bits,
+                   float* reward, int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
                    int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,
                    void* stream) {
     if (census == nullptr || state == nullptr) return HK_ERR_BAD_ARG;
@@ -193,6 +208,7 @@ int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis,
     p.host_action = host_action;
     p.axis = axis;
     p.done = done;
+    p.done_bits = done_bits;
     p.reward = reward;
     p.num_points = num_points;
     p.census = census;
@@ -399,10 +415,48 @@ struct hk_session {
     int32_t* counts_pinned; // pinned host mirror: a D2H copy into pageable memory would block the host every step
     int counts_cap;
     uint8_t* done;         // two slots of B bytes (double buffer for the per-step read-back of hk_session_rollout_ex)
+    uint32_t* done_bits;   // two slots of ceil(B/32) words (hk_session_rollout_bits)
     float* reward;
     int32_t* done_count;
     uint8_t* census;       // [B] census of the resident state (hk_step_census); zeroed whenever the state is set
+    // hk_session_rollout_ex replayed as a CUDA graph: the second call with the same arguments captures the
+    // three-stream schedule once, later calls launch it (a rollout is ~10 API calls per step otherwise, and the
+    // steps of a census rollout are shorter than that)
+    cudaEvent_t fork, join_copy, join_back;
+    cudaGraphExec_t rollout_exec;
+    struct RolloutKey {
+        const void* ha;
+        const void* ax;
+        int32_t* dc;
+        uint8_t* done;
+        uint32_t* bits;
+        int32_t T;
+        uint32_t ops, flags;
+        int force_generic;
+    } last_key, exec_key;
 };
+
+// page-locked host memory?  (copies from pageable memory are staged by the driver and cannot be captured)
+static bool is_pinned(const void* ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static bool same_key(const hk_session::RolloutKey& a, const hk_session::RolloutKey& b) {
+    return a.ha == b.ha && a.ax == b.ax && a.dc == b.dc && a.done == b.done && a.bits == b.bits && a.T == b.T && a.ops == b.ops &&
+           a.flags == b.flags && a.force_generic == b.force_generic;
+}
+
+// bytes of one step's action array of B games under the action-format flags
+static size_t action_bytes(long long B, uint32_t flags) {
+    if (flags & HK_F_ACT_NIBBLE) return (size_t)((B + 1) / 2);
+    return (size_t)B * ((flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4);
+}
 
 // the census step serves in-place single steps without fused observation or in-kernel players
 static bool census_eligible(uint32_t ops, uint32_t flags) {
@@ -451,10 +505,14 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->freed[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->drained[i], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->join_copy, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->join_back, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->state, (size_t)B * N * d * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->host_action, (size_t)B * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_bits, (size_t)((B + 31) / 32) * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->census, (size_t)B);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->census, 0, (size_t)B, s->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->reward, (size_t)B * 4);
@@ -480,6 +538,7 @@ int hk_session_destroy(hk_session* s) {
     cudaFree(s->host_action);
     cudaFree(s->axis);
     cudaFree(s->done);
+    cudaFree(s->done_bits);
     cudaFree(s->census);
     cudaFree(s->reward);
     cudaFree(s->done_count);
@@ -490,6 +549,10 @@ int hk_session_destroy(hk_session* s) {
         if (s->freed[i]) cudaEventDestroy(s->freed[i]);
         if (s->drained[i]) cudaEventDestroy(s->drained[i]);
     }
+    if (s->rollout_exec) cudaGraphExecDestroy(s->rollout_exec);
+    if (s->fork) cudaEventDestroy(s->fork);
+    if (s->join_copy) cudaEventDestroy(s->join_copy);
+    if (s->join_back) cudaEventDestroy(s->join_back);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->back_stream) cudaStreamDestroy(s->back_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -518,8 +581,8 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
                     float* reward_host, int32_t* done_count_host, uint32_t ops, uint32_t flags) {
     if (!s) return HK_ERR_BAD_ARG;
     DeviceGuard guard_(s->device);
-    const bool packed = flags & HK_F_ACT_PACKED;
-    const size_t abytes = (size_t)s->B * ((flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4);
+    const bool packed = flags & (HK_F_ACT_PACKED | HK_F_ACT_NIBBLE);
+    const size_t abytes = action_bytes(s->B, flags);
     if ((ops & HK_OP_SHIFT) && host_action_host)
         HK_CUDA(cudaMemcpyAsync(s->host_action, host_action_host, abytes, cudaMemcpyHostToDevice, s->stream));
     if ((ops & HK_OP_SHIFT) && axis_host && !packed)
@@ -546,25 +609,19 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
     return HK_OK;
 }
 
-int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
-                          int32_t* done_count_host, uint8_t* done_host, uint32_t ops, uint32_t flags) {
-    const bool packed = flags & HK_F_ACT_PACKED;
-    if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || (!axis_host && !packed)) return HK_ERR_BAD_ARG;
-    DeviceGuard guard_(s->device);
-    if (s->counts_cap < T) {
-        cudaFree(s->counts);
-        if (s->counts_pinned) cudaFreeHost(s->counts_pinned);
-        s->counts = nullptr;
-        s->counts_pinned = nullptr;
-        s->counts_cap = 0;
-        HK_CUDA(cudaMalloc((void**)&s->counts, (size_t)T * 4));
-        HK_CUDA(cudaMallocHost((void**)&s->counts_pinned, (size_t)T * 4));
-        s->counts_cap = T;
-    }
-    const size_t esz = (flags & (HK_F_ACT_U8 | HK_F_ACT_PACKED)) ? 1 : 4;
-    const size_t abytes = (size_t)s->B * esz;
+// the three-stream schedule of one rollout, enqueued (or captured: every call below is capturable)
+static int enqueue_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                           int32_t* done_count_host, uint8_t* done_host, uint32_t* bits_host, uint32_t ops, uint32_t flags,
+                           int force_generic) {
+    const bool packed = flags & (HK_F_ACT_PACKED | HK_F_ACT_NIBBLE);
+    const size_t abytes = action_bytes(s->B, flags);
+    const size_t bwords = (size_t)((s->B + 31) / 32);
     const bool use_census = census_eligible(ops, flags);
     HK_CUDA(cudaMemsetAsync(s->counts, 0, (size_t)T * 4, s->stream));
+    // uploads and read-backs branch off the step stream here and join it again at the end
+    HK_CUDA(cudaEventRecord(s->fork, s->stream));
+    HK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->fork, 0));
+    HK_CUDA(cudaStreamWaitEvent(s->back_stream, s->fork, 0));
     // Three streams: uploads (copy_stream), steps (stream), read-backs (back_stream).  Step t uses slot t & 1 of
     // the action and done buffers; the upload of step t waits until step t - 2 has run (freed), the read-back of
     // step t waits for step t, and step t + 2 waits until that read-back has drained the slot (drained).
@@ -575,6 +632,9 @@ int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const voi
             HK_CUDA(cudaMemcpyAsync(s->counts_pinned + t, s->counts + t, 4, cudaMemcpyDeviceToHost, s->back_stream));
         if (done_host)
             HK_CUDA(cudaMemcpyAsync(done_host + (size_t)t * s->B, s->done + (size_t)slot * s->B, (size_t)s->B,
+                                    cudaMemcpyDeviceToHost, s->back_stream));
+        if (bits_host)
+            HK_CUDA(cudaMemcpyAsync(bits_host + (size_t)t * bwords, s->done_bits + (size_t)slot * bwords, bwords * 4,
                                     cudaMemcpyDeviceToHost, s->back_stream));
         HK_CUDA(cudaEventRecord(s->drained[slot], s->back_stream));
         return HK_OK;
@@ -595,16 +655,17 @@ int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const voi
                                     s->copy_stream));
         HK_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
         HK_CUDA(cudaStreamWaitEvent(s->stream, s->ready[slot], 0));
-        if (t >= 2 && done_host) HK_CUDA(cudaStreamWaitEvent(s->stream, s->drained[slot], 0));
+        if (t >= 2 && (done_host || bits_host)) HK_CUDA(cudaStreamWaitEvent(s->stream, s->drained[slot], 0));
         StepParams p = make_params(s->state, s->state, s->B, s->N, s->d, s->pad);
         p.host_action = ha;
         p.axis = packed ? nullptr : ax;
         p.done_count = s->counts + t;
         p.done = done_host ? s->done + (size_t)slot * s->B : nullptr;
+        p.done_bits = bits_host ? s->done_bits + (size_t)slot * bwords : nullptr;
         p.census = use_census ? s->census : nullptr;
         p.ops = ops;
         p.flags = flags;
-        int rc = run(p, s->dtype, g_force_generic.load(), s->stream);
+        int rc = run(p, s->dtype, force_generic, s->stream);
         if (rc != HK_OK) return rc;
         HK_CUDA(cudaEventRecord(s->freed[slot], s->stream));
     }
@@ -613,16 +674,87 @@ int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const voi
         int rb = read_back(t);
         if (rb != HK_OK) return rb;
     }
-    HK_CUDA(cudaStreamSynchronize(s->stream));
-    HK_CUDA(cudaStreamSynchronize(s->copy_stream));
-    HK_CUDA(cudaStreamSynchronize(s->back_stream));
+    HK_CUDA(cudaEventRecord(s->join_copy, s->copy_stream));
+    HK_CUDA(cudaEventRecord(s->join_back, s->back_stream));
+    HK_CUDA(cudaStreamWaitEvent(s->stream, s->join_copy, 0));
+    HK_CUDA(cudaStreamWaitEvent(s->stream, s->join_back, 0));
+    return HK_OK;
+}
+
+static int session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                           int32_t* done_count_host, uint8_t* done_host, uint32_t* bits_host, uint32_t ops, uint32_t flags) {
+    const bool packed = flags & (HK_F_ACT_PACKED | HK_F_ACT_NIBBLE);
+    if (!s || T < 1 || !(ops & HK_OP_SHIFT) || !host_action_host || (!axis_host && !packed)) return HK_ERR_BAD_ARG;
+    if (bits_host && !census_eligible(ops, flags)) return HK_ERR_UNSUPPORTED;
+    DeviceGuard guard_(s->device);
+    if (s->counts_cap < T) {
+        if (s->rollout_exec) {  // the graph holds the old buffers
+            cudaGraphExecDestroy(s->rollout_exec);
+            s->rollout_exec = nullptr;
+        }
+        cudaFree(s->counts);
+        if (s->counts_pinned) cudaFreeHost(s->counts_pinned);
+        s->counts = nullptr;
+        s->counts_pinned = nullptr;
+        s->counts_cap = 0;
+        HK_CUDA(cudaMalloc((void**)&s->counts, (size_t)T * 4));
+        HK_CUDA(cudaMallocHost((void**)&s->counts_pinned, (size_t)T * 4));
+        s->counts_cap = T;
+    }
+    const int fg = g_force_generic.load();
+    const hk_session::RolloutKey key = {host_action_host, axis_host, done_count_host, done_host, bits_host, T, ops, flags, fg};
+    int rc = HK_OK;
+    if (s->rollout_exec && same_key(key, s->exec_key)) {
+        HK_CUDA(cudaGraphLaunch(s->rollout_exec, s->stream));
+    } else if (same_key(key, s->last_key) && !g_no_session_graphs.load() && is_pinned(host_action_host) &&
+               is_pinned(axis_host) && is_pinned(done_host) && is_pinned(bits_host)) {
+        // second call with these arguments (the first ran eagerly, so every kernel is set up): capture and keep
+        if (s->rollout_exec) {
+            cudaGraphExecDestroy(s->rollout_exec);
+            s->rollout_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        HK_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_rollout(s, host_action_host, axis_host, T, done_count_host, done_host, bits_host, ops, flags, fg);
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc == HK_OK && e != cudaSuccess) rc = (int)e;
+        if (rc == HK_OK) {
+            e = cudaGraphInstantiate(&s->rollout_exec, graph, 0);
+            if (e != cudaSuccess) {
+                s->rollout_exec = nullptr;
+                rc = (int)e;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != HK_OK) {
+            cudaGetLastError();
+            return rc;
+        }
+        s->exec_key = key;
+        HK_CUDA(cudaGraphLaunch(s->rollout_exec, s->stream));
+    } else {
+        rc = enqueue_rollout(s, host_action_host, axis_host, T, done_count_host, done_host, bits_host, ops, flags, fg);
+        if (rc != HK_OK) return rc;
+    }
+    s->last_key = key;
+    HK_CUDA(cudaStreamSynchronize(s->stream));  // (the other two streams were joined into this one)
     if (done_count_host) memcpy(done_count_host, s->counts_pinned, (size_t)T * 4);
     return HK_OK;
 }
 
+int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                          int32_t* done_count_host, uint8_t* done_host, uint32_t ops, uint32_t flags) {
+    return session_rollout(s, host_action_host, axis_host, T, done_count_host, done_host, nullptr, ops, flags);
+}
+
+int hk_session_rollout_bits(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                            int32_t* done_count_host, uint32_t* done_bits_host, uint32_t ops, uint32_t flags) {
+    return session_rollout(s, host_action_host, axis_host, T, done_count_host, nullptr, done_bits_host, ops, flags);
+}
+
 int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                        int32_t* done_count_host, uint32_t ops, uint32_t flags) {
-    return hk_session_rollout_ex(s, host_action_host, axis_host, T, done_count_host, nullptr, ops, flags);
+    return session_rollout(s, host_action_host, axis_host, T, done_count_host, nullptr, nullptr, ops, flags);
 }
 
 void* hk_session_state_ptr(hk_session* s) { return s ? s->state : nullptr; }

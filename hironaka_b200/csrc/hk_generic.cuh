@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     if (p.done) p.done[g] = 1;
                     if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
                     if (p.num_points) p.num_points[g] = (int32_t)(cvg & 1u);
+                    if (p.done_bits) atomicOr(p.done_bits + (g >> 5), 1u << (g & 31));
                 }
                 if (p.done_count) count_done(0);
                 continue;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
                 if (p.num_points) p.num_points[g] = cnt;
                 if (p.length) p.length[g] = 0;
+                if (CENSUS && p.done_bits) atomicOr(p.done_bits + (g >> 5), 1u << (g & 31));
             }
             if (p.done_count) count_done(0);
             if (use_census) {  // (dead rows are normalised by now: kops != 0 on the census path)
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 const bool dn = cur < 2;
                 if (lane == 0) {
                     if (p.done) p.done[(long long)st * p.B + g] = dn ? 1 : 0;
+                    if (CENSUS && p.done_bits && dn) atomicOr(p.done_bits + (g >> 5), 1u << (g & 31));
                     if (p.reward) {
                         const float rw = (dn && !prev_done) ? 1.0f : 0.0f;
                         p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;
@@ -800,6 +803,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             const bool dn = cnt < 2;
             if (lane == 0) {
                 if (p.done) p.done[(long long)st * p.B + g] = dn ? 1 : 0;
+                if (CENSUS && p.done_bits && dn) atomicOr(p.done_bits + (g >> 5), 1u << (g & 31));
                 if (p.reward) {
                     float rw = (dn && !prev_done) ? 1.0f : 0.0f;
                     p.reward[(long long)st * p.B + g] = (kflags & HK_F_ROLE_AGENT) ? -rw : rw;

@@ -24,6 +24,9 @@
 namespace hk {
 
 constexpr int SCHED_ROUND_TILES = 32;  // tiles (of 32 games) a warp schedules together
+#ifndef SCHED_TILE_GROUP
+#define SCHED_TILE_GROUP 0  // 0: a warp owns one contiguous run of tiles; G > 0: runs of G tiles, dealt round-robin to the warps
+#endif
 #ifndef SCHED_NATURAL_NUM
 #define SCHED_NATURAL_NUM 1  // a round is stepped tile by tile in natural order while at least NUM / DEN of
 #define SCHED_NATURAL_DEN 2  // its games are in play (tools/time_census.py)
@@ -91,43 +94,75 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
 
     // A warp owns a CONTIGUOUS run of tiles (its games share DRAM pages when they are gathered one by one),
     // scheduled in rounds of SCHED_ROUND_TILES.
+#if SCHED_TILE_GROUP == 0
     const long long tpw = (ntiles + nw - 1) / nw;
     const long long t_begin = gw * tpw;
     const long long t_end = (t_begin + tpw < ntiles) ? (t_begin + tpw) : ntiles;
-    for (long long t0 = t_begin; t0 < t_end; t0 += SCHED_ROUND_TILES) {
+    auto tile_of = [&](long long j) -> long long { return t_begin + j; };  // the warp's j-th tile
+#else
+    constexpr int TG = SCHED_TILE_GROUP;
+    const long long t_end = ntiles;
+    auto tile_of = [&](long long j) -> long long { return ((j / TG) * nw + gw) * TG + (j % TG); };
+#endif
+    for (long long j0 = 0; tile_of(j0) < t_end; j0 += SCHED_ROUND_TILES) {
         // ---- census of this round's tiles: outputs of the games at rest, class bytes of the others ----
-        const int nk = (int)((t_end - t0 < SCHED_ROUND_TILES) ? (t_end - t0) : SCHED_ROUND_TILES);
+#if SCHED_TILE_GROUP == 0
+        const int nk = (int)((t_end - t_begin - j0 < SCHED_ROUND_TILES) ? (t_end - t_begin - j0) : SCHED_ROUND_TILES);
+#else
+        int nk = 0;  // tiles of this round that exist: whole runs, then the part of the run that crosses the end
+#pragma unroll
+        for (int q = 0; q < SCHED_ROUND_TILES / TG; ++q) {
+            const long long left = t_end - tile_of(j0 + q * TG);
+            nk += (left >= TG) ? TG : (left > 0 ? (int)left : 0);
+        }
+#endif
         uint32_t tilemask = 0, classes = 0;
         int inplay = 0, ngames = 0;
-        // all census bytes of the round are requested before the first one is used (the stores below may alias
-        // them as far as the compiler knows, so a single loop would wait for every load in turn)
-        uint32_t cv[SCHED_ROUND_TILES];
-#pragma unroll
-        for (int k = 0; k < SCHED_ROUND_TILES; ++k) {
-            const long long g = ((t0 + k) << 5) + lane;
-            cv[k] = (k < nk && g < B) ? (uint32_t)__ldg(p.census + g) : 0x100u;  // 0x100: no such game
-        }
-#pragma unroll
-        for (int k = 0; k < SCHED_ROUND_TILES; ++k) {
-            if (k < nk) {
-                const long long g = ((t0 + k) << 5) + lane;
-                const uint32_t v = cv[k];
-                const bool valid = v != 0x100u;
-                const bool rest = valid && (v & 0x80u) && ((v & 2u) || frozen_rest);
-                if (rest) {
-                    if (p.done) p.done[g] = 1;
-                    if (p.reward) p.reward[g] = rest_reward;
-                    if (p.num_points) p.num_points[g] = (int32_t)(v & 1u);
+        // The round's census bytes are staged in shared memory (the class array doubles as the landing zone):
+        // cp.async in 4-byte pieces, 8 lanes per tile, all requests in flight at once, then ONE rolled loop
+        // over the tiles (an unrolled register version was 16 KB of straight-line code in a kernel whose hot
+        // loops compete for the instruction cache).
+        {
+            const uint8_t* cbase = p.census + (tile_of(j0) << 5);
+            const long long cbytes = ((B - (tile_of(j0) << 5)) < (long long)nk * 32) ? (B - (tile_of(j0) << 5)) : (long long)nk * 32;
+            if (SCHED_TILE_GROUP == 0 && ((reinterpret_cast<uintptr_t>(cbase) & 3u) == 0)) {
+                for (int o = lane * 4; o < nk * 32; o += 128) {
+                    if (o + 4 <= cbytes) cp_async_4(clsb + o, cbase + o);
+                    else {
+                        for (int q = 0; q < 4; ++q) clsb[o + q] = (o + q < cbytes) ? __ldg(cbase + o + q) : (uint8_t)0;
+                    }
                 }
-                const int c = (!valid || rest) ? 0 : census_class(v);
-                clsb[k * 32 + lane] = (uint8_t)c;
-                settled_total += __popc(__ballot_sync(0xffffffffu, rest));
-                const uint32_t play = __ballot_sync(0xffffffffu, c != 0);
-                if (play) tilemask |= 1u << k;
-                inplay += __popc(play);
-                ngames += __popc(__ballot_sync(0xffffffffu, valid));
-                classes |= 1u << c;
+                cp_async_commit();
+                cp_async_wait<0>();
+            } else {
+                for (int k = 0; k < nk; ++k) {
+                    const long long g = (tile_of(j0 + k) << 5) + lane;
+                    clsb[k * 32 + lane] = (g < B) ? __ldg(p.census + g) : (uint8_t)0;
+                }
             }
+            __syncwarp();
+        }
+        for (int k = 0; k < nk; ++k) {
+            const long long g = (tile_of(j0 + k) << 5) + lane;
+            const bool valid = g < B;
+            const uint32_t v = clsb[k * 32 + lane];
+            const bool rest = valid && (v & 0x80u) && ((v & 2u) || frozen_rest);
+            if (rest) {
+                if (p.done) p.done[g] = 1;
+                if (p.reward) p.reward[g] = rest_reward;
+                if (p.num_points) p.num_points[g] = (int32_t)(v & 1u);
+            }
+            const int c = (!valid || rest) ? 0 : census_class(v);
+            clsb[k * 32 + lane] = (uint8_t)c;
+            const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
+            settled_total += __popc(restmask);
+            // the tile's word of the done mask: the games at rest now, the games that finish in this step later
+            if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
+            const uint32_t play = __ballot_sync(0xffffffffu, c != 0);
+            if (play) tilemask |= 1u << k;
+            inplay += __popc(play);
+            ngames += __popc(__ballot_sync(0xffffffffu, valid));
+            classes |= 1u << c;
         }
         classes = __reduce_or_sync(0xffffffffu, classes) & ~1u;
         __syncwarp();
@@ -158,14 +193,14 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             if (natural) {
                 const int k = __ffs((int)tiles_left) - 1;
                 tiles_left &= tiles_left - 1;
-                g = ((t0 + k) << 5) + lane;
+                g = (tile_of(j0 + k) << 5) + lane;
                 valid = (g < B) && (clsb[k * 32 + lane] != 0);
                 return;
             }
             const int idx = v * 32 + lane;
             valid = idx < total;
             const int lid = valid ? (int)order[idx] : 0;
-            g = ((t0 + (lid >> 5)) << 5) + (lid & 31);
+            g = (tile_of(j0 + (lid >> 5)) << 5) + (lid & 31);
         };
         // gather the chunk's games into a stage: game slot s at s * W words
         auto gather = [&](long long g, bool valid, uint32_t* stage, int sidx) {
@@ -267,6 +302,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             small_process_tile<T, N, D, false>(p, ls, row, exceed, chg);
             if (ls.valid) {
                 if (p.num_points) p.num_points[ls.g] = ls.cnt;
+                if (p.done_bits && ls.cnt < 2) atomicOr(p.done_bits + (ls.g >> 5), 1u << (ls.g & 31));
                 const uint32_t nv = (ls.cnt <= 1) ? (0x80u | (ls.origin ? 2u : 0u) | (uint32_t)ls.cnt)
                                                   : (uint32_t)(ls.cnt > 127 ? 127 : ls.cnt);
                 p.census[ls.g] = (uint8_t)nv;

@@ -97,14 +97,15 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
          write_state: bool = True, want_done: bool = False, want_reward: bool = False,
          want_num_points: bool = False, want_obs: bool = False, obs_coord=None,
          exceed_flag: Optional[torch.Tensor] = None, value_threshold: float = 1e8,
-         census: Optional[torch.Tensor] = None, done_count: Optional[torch.Tensor] = None) -> StepResult:
+         census: Optional[torch.Tensor] = None, done_count: Optional[torch.Tensor] = None,
+         done_bits: Optional[torch.Tensor] = None) -> StepResult:
     """One fused game-step (hk_step).  `host_action` is an int32 [B] tensor of coordinate
     bitmasks, or discrete ids when HK_F_ACT_DISCRETE is set; `axis` an int [B] tensor.
 
     `census` (uint8 [B], in/out; see `new_census`) selects hk_step_census: the in-place step whose work
     follows the games still in play (games at rest are not read, the others are ordered by live count).
     Zero the bytes of any game you rewrite between calls.  `done_count` (int32 [1]) is incremented by the
-    number of finished games."""
+    number of finished games; `done_bits` (int32 [ceil(B/32)]) receives the done flags as a bit mask."""
     dt = _require_state(state)
     B, N, d = state.shape
     dev = state.device
@@ -136,6 +137,9 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
         obs = torch.empty((B, N * d + (d if oc is not None else 0)), dtype=torch.float32, device=dev)
     if exceed_flag is not None and (exceed_flag.dtype != torch.int32 or exceed_flag.device != dev):
         raise ValueError("exceed_flag must be an int32 tensor on the state's device")
+    if done_bits is not None and (census is None or done_bits.dtype != torch.int32 or done_bits.numel() != (B + 31) // 32
+                                  or done_bits.device != dev):
+        raise ValueError("done_bits needs a census and must be an int32 [ceil(B/32)] tensor on the state's device")
     if census is not None:
         if census.dtype != torch.uint8 or census.shape != (B,) or census.device != dev or not census.is_contiguous():
             raise ValueError("census must be a contiguous uint8 [B] tensor on the state's device")
@@ -143,7 +147,7 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
             raise ValueError("the census step runs in place and has no fused observation")
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib().hk_step_census(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(reward), _ptr(npts), _ptr(census),
+            rc = lib().hk_step_census(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(done_bits), _ptr(reward), _ptr(npts), _ptr(census),
                                       _ptr(done_count), _ptr(exceed_flag), B, N, d, dt, ops, flags, float(padding_value),
                                       float(value_threshold), stream)
         check(rc, "hk_step_census")

@@ -94,6 +94,10 @@ extern "C" {
                                        unchanged: calculate_rescale of the JAX flavour (hironaka/src/_jax_ops.py:93-98).
                                        Unset = rescale_torch: only a maximum of exactly 0 is replaced by 1 (_torch_ops.py:139) */
 
+#define HK_F_ACT_NIBBLE (1u << 16) /* host_action[] is a uint8 array holding the actions of TWO games per byte (game 2i in the low
+                                      nibble, 2i+1 in the high one); a nibble is the discrete host id (< 4) | axis (< 4) << 2.
+                                      Half a byte of action stream per game-step; d <= 3 with HK_F_ACT_DISCRETE only; axis[] ignored. */
+
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
 const char* hk_error_string(int code);
@@ -109,6 +113,9 @@ int hk_debug_set_pdl(int on);
 
 /* Tuning hook: geometry of the census-scheduled kernel (0 = 4 warps x 2 stages, 1 = 8 warps x 1 stage). */
 int hk_debug_set_sched_geometry(int which);
+
+/* Test / tuning hook: hk_session_rollout_ex replays a repeated call (same arguments) as a CUDA graph; 0 turns that off. */
+int hk_debug_set_session_graphs(int on);
 
 /* ---- the fused step ------------------------------------------------------------------
  * One launch = one game-step for B independent games:
@@ -150,11 +157,13 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
  *   census [B] uint8, in/out.  0 = unknown (the game is read and counted): zero-fill before the first call
  *          and ZERO THE BYTE OF ANY GAME YOU REWRITE between calls.  Other values belong to the library
  *          (1..127: live rows of a game in play; 0x80 | rows | 2 * at_rest: ended game, dead rows normalised).
+ *   done_bits [ceil(B/32)] uint32, nullable: the done flags as a bit mask (bit g % 32 of word g / 32), every word
+ *          written — one eighth of the bytes of `done` for a host that reads the flags back every step.
  *   done_count [1] int32, nullable: incremented by the number of finished games after the step.
  * Not available with a fused observation, the in-kernel players, out-of-place states or ops == 0
  * (HK_ERR_UNSUPPORTED). */
-int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, float* reward,
-                   int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
+int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, uint32_t* done_bits,
+                   float* reward, int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
                    int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,
                    void* stream);
 
@@ -252,10 +261,15 @@ int hk_session_step(hk_session* s, const int32_t* host_action_host, const int32_
 int hk_session_rollout(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                        int32_t* done_count_host, uint32_t ops, uint32_t flags);
 /* The same with the per-game results of every step: done_host [T,B] uint8 (pinned recommended; nullable) receives
- * each step's done flags, read back on a third stream while the next steps run.  The session keeps a census
+ * each step's done flags, read back on a third stream while the next steps run.  From the second call with the
+ * same arguments on, the whole schedule (uploads, steps, read-backs) is one CUDA-graph launch.  The session keeps a census
  * of its resident state (hk_step_census), so the steps of a long rollout cost what the games still in play cost. */
 int hk_session_rollout_ex(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
                           int32_t* done_count_host, uint8_t* done_host, uint32_t ops, uint32_t flags);
+/* The same with the done flags of every step as bit masks: done_bits_host [T, ceil(B/32)] uint32 (pinned
+ * recommended): 1 bit instead of 1 byte per game-step comes back over PCIe. */
+int hk_session_rollout_bits(hk_session* s, const void* host_action_host, const void* axis_host, int32_t T,
+                            int32_t* done_count_host, uint32_t* done_bits_host, uint32_t ops, uint32_t flags);
 void* hk_session_state_ptr(hk_session* s); /* device pointer of the resident state (zero-copy interop) */
 void* hk_session_stream(hk_session* s);
 

@@ -594,17 +594,21 @@ def test_uint8_actions_and_session_rollout():
             s.close()
         # per-game done flags of every step read back on the third stream, several rollouts on one session
         # (the session's census carries over from call to call and is reset with the state)
+        # The buffers are pinned and reused, so the second call captures the schedule as a CUDA graph and the
+        # later ones replay it (the first runs eagerly).
         s = HostSession(x)
         oo = x
-        for rep in range(3):
-            done = torch.empty((Tn, B), dtype=torch.uint8).pin_memory().numpy()
-            got = s.rollout(packed, None, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED, done=done)
+        packed_pin = torch.from_numpy(packed).pin_memory().numpy()
+        done = torch.empty((Tn, B), dtype=torch.uint8).pin_memory().numpy()
+        for rep in range(5):
+            done[:] = 7
+            got = s.rollout(packed_pin, None, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_PACKED, done=done)
             for t in range(Tn):
                 oo, od, _, _ = cport.step(oo, ha[t], ax[t], op_bits, O.F_ACT_DISCRETE)
                 assert np.array_equal(done[t], od), (rep, t)
                 assert got[t] == int(od.sum()), (rep, t)
             assert np.array_equal(s.get_state(), oo), rep
-            if rep == 1:  # a fresh state resets the census
+            if rep == 2:  # a fresh state resets the census
                 s.set_state(x)
                 oo = x
         s.close()
@@ -662,3 +666,58 @@ def test_reference_arm_matches_the_gpu():
                      inplace=True, want_done=True, want_reward=True, census=census)
         assert np.array_equal(g.cpu().numpy().astype(np.float32), rec[t][0]), t
         assert np.array_equal(r.done.cpu().numpy(), rec[t][1]) and np.array_equal(r.reward.cpu().numpy(), rec[t][2]), t
+
+
+def test_done_bits_and_nibble_actions():
+    """The compact transport of the end-to-end path: done flags as a bit mask (hk_step_census done_bits,
+    hk_session_rollout_bits) and two games' actions per byte (HK_F_ACT_NIBBLE), both kernel families,
+    ragged batch sizes, against the oracle on the unpacked actions."""
+    from hironaka_b200 import HostSession, constants as C, ops
+    rng = np.random.default_rng(23)
+    op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    for (B, N, d) in [(3001, 20, 3), (999, 10, 3), (64, 5, 3), (777, 33, 3)]:
+        Tn = 9
+        x = rng.integers(0, 12, (B, N, d)).astype(np.int32)
+        x[::4, 2:] = -1
+        ha = rng.integers(0, 4, (Tn, B)).astype(np.int32)
+        ax = rng.integers(0, 3, (Tn, B)).astype(np.int32)
+        nib = HostSession.pack_actions_nibble(ha, ax)
+        assert nib.shape == (Tn, (B + 1) // 2)
+        o = x
+        g = T(x)
+        census = ops.new_census(g)
+        bits = torch.zeros((B + 31) // 32, dtype=torch.int32, device="cuda")
+        ref_done = []
+        for t in range(Tn):
+            o, od, _, _ = cport.step(o, ha[t], ax[t], op_bits, O.F_ACT_DISCRETE)
+            ref_done.append(od.astype(bool))
+            bits.fill_(-1 if t % 2 else 0)  # every word must be written, whatever it held
+            from hironaka_b200._lib import check, lib
+            dn = torch.empty(B, dtype=torch.uint8, device="cuda")
+            nb = T(nib[t])
+            check(lib().hk_step_census(g.data_ptr(), nb.data_ptr(), None, dn.data_ptr(), bits.data_ptr(), None, None,
+                                       census.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32, op_bits,
+                                       C.HK_F_ACT_DISCRETE | C.HK_F_ACT_NIBBLE, -1.0, 1e8, torch.cuda.current_stream().cuda_stream))
+            assert eq(g, o), (B, N, t)
+            assert np.array_equal(dn.cpu().numpy().astype(bool), ref_done[-1]), (B, N, t)
+            got = HostSession.unpack_done_bits(bits.cpu().numpy().view(np.uint32), B)
+            assert np.array_equal(got, ref_done[-1]), (B, N, t)
+        # host-buffer session: nibble stream up, bit masks down, graph replay from the second call on
+        s = HostSession(x)
+        nib_pin = torch.from_numpy(nib).pin_memory().numpy()
+        bits_pin = torch.empty((Tn, (B + 31) // 32), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        for rep in range(3):
+            s.set_state(x)
+            bits_pin[:] = 0xdeadbeef
+            counts = s.rollout(nib_pin, None, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_NIBBLE, done_bits=bits_pin)
+            got = HostSession.unpack_done_bits(bits_pin, B)
+            assert np.array_equal(got, np.stack(ref_done)), (B, N, rep)
+            assert counts.tolist() == [int(r.sum()) for r in ref_done], (B, N, rep)
+            assert np.array_equal(s.get_state(), o)
+        s.close()
+    # refused where it cannot be represented
+    from hironaka_b200._lib import lib
+    g = T(np.zeros((4, 16, 4), np.int32))
+    assert lib().hk_step(g.data_ptr(), g.data_ptr(), g.data_ptr(), None, None, None, None, None, None, None, 4, 16, 4,
+                         C.HK_DTYPE_I32, op_bits, C.HK_F_ACT_DISCRETE | C.HK_F_ACT_NIBBLE, -1.0, 1e8,
+                         torch.cuda.current_stream().cuda_stream) != 0

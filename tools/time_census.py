@@ -36,7 +36,7 @@ def run(census_mode, geometry=0):
         census = torch.zeros(B, dtype=torch.uint8, device=dev)
         cp = census.data_ptr() if census_mode else None
         if census_mode:
-            rc = L.hk_step_census(x.data_ptr(), None, None, None, None, None, cp, None, None, B, N, d, C.HK_DTYPE_I32, ROOT, 0,
+            rc = L.hk_step_census(x.data_ptr(), None, None, None, None, None, None, cp, None, None, B, N, d, C.HK_DTYPE_I32, ROOT, 0,
                                   -1.0, 1e8, stream)
         else:
             rc = L.hk_step(x.data_ptr(), x.data_ptr(), None, None, None, None, None, None, None, None, B, N, d,
@@ -47,7 +47,7 @@ def run(census_mode, geometry=0):
         ev[0].record()
         for t in range(T):
             if census_mode:
-                rc = L.hk_step_census(x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), rew.data_ptr(), None,
+                rc = L.hk_step_census(x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), None, rew.data_ptr(), None,
                                       cp, None, None, B, N, d, C.HK_DTYPE_I32, OPS, C.HK_F_ACT_DISCRETE, -1.0, 1e8, stream)
             else:
                 rc = L.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(),

@@ -533,6 +533,30 @@ def measure_secondary(torch, lib, C, dev):
             per.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
     per = np.mean(np.array(per), axis=0)
     ms = float(per.mean())
+    # the same rollout through hk_step_census: the games down to <= 8 live rows are stepped thread-per-game on their
+    # live rows alone (hk_rows_kernel), games at rest are skipped, the rest goes warp-per-game (two launches a step)
+    census5 = torch.zeros(lib.hk_census_bytes(B, N, d), dtype=torch.uint8, device=dev)
+    per_c = []
+    for rep in range(3):
+        x.copy_(pristine)
+        census5.zero_()
+        rc = lib.hk_step_census(x.data_ptr(), None, None, None, None, None, None, census5.data_ptr(), None, None, B, N, d,
+                                C.HK_DTYPE_I32, C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0, -1.0, 1e8, stream)  # fills the census
+        assert rc == 0
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+        ev[0].record()
+        for t in range(T):
+            rc = lib.hk_step_census(x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), None, rew.data_ptr(),
+                                    None, census5.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32,
+                                    C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, C.HK_F_ACT_DISCRETE, -1.0, 1e8, stream)
+            assert rc == 0
+            ev[t + 1].record()
+        torch.cuda.synchronize()
+        if rep:
+            per_c.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
+    per_c = np.mean(np.array(per_c), axis=0)
+    ms_c = float(per_c.mean())
     ops5 = N * (N - 1) * (d + 1) + 3 * N * d + N
     bytes5 = 8 * N * d + 13
     # the same kernel on the ROOT filter (64 random live points per game = the dense worst case)
@@ -555,6 +579,11 @@ def measure_secondary(torch, lib, C, dev):
                  # SURVEY 8d accounting for the ALU-bound shape: game-steps/s x dense OPS(N,d) / INT32 peak
                  "int32_frac_algorithmic": B * ops5 / (ms * 1e-3) / peak_int,
                  "int_ops_per_game_step_dense": ops5, "int32_peak": peak_int, "int32_peak_source": int_src,
+                 "census": {"api": "hk_step_census: hk_rows_kernel (games with <= 8 live rows, thread-per-game on live rows) + "
+                                   "hk_generic_kernel (the rest), games at rest skipped",
+                            "ms_per_step": ms_c, "game_steps_per_s": B / (ms_c * 1e-3),
+                            "ms_by_rollout_step": [round(float(v), 4) for v in per_c],
+                            "hbm_frac": B * bytes5 / (ms_c * 1e-3) / 1e9 / peak_hbm},
                  "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
                  "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
                          "dense count; the dense count is what the root filter (64 live points) executes"}

@@ -32,6 +32,7 @@ int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream
 
 namespace {
 
+std::atomic<int> g_no_rows_kernel{0};  // test / tuning hook (hk_debug_set_rows_kernel)
 std::atomic<int> g_sched_geometry{0};  // tuning hook (hk_debug_set_sched_geometry)
 std::atomic<int> g_use_pdl{0};  // programmatic dependent launch of the thread-per-game kernel (hk_debug_set_pdl)
 
@@ -99,7 +100,15 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
         if (p.out != p.in || p.T != 1 || obs || policy || p.host_out || p.ops == 0) return HK_ERR_UNSUPPORTED;
         if (hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE))
             return dtype == HK_DTYPE_I32 ? hk::launch_sched_i32(p, dev, stream) : hk::launch_sched_f32(p, dev, stream);
-        if (p.done_bits) {  // the warp-per-game kernel ORs the bits in, one game at a time
+        // Large padded shapes with at most 64 rows: the census carries a live mask per game after the bytes, and the
+        // games with few live rows are stepped thread-per-game on their live rows alone (hk_rows_kernel) before
+        // the warp-per-game kernel takes the rest.
+        if (hk::rows_shape(p.N, p.d) && !(p.ops & HK_OP_DEDUPE) && !g_no_rows_kernel.load()) {
+            p.live_mask = reinterpret_cast<uint64_t*>(p.census + ((p.B + 7) & ~7ll));
+            int rc2 = dtype == HK_DTYPE_I32 ? hk::launch_rows_i32(p, dev, stream) : hk::launch_rows_f32(p, dev, stream);
+            if (rc2 != HK_OK) return rc2;
+            p.rows_k = hk::ROWS_K;
+        } else if (p.done_bits) {  // the warp-per-game kernel ORs the bits in, one game at a time
             e = cudaMemsetAsync(p.done_bits, 0, (size_t)((p.B + 31) / 32) * 4, stream);
             if (e != cudaSuccess) return (int)e;
         }
@@ -166,6 +175,18 @@ int hk_debug_set_pdl(int on) {
 int hk_debug_set_sched_geometry(int which) {
     g_sched_geometry.store(which);
     return HK_OK;
+}
+
+// test / tuning hook: the small-games kernel of large padded shapes (on by default)
+int hk_debug_set_rows_kernel(int on) {
+    g_no_rows_kernel.store(on ? 0 : 1);
+    return HK_OK;
+}
+
+int64_t hk_census_bytes(int64_t B, int32_t N, int32_t d) {
+    if (B < 0) return 0;
+    if (hk::is_small_shape(N, d) || !hk::rows_shape(N, d)) return B;
+    return ((B + 7) & ~7ll) + 8 * B;  // census bytes, then one 64-bit live mask per game
 }
 
 // test / tuning hook: host-buffer rollouts replayed as CUDA graphs (on by default)
@@ -513,7 +534,7 @@ int hk_session_create(hk_session** out, int device, int64_t B, int32_t N, int32_
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->axis, (size_t)B * 4 * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done, (size_t)B * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_bits, (size_t)((B + 31) / 32) * 4 * 2);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->census, (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->census, (size_t)hk_census_bytes(B, N, d));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->census, 0, (size_t)B, s->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->reward, (size_t)B * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->done_count, 4);

@@ -119,22 +119,23 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         }
     };
 
-    // ---- census (hk_step_census): games at rest are answered from their census byte and never loaded.
-    // Lane l holds the byte of the game this warp visits l iterations after `cbase` (two batches of 32, so that
-    // the look-ahead of the prefetch never waits on a load).
+    // ---- census (hk_step_census): games at rest are answered from their census byte and never loaded, and
+    // (rows_k > 0) the small games that hk_rows_kernel stepped just before this launch are not touched.
+    // The warp visits game gw + it * nw at iteration `it`.  Census bytes are held 32 iterations at a time (lane l:
+    // iteration cbase + l; two batches, so the look-ahead never waits on a load); a ballot turns a batch into a
+    // mask of the games to PLAY, and the loop jumps from one set bit to the next: a skipped game costs nothing.
+    static_assert(DEPTH == 1, "one game ahead");
     const bool use_census = CENSUS && (p.census != nullptr);
     const bool frozen_rest = (kflags & HK_F_FREEZE_ENDED) && !(kops & (HK_OP_REPOSITION | HK_OP_RESCALE));
-    auto census_fetch = [&](long long it0) -> uint32_t {
-        const long long gg = gw + (it0 + lane) * nw;
-        return (use_census && gg < p.B) ? (uint32_t)__ldg(p.census + gg) : 0u;
-    };
-    long long cbase = 0;
-    uint32_t cv_cur = census_fetch(0), cv_nxt = census_fetch(32);
-    auto census_of = [&](long long it) -> uint32_t {  // it in [cbase, cbase + 64), warp-uniform
-        const int o = (int)(it - cbase);
-        return __shfl_sync(0xffffffffu, (o < 32) ? cv_cur : cv_nxt, o & 31);
-    };
+    const uint32_t rows_k = CENSUS ? (uint32_t)p.rows_k : 0u;
     auto at_rest = [&](uint32_t v) -> bool { return (v & 0x80u) && ((v & 2u) || frozen_rest); };
+    auto skip_game = [&](uint32_t v) -> bool {
+        return at_rest(v) || (rows_k && v != 0 && (((v & 0x80u) ? (v & 1u) : v) <= rows_k));
+    };
+    // census mask of the game just stepped: bit i <=> row i alive (N <= 64)
+    auto store_mask = [&](long long gg, uint32_t lo, uint32_t hi) {
+        if (p.live_mask && lane == 0) p.live_mask[gg] = ((uint64_t)hi << 32) | lo;
+    };
     // finished-game counts: lane l accumulates the games finished after steps l and l + 32 and flushes them
     // once, instead of one same-address atomic per game and step
     int dc0 = 0, dc1 = 0;
@@ -143,47 +144,83 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         else if (st < 64) dc1 += (lane == st - 32) ? 1 : 0;
         else if (lane == 0) atomicAdd(p.done_count + st, 1);
     };
+    const long long n_it = (CENSUS && p.B > gw) ? (p.B - gw + nw - 1) / nw : 0;  // iterations of this warp
+    // one batch of census bytes: the lane's byte, the play mask, and the outputs of the batch's games at rest
+    // (when no hk_rows_kernel ran before: it writes them otherwise)
+    auto census_batch = [&](long long it0, uint32_t& cv) -> uint32_t {
+        const long long itl = it0 + lane;
+        const bool exists = itl < n_it;
+        const long long gg = gw + itl * nw;
+        cv = (use_census && exists) ? (uint32_t)__ldg(p.census + gg) : 0u;
+        if (use_census && !rows_k) {
+            const bool rest = exists && at_rest(cv);
+            if (rest) {
+                if (p.done) p.done[gg] = 1;
+                if (p.reward) p.reward[gg] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
+                if (p.num_points) p.num_points[gg] = (int32_t)(cv & 1u);
+                if (p.done_bits) atomicOr(p.done_bits + (gg >> 5), 1u << (gg & 31));
+            }
+            if (p.done_count) {
+                const int n = __popc(__ballot_sync(0xffffffffu, rest));
+                dc0 += (lane == 0) ? n : 0;
+            }
+        }
+        return __ballot_sync(0xffffffffu, exists && !(use_census && skip_game(cv)));
+    };
+    long long cbase = 0;
+    uint32_t cv_cur = 0, cv_nxt = 0;
+    uint32_t pm_cur = CENSUS ? census_batch(0, cv_cur) : 0u, pm_nxt = CENSUS ? census_batch(32, cv_nxt) : 0u;
+    constexpr long long IT_END = -1;
+    // the first iteration to play at or after `from` (which lies in [cbase, cbase + 64]), IT_END if none is left
+    auto next_play = [&](long long from) -> long long {
+        for (;;) {
+            int o = (int)(from - cbase);
+            if (o < 32) {
+                const uint32_t m = pm_cur & (0xffffffffu << o);
+                if (m) return cbase + (__ffs((int)m) - 1);
+                o = 32;
+            }
+            if (o < 64) {
+                const uint32_t m = pm_nxt & (0xffffffffu << (o - 32));
+                if (m) return cbase + 32 + (__ffs((int)m) - 1);
+            }
+            if (cbase + 64 >= n_it) return IT_END;
+            cbase += 32;  // nothing left in the older batch: bring in the next one
+            cv_cur = cv_nxt;
+            pm_cur = pm_nxt;
+            pm_nxt = census_batch(cbase + 32, cv_nxt);
+            from = cbase + 32;
+        }
+    };
 
     int b = 0;
     int32_t ha_nx = 3, ax_nx = 0;
-    if ((kops & HK_OP_SHIFT) && gw < p.B) {
-        load_actions(p, kflags, gw, ha_nx, ax_nx);
+    // the loop runs over game indices; -1 ends it.  Without a census the next game is simply g + nw.
+    long long it = CENSUS ? next_play(0) : 0;
+    long long g = CENSUS ? (it == IT_END ? -1 : gw + it * nw) : (gw < p.B ? gw : -1);
+    long long g_nx = -1;
+    if (g >= 0) {
+        if (kops & HK_OP_SHIFT) load_actions(p, kflags, g, ha_nx, ax_nx);
+        prefetch(g, 0);
     }
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k) {
-        if (gw + k * nw < p.B && !(use_census && at_rest(census_of(k)))) prefetch(gw + k * nw, k);
-        cp_async_commit();
-    }
-    long long it = 0;
-    for (long long g = gw; g < p.B; g += nw, ++it, b = (b + 1 == NBUF) ? 0 : b + 1) {
-        if (use_census && it - cbase == 32) {
-            cbase += 32;
-            cv_cur = cv_nxt;
-            cv_nxt = census_fetch(cbase + 32);
+    cp_async_commit();
+    for (; g >= 0; g = g_nx, b = (b + 1 == NBUF) ? 0 : b + 1) {
+        if constexpr (CENSUS) {
+            it = next_play(it + 1);
+            g_nx = (it == IT_END) ? -1 : gw + it * nw;
+        } else {
+            g_nx = (g + nw < p.B) ? g + nw : -1;
         }
-        {   // the buffer that held the previous game is free: the game DEPTH iterations ahead goes there
-            const int bn = (b + DEPTH >= NBUF) ? b + DEPTH - NBUF : b + DEPTH;
-            if (g + DEPTH * nw < p.B && !(use_census && at_rest(census_of(it + DEPTH)))) prefetch(g + DEPTH * nw, bn);
+        {   // the buffer that held the previous game is free: the next game to play goes there
+            const int bn = (b + 1 >= NBUF) ? b + 1 - NBUF : b + 1;
+            if (g_nx >= 0) prefetch(g_nx, bn);
         }
         cp_async_commit();  // one group per iteration (possibly empty) keeps the wait count uniform
         // this game's actions were requested one iteration ago (a dependent global load per game would
         // otherwise sit on the critical path of the short iterations); request the next game's now
         int32_t ha = ha_nx, ax = ax_nx;
-        if ((kops & HK_OP_SHIFT) && g + nw < p.B) {
-            load_actions(p, kflags, g + nw, ha_nx, ax_nx);
-        }
-        if (use_census) {
-            const uint32_t cvg = census_of(it);
-            if (at_rest(cvg)) {  // nothing to load, nothing to do: the outputs of a game at rest are constants
-                if (lane == 0) {
-                    if (p.done) p.done[g] = 1;
-                    if (p.reward) p.reward[g] = (kflags & HK_F_ROLE_AGENT) ? -0.0f : 0.0f;
-                    if (p.num_points) p.num_points[g] = (int32_t)(cvg & 1u);
-                    if (p.done_bits) atomicOr(p.done_bits + (g >> 5), 1u << (g & 31));
-                }
-                if (p.done_count) count_done(0);
-                continue;
-            }
+        if ((kops & HK_OP_SHIFT) && g_nx >= 0) {
+            load_actions(p, kflags, g_nx, ha_nx, ax_nx);
         }
         cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
@@ -283,6 +320,8 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 }
                 const bool org = !__any_sync(0xffffffffu, moving);
                 if (lane == 0) p.census[g] = (uint8_t)(0x80u | (org ? 2u : 0u) | (uint32_t)cnt);
+                if (p.live_mask)
+                    store_mask(g, __ballot_sync(0xffffffffu, mylive & 1u), __ballot_sync(0xffffffffu, (mylive >> 1) & 1u));
             }
             if (p.exceed_flag) {
                 if (__any_sync(0xffffffffu, exceed) && lane == 0) *p.exceed_flag = 1;
@@ -460,6 +499,12 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                 const bool org = !__any_sync(0xffffffffu, moving);
                 if (lane == 0)
                     p.census[g] = (uint8_t)((cur <= 1) ? (0x80u | (org ? 2u : 0u) | (uint32_t)cur) : (uint32_t)(cur > 127 ? 127 : cur));
+                if (p.live_mask) {
+                    const bool al = (live >> lane) & 1u;
+                    const uint32_t lo = __reduce_or_sync(0xffffffffu, (al && myslot < 32) ? (1u << myslot) : 0u);
+                    const uint32_t hi = __reduce_or_sync(0xffffffffu, (al && myslot >= 32 && myslot < 64) ? (1u << (myslot - 32)) : 0u);
+                    store_mask(g, lo, hi);
+                }
             }
             // survivors and killed rows go back to their slots of the padded game
             const bool alive = (live >> lane) & 1u;
@@ -830,6 +875,8 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
             const bool org = !__any_sync(0xffffffffu, moving);
             if (lane == 0)
                 p.census[g] = (uint8_t)((cnt <= 1) ? (0x80u | (org ? 2u : 0u) | (uint32_t)cnt) : (uint32_t)(cnt > 127 ? 127 : cnt));
+            if (p.live_mask)
+                store_mask(g, __ballot_sync(0xffffffffu, mylive & 1u), __ballot_sync(0xffffffffu, (mylive >> 1) & 1u));
         }
         // ---- outputs ----
         bool exceed = false;

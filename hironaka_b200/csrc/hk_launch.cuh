@@ -53,6 +53,11 @@ int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream
 // census-scheduled thread-per-game kernel (hk_sched.cuh): in-place single steps with p.census
 int launch_sched_i32(const StepParams& p, int dev, cudaStream_t stream);
 int launch_sched_f32(const StepParams& p, int dev, cudaStream_t stream);
+// small games of large padded shapes, thread-per-game on census masks (hk_rows.cuh)
+int launch_rows_i32(const StepParams& p, int dev, cudaStream_t stream);
+int launch_rows_f32(const StepParams& p, int dev, cudaStream_t stream);
+constexpr int ROWS_K = 8;  // = ROWS_MAX_K of hk_rows.cuh
+inline bool rows_shape(int N, int d) { return N <= 64 && d >= 2 && d <= 5; }
 // warp-per-game family (hk_generic.cuh)
 int launch_generic_i32(const StepParams& p, bool obs, int dev, cudaStream_t stream);
 int launch_generic_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream);

@@ -141,8 +141,9 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
                                   or done_bits.device != dev):
         raise ValueError("done_bits needs a census and must be an int32 [ceil(B/32)] tensor on the state's device")
     if census is not None:
-        if census.dtype != torch.uint8 or census.shape != (B,) or census.device != dev or not census.is_contiguous():
-            raise ValueError("census must be a contiguous uint8 [B] tensor on the state's device")
+        need = lib().hk_census_bytes(B, N, d)
+        if census.dtype != torch.uint8 or census.numel() < need or census.device != dev or not census.is_contiguous():
+            raise ValueError(f"census must be a contiguous uint8 tensor of {need} bytes (new_census) on the state's device")
         if not (write_state and inplace) or want_obs:
             raise ValueError("the census step runs in place and has no fused observation")
         with torch.cuda.device(dev):
@@ -162,8 +163,11 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
 
 
 def new_census(state: torch.Tensor) -> torch.Tensor:
-    """A zeroed census for `state` (uint8 [B], every game unknown); pass it to `step(..., census=)`."""
-    return torch.zeros(state.shape[0], dtype=torch.uint8, device=state.device)
+    """A zeroed census for `state` (every game unknown); pass it to `step(..., census=)`.  uint8
+    [hk_census_bytes(B, N, d)]: byte g describes game g (zero it when you rewrite the game); large padded shapes
+    append a 64-bit live mask per game."""
+    B, N, d = state.shape
+    return torch.zeros(lib().hk_census_bytes(B, N, d), dtype=torch.uint8, device=state.device)
 
 
 def rollout(state: torch.Tensor, host_actions: Optional[torch.Tensor], axes: Optional[torch.Tensor], *, ops: int,

@@ -114,6 +114,8 @@ int hk_debug_set_pdl(int on);
 /* Tuning hook: geometry of the census-scheduled kernel (0 = 4 warps x 2 stages, 1 = 8 warps x 1 stage). */
 int hk_debug_set_sched_geometry(int which);
 
+/* Test / tuning hook: the small-games kernel of large padded shapes (hk_rows_kernel); 0 turns it off. */
+int hk_debug_set_rows_kernel(int on);
 /* Test / tuning hook: hk_session_rollout_ex replays a repeated call (same arguments) as a CUDA graph; 0 turns that off. */
 int hk_debug_set_session_graphs(int on);
 
@@ -154,14 +156,19 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
  * reward = 0 and num_points come from its census byte.  Games in play are ordered by their live-row count
  * before they are processed (thread-per-game shapes), so that the 32 games a warp steps together are alike.
  * Results are identical to hk_step's, bit for bit.
- *   census [B] uint8, in/out.  0 = unknown (the game is read and counted): zero-fill before the first call
- *          and ZERO THE BYTE OF ANY GAME YOU REWRITE between calls.  Other values belong to the library
- *          (1..127: live rows of a game in play; 0x80 | rows | 2 * at_rest: ended game, dead rows normalised).
+ *   census [hk_census_bytes(B, N, d)] uint8, in/out.  Byte g describes game g: 0 = unknown (the game is read and
+ *          counted): zero-fill the first B bytes before the first call and ZERO THE BYTE OF ANY GAME YOU REWRITE
+ *          between calls.  Other values belong to the library (1..127: live rows of a game in play;
+ *          0x80 | rows | 2 * at_rest: ended game, dead rows normalised).  For large padded shapes with N <= 64 and
+ *          2 <= d <= 5 the buffer continues, 8-byte aligned after the B bytes, with one 64-bit live mask per game
+ *          (bit i <=> row i alive, meaningful while the byte is non-zero): games down to at most 8 live rows are
+ *          then stepped thread-per-game on their live rows alone (hk_rows_kernel), the others warp-per-game.
  *   done_bits [ceil(B/32)] uint32, nullable: the done flags as a bit mask (bit g % 32 of word g / 32), every word
  *          written — one eighth of the bytes of `done` for a host that reads the flags back every step.
  *   done_count [1] int32, nullable: incremented by the number of finished games after the step.
  * Not available with a fused observation, the in-kernel players, out-of-place states or ops == 0
  * (HK_ERR_UNSUPPORTED). */
+int64_t hk_census_bytes(int64_t B, int32_t N, int32_t d);
 int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, uint32_t* done_bits,
                    float* reward, int32_t* num_points, uint8_t* census, int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N,
                    int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,

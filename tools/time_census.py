@@ -33,7 +33,7 @@ def run(census_mode, geometry=0):
     final = None
     for rep in range(reps):
         x = x0.clone()
-        census = torch.zeros(B, dtype=torch.uint8, device=dev)
+        census = torch.zeros(L.hk_census_bytes(B, N, d), dtype=torch.uint8, device=dev)
         cp = census.data_ptr() if census_mode else None
         if census_mode:
             rc = L.hk_step_census(x.data_ptr(), None, None, None, None, None, None, cp, None, None, B, N, d, C.HK_DTYPE_I32, ROOT, 0,

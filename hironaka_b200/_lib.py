@@ -39,10 +39,14 @@ SIGNATURES = {
     "hk_dones": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "hk_host_policy": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _u32, _f32, _p]),
     "hk_rollout": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _u32, _u32, _f32, _p]),
+    "hk_rollout_seeded": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _u32, _u32, _f32,
+                                         ctypes.c_uint64, _i32, _p]),
+    "hk_random_actions": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, ctypes.c_uint64, _i32, _p]),
     "hk_experience_scratch_words": (_i64, [_i64]),
     "hk_experience_append": (ctypes.c_int, [_p, _p, _p, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
                                             _p, _p, _i64, _p]),
     "hk_value_targets": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _p]),
+    "hk_overflow": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f32, _i32, _p]),
     "hk_pack_coords": (ctypes.c_int, [_p, _i32, _p, _i64, _i32, _p]),
     "hk_session_create": (ctypes.c_int, [ctypes.POINTER(_p), ctypes.c_int, _i64, _i32, _i32, _i32, _f32]),
     "hk_session_destroy": (ctypes.c_int, [_p]),

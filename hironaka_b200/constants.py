@@ -38,6 +38,8 @@ HK_F_STORE_ALL = 1 << 13
 HK_F_ACT_PACKED = 1 << 14
 HK_F_RESCALE_EPS = 1 << 15
 HK_F_ACT_NIBBLE = 1 << 16
+HK_F_HOST_RANDOM = 1 << 17
+HK_F_AGENT_RANDOM = 1 << 18
 
 # the two semantics of the reference
 TORCH_SEMANTICS = HK_F_NOOP_INVALID | HK_F_FREEZE_ENDED  # hironaka/src/_torch_ops.py:90-93

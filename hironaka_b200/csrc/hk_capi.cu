@@ -66,8 +66,10 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     if (p.in == nullptr) return HK_ERR_BAD_ARG;
     if ((((uintptr_t)p.in) & 3u) || (((uintptr_t)p.out) & 3u)) return HK_ERR_ALIGN;
     {
-        const bool host_fixed = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER);
-        const bool agent_fixed = p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
+        const bool host_fixed = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_HOST_RANDOM);
+        const bool agent_fixed = p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST | HK_F_AGENT_RANDOM);
+        if ((p.flags & HK_F_HOST_RANDOM) && (p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER))) return HK_ERR_BAD_ARG;
+        if ((p.flags & HK_F_AGENT_RANDOM) && (p.flags & (HK_F_AGENT_FIRST | HK_F_AGENT_LAST))) return HK_ERR_BAD_ARG;
         if ((p.flags & HK_F_HOST_ALL_COORD) && (p.flags & HK_F_HOST_ZEILLINGER)) return HK_ERR_BAD_ARG;
         if ((p.flags & HK_F_AGENT_FIRST) && (p.flags & HK_F_AGENT_LAST)) return HK_ERR_BAD_ARG;
         const bool nibble = p.flags & HK_F_ACT_NIBBLE;
@@ -325,6 +327,36 @@ int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action
     return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
 }
 
+int hk_rollout_seeded(const void* state_in, void* state_out, const int32_t* host_action_t, const int32_t* axis_t,
+                      uint8_t* done_t, float* reward_t, int32_t* done_count, int32_t* length, int64_t B, int32_t N,
+                      int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value,
+                      uint64_t seed, int32_t step_offset, void* stream) {
+    if (T < 1 || !(flags & (HK_F_HOST_RANDOM | HK_F_AGENT_RANDOM))) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state_in, state_out, B, N, d, padding_value);
+    p.host_action = (flags & HK_F_HOST_RANDOM) ? nullptr : host_action_t;
+    p.axis = (flags & HK_F_AGENT_RANDOM) ? nullptr : axis_t;
+    p.done = done_t;
+    p.reward = reward_t;
+    p.done_count = done_count;
+    p.length = length;
+    p.T = T;
+    p.ops = ops;
+    p.flags = flags;
+    p.seed = seed;
+    p.step_offset = step_offset;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_random_actions(int32_t* host_action_t, int32_t* axis_t, int64_t B, int32_t d, int32_t T, uint64_t seed,
+                      int32_t step_offset, void* stream) {
+    if (B < 0 || T < 1 || d < 1 || d > HK_MAX_DIM || (!host_action_t && !axis_t)) return HK_ERR_BAD_ARG;
+    if (B == 0) return HK_OK;
+    const long long total = (long long)B * T;
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    hk::hk_random_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(host_action_t, axis_t, B, d, T, seed, step_offset);
+    return (int)cudaGetLastError();
+}
+
 int64_t hk_experience_scratch_words(int64_t B) {
     if (B < 0) return 0;
     return (B + hk::EXP_ROWS_PER_BLOCK - 1) / hk::EXP_ROWS_PER_BLOCK + 4;
@@ -401,6 +433,24 @@ int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_p
     long long ctas = (B + warps - 1) / warps;
     if (ctas > 148 * 8) ctas = 148 * 8;
     hk::hk_value_targets_kernel<<<(unsigned)ctas, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int hk_overflow(const void* state, uint8_t* overflow, int64_t B, int32_t N, int32_t d, int32_t dtype, float value_threshold,
+                int32_t strict, void* stream) {
+    int rc = check_shape(B, N, d, dtype);
+    if (rc != HK_OK) return rc;
+    if (B == 0) return HK_OK;
+    if (!state || !overflow) return HK_ERR_BAD_ARG;
+    const int warps = 8;
+    long long ctas = (B + warps - 1) / warps;
+    if (ctas > 148 * 16) ctas = 148 * 16;
+    if (dtype == HK_DTYPE_I32)
+        hk::hk_overflow_kernel<int32_t><<<(unsigned)ctas, warps * 32, 0, (cudaStream_t)stream>>>(
+            (const int32_t*)state, overflow, B, N * d, value_threshold, strict);
+    else
+        hk::hk_overflow_kernel<float><<<(unsigned)ctas, warps * 32, 0, (cudaStream_t)stream>>>(
+            (const float*)state, overflow, B, N * d, value_threshold, strict);
     return (int)cudaGetLastError();
 }
 

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
     long long g = CENSUS ? (it == IT_END ? -1 : gw + it * nw) : (gw < p.B ? gw : -1);
     long long g_nx = -1;
     if (g >= 0) {
-        if (kops & HK_OP_SHIFT) load_actions(p, kflags, g, ha_nx, ax_nx);
+        if (kops & HK_OP_SHIFT) load_actions(p, kflags, g, 0, ha_nx, ax_nx);
         prefetch(g, 0);
     }
     cp_async_commit();
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         // otherwise sit on the critical path of the short iterations); request the next game's now
         int32_t ha = ha_nx, ax = ax_nx;
         if ((kops & HK_OP_SHIFT) && g_nx >= 0) {
-            load_actions(p, kflags, g_nx, ha_nx, ax_nx);
+            load_actions(p, kflags, g_nx, 0, ha_nx, ax_nx);
         }
         cp_async_wait<DEPTH>();  // everything but the newest DEPTH groups has landed: game g is in buffer b
         __syncwarp();
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
                     chg = true;
                 }
                 int32_t ha_n = 3, ax_n = 0;
-                if ((kops & HK_OP_SHIFT) && st + 1 < kT) load_actions(p, kflags, (long long)(st + 1) * p.B + g, ha_n, ax_n);
+                if ((kops & HK_OP_SHIFT) && st + 1 < kT) load_actions(p, kflags, g, st + 1, ha_n, ax_n);
                 const bool prev_done = cur < 2;
                 const bool alive0 = (live >> lane) & 1u;
                 if ((kops & HK_OP_SHIFT) && cur > 0) {
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(256, HK_GENERIC_MIN_CTAS) hk_generic_kernel(co
         for (int st = 0; st < kT; ++st) {
             int32_t ha_n = 3, ax_n = 0;
             if ((kops & HK_OP_SHIFT) && st + 1 < kT) {
-                load_actions(p, kflags, (long long)(st + 1) * p.B + g, ha_n, ax_n);
+                load_actions(p, kflags, g, st + 1, ha_n, ax_n);
             }
             const bool prev_done = cnt < 2;
 

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_rows_kernel(const StepParams p)
         for (int v = 0; v < nchunks; ++v) {
             uint32_t* stage = stages + (STAGES == 1 ? 0 : (v & 1)) * L::STAGE_WORDS;
             int32_t ha = 3, ax = 0;
-            if ((p.ops & HK_OP_SHIFT) && cur.valid) load_actions(p, p.flags, cur.g, ha, ax);
+            if ((p.ops & HK_OP_SHIFT) && cur.valid) load_actions(p, p.flags, cur.g, 0, ha, ax);
             if (STAGES >= 2 && v + 1 < nchunks) {
                 nxt = pick(v + 1);
                 gather(nxt, stages + ((v + 1) & 1) * L::STAGE_WORDS);

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             ls.ha = 3;
             ls.ax = 0;
             ls.origin = false;
-            if (ls.shift) load_actions(p, p.flags, ls.g, ls.ha, ls.ax);
+            if (ls.shift) load_actions(p, p.flags, ls.g, 0, ls.ha, ls.ax);
             if (bulk) {  // this chunk's games have landed (they were requested one chunk ago)
                 mbar_wait(&bar[sidx], (phase_bits >> sidx) & 1u);
                 phase_bits ^= (1u << sidx);

@@ -439,7 +439,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
         const uint32_t clm_before = clm;
         int32_t ha_n = 3, ax_n = 0;
         if (ls.shift && st + 1 < p.T) {  // prefetch the next step's actions
-            load_actions(p, p.flags, (long long)(st + 1) * B + ls.g, ha_n, ax_n);
+            load_actions(p, p.flags, ls.g, st + 1, ha_n, ax_n);
         }
         const bool prev_done = ls.cnt < 2;
         clm = game_step<T, K, D, RS, POLICY>(y, clm, p.ops, p.flags, ls.ha, ls.ax, row);
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         ls.ha = 3;
         ls.ax = 0;
         if (ls.shift) {
-            load_actions(p, p.flags, ls.g, ls.ha, ls.ax);
+            load_actions(p, p.flags, ls.g, 0, ls.ha, ls.ax);
         }
 
         if (tma) {

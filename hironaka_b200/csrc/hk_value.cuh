@@ -82,4 +82,42 @@ __global__ void __launch_bounds__(256) hk_pack_coords_kernel(const S* coords, in
     mask[b] = (int32_t)m;
 }
 
+// Per-game overflow flags: overflow[b] = 1 iff some entry of game b reaches the threshold (>= ; > when strict) —
+// TensorPoints.exceed_threshold per game (hironaka/core/tensor_points.py:57-63, whole-batch there) and the
+// per-game rule of the gym environments (ListPoints.exceed_threshold, strict; hironaka_base.py:116-131).
+// Dead rows hold a non-positive padding value, so looking at every entry is looking at the live ones.
+// One warp per game, coalesced 4-byte reads, one vote.
+template <typename T>
+__global__ void __launch_bounds__(256) hk_overflow_kernel(const T* state, uint8_t* overflow, long long B, int W, float threshold,
+                                                          int strict) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    for (long long b = (long long)blockIdx.x * warps + warp; b < B; b += (long long)gridDim.x * warps) {
+        const T* x = state + b * W;
+        bool over = false;
+        for (int w = lane; w < W; w += 32) {
+            const float v = (float)x[w];
+            over = over || (strict ? (v > threshold) : (v >= threshold));
+        }
+        over = __any_sync(0xffffffffu, over);
+        if (lane == 0) overflow[b] = over ? 1 : 0;
+    }
+}
+
+// The action streams of the in-kernel random players, written out (hk_random_actions): the same draw as
+// load_actions makes inside the step kernels.
+__global__ void __launch_bounds__(256) hk_random_actions_kernel(int32_t* host_action_t, int32_t* axis_t, long long B, int d,
+                                                                int T, unsigned long long seed, int step_offset) {
+    const long long total = B * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i % B;
+        const int t = (int)(i / B);
+        uint32_t r0, r1;
+        philox4x32_10((uint32_t)g, (uint32_t)((unsigned long long)g >> 32), (uint32_t)(step_offset + t), 0u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r0, r1);
+        if (host_action_t) host_action_t[i] = (int32_t)__umulhi(r0, (1u << d) - (uint32_t)d - 1u);
+        if (axis_t) axis_t[i] = (int32_t)__umulhi(r1, (uint32_t)d);
+    }
+}
+
 }  // namespace hk

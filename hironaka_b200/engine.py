@@ -57,12 +57,15 @@ class GameBatch:
                      (FusedGame.agent_move, hironaka/trainer/fused_game.py:150-162)
     """
 
-    HOST_POLICIES = {None: 0, "stream": 0, "all_coord": C.HK_F_HOST_ALL_COORD, "zeillinger": C.HK_F_HOST_ZEILLINGER}
-    AGENT_POLICIES = {None: 0, "stream": 0, "choose_first": C.HK_F_AGENT_FIRST, "choose_last": C.HK_F_AGENT_LAST}
+    HOST_POLICIES = {None: 0, "stream": 0, "all_coord": C.HK_F_HOST_ALL_COORD, "zeillinger": C.HK_F_HOST_ZEILLINGER,
+                     "random": C.HK_F_HOST_RANDOM}
+    AGENT_POLICIES = {None: 0, "stream": 0, "choose_first": C.HK_F_AGENT_FIRST, "choose_last": C.HK_F_AGENT_LAST,
+                      "random": C.HK_F_AGENT_RANDOM}
 
     def __init__(self, points: torch.Tensor, *, semantics: str = "jax", reposition: bool = True,
                  discrete_host_action: bool = True, role: str = "host", initial_filter: bool = False,
-                 host_policy: Optional[str] = None, agent_policy: Optional[str] = None, census: bool = True):
+                 host_policy: Optional[str] = None, agent_policy: Optional[str] = None, census: bool = True,
+                 seed: int = 0):
         if semantics not in ("jax", "torch"):
             raise ValueError("semantics must be 'jax' or 'torch'")
         if not points.is_cuda:
@@ -77,9 +80,10 @@ class GameBatch:
             (C.HK_F_ACT_DISCRETE if discrete_host_action else 0) | (C.HK_F_ROLE_AGENT if role == "agent" else 0) | \
             self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]
         self.reposition = reposition
+        self.seed, self.steps_played = int(seed), 0  # key and step counter of the in-kernel random players
         # The census (one byte per game, hk_step_census) lets a step skip the games at rest and order the others
         # by live count.  It describes `self.points`: call reset_census() after writing into the tensor yourself.
-        fixed = self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]
+        fixed = (self.HOST_POLICIES[host_policy] | self.AGENT_POLICIES[agent_policy]) & ~(C.HK_F_HOST_RANDOM | C.HK_F_AGENT_RANDOM)
         self.census = _ops.new_census(self.points) if (census and not fixed) else None
         if initial_filter:  # generate_pts: newton -> (reposition) on the root states (util.py:385-392)
             _ops.step(self.points, ops=C.HK_OP_NEWTON | (C.HK_OP_REPOSITION if reposition else 0), inplace=True,
@@ -106,9 +110,17 @@ class GameBatch:
                 steps: Optional[int] = None):
         """T game-steps in ONE launch, state on chip in between.  Returns
         (done [T,B] | None, reward [T,B] | None, done_count [T] int32, length [B] int32 | None)."""
-        _, done, reward, dcount, length = _ops.rollout(self.points, host_actions, axes, ops=self.ops, flags=self.flags,
-                                                       inplace=True, want_done=want_done, want_reward=want_reward,
-                                                       want_done_count=True, want_length=want_length, steps=steps)
+        if self.flags & (C.HK_F_HOST_RANDOM | C.HK_F_AGENT_RANDOM):  # random players drawn in the kernel: no streams
+            T = steps if steps else (host_actions if host_actions is not None else axes).shape[0]
+            _, done, reward, dcount, length = _ops.rollout_random(
+                self.points, T, self.seed, ops=self.ops, flags=self.flags, host_actions=host_actions, axes=axes,
+                step_offset=self.steps_played, inplace=True, want_done=want_done, want_reward=want_reward,
+                want_length=want_length)
+            self.steps_played += T
+        else:
+            _, done, reward, dcount, length = _ops.rollout(self.points, host_actions, axes, ops=self.ops, flags=self.flags,
+                                                           inplace=True, want_done=want_done, want_reward=want_reward,
+                                                           want_done_count=True, want_length=want_length, steps=steps)
         self.reset_census()  # the one-launch rollout does not keep it
         return done, reward, dcount, length
 
@@ -170,15 +182,15 @@ class GameBatch:
 
 def compute_rho(host: str, agent: str, batch_size: int, spec: Tuple[int, int], max_value: int, max_length: int,
                 num_of_loops: int = 10, reposition: bool = True, generator: Optional[torch.Generator] = None,
-                device="cuda"):
+                device="cuda", seed: int = 0):
     """rho between a fixed host and a fixed agent, the validation loop of the reference
     (JAXTrainer.compute_rho, hironaka/jax/jax_trainer.py:467-556) with every game-step on the device
     and ONE launch per batch of games: root states randint[0, max_value) -> newton -> (reposition),
     then max_length - 1 steps of `host` vs `agent`.
 
     host: "random" | "all_coord" | "zeillinger";  agent: "random" | "choose_first" | "choose_last"
-    (hironaka/jax/players.py).  Random players draw their action streams with torch on the device;
-    the other players are evaluated inside the kernel.  Returns (rho, details) like the reference:
+    (hironaka/jax/players.py).  Every player is evaluated inside the kernel; the random ones draw from a
+    counter-based generator keyed by `seed` (Philox, one key per loop), so no action stream is ever materialised.  Returns (rho, details) like the reference:
     rho = sum(details[1:]) / sum(i * details[i])."""
     n, d = spec
     if host not in ("random", "all_coord", "zeillinger") or agent not in ("random", "choose_first", "choose_last"):
@@ -186,16 +198,12 @@ def compute_rho(host: str, agent: str, batch_size: int, spec: Tuple[int, int], m
     steps = max_length - 1
     ncls = 2 ** d - d - 1
     details = [0] * max_length
-    for _ in range(num_of_loops):
+    for loop in range(num_of_loops):
         pts = torch.randint(0, max_value, (batch_size, n, d), generator=generator, device=device, dtype=torch.int32)
-        gb = GameBatch(pts, semantics="jax", reposition=reposition, initial_filter=True,
-                       host_policy=None if host == "random" else host, agent_policy=None if agent == "random" else agent)
+        gb = GameBatch(pts, semantics="jax", reposition=reposition, initial_filter=True, host_policy=host,
+                       agent_policy=agent, seed=(int(seed) << 20) + loop)
         done0 = int(gb.dones().sum())
-        ha = torch.randint(0, ncls, (steps, batch_size), generator=generator, device=device, dtype=torch.int32) \
-            if host == "random" else None
-        ax = torch.randint(0, d, (steps, batch_size), generator=generator, device=device, dtype=torch.int32) \
-            if agent == "random" else None
-        _, _, dcount, _ = gb.rollout(ha, ax, want_length=False, steps=steps)
+        _, _, dcount, _ = gb.rollout(None, None, want_length=False, steps=steps)
         for t, v in enumerate(GameBatch.details(done0, dcount, batch_size)):
             details[t] += v
     denom = sum(i * v for i, v in enumerate(details))

@@ -208,6 +208,44 @@ def rollout(state: torch.Tensor, host_actions: Optional[torch.Tensor], axes: Opt
     return dst, (None if done is None else done.view(torch.bool)), reward, dcount, length
 
 
+def rollout_random(state: torch.Tensor, steps: int, seed: int, *, ops: int, flags: int = 0, host_actions=None, axes=None,
+                   step_offset: int = 0, padding_value: float = -1.0, inplace: bool = True, want_done: bool = False,
+                   want_reward: bool = False, want_length: bool = False):
+    """`steps` fused steps with random players drawn INSIDE the kernel (hk_rollout_seeded): no [T, B] action streams.
+    `flags` carries HK_F_HOST_RANDOM and / or HK_F_AGENT_RANDOM; the other player comes from its [T, B] stream or a
+    fixed-player flag.  Philox4x32-10 keyed by `seed`, counter (game, step_offset + t): see `random_actions`."""
+    dt = _require_state(state)
+    B, N, d = state.shape
+    dev = state.device
+    T = int(steps)
+    ha = None if host_actions is None else host_actions.to(device=dev, dtype=torch.int32).contiguous()
+    ax = None if axes is None else axes.to(device=dev, dtype=torch.int32).contiguous()
+    dst = state if inplace else torch.empty_like(state)
+    done = torch.empty((T, B), dtype=torch.uint8, device=dev) if want_done else None
+    reward = torch.empty((T, B), dtype=torch.float32, device=dev) if want_reward else None
+    dcount = torch.zeros(T, dtype=torch.int32, device=dev)
+    length = torch.empty(B, dtype=torch.int32, device=dev) if want_length else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib().hk_rollout_seeded(_ptr(state), _ptr(dst), _ptr(ha), _ptr(ax), _ptr(done), _ptr(reward), _ptr(dcount),
+                                     _ptr(length), B, N, d, T, dt, ops, flags, float(padding_value), int(seed) & (2 ** 64 - 1),
+                                     int(step_offset), stream)
+    check(rc, "hk_rollout_seeded")
+    return dst, (None if done is None else done.view(torch.bool)), reward, dcount, length
+
+
+def random_actions(B: int, d: int, steps: int, seed: int, step_offset: int = 0, device="cuda"):
+    """The action streams the in-kernel random players draw, written out: (host ids [T, B], axes [T, B]) int32."""
+    dev = torch.device(device)
+    ha = torch.empty((steps, B), dtype=torch.int32, device=dev)
+    ax = torch.empty((steps, B), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib().hk_random_actions(_ptr(ha), _ptr(ax), B, d, steps, int(seed) & (2 ** 64 - 1), int(step_offset),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+    check(rc, "hk_random_actions")
+    return ha, ax
+
+
 def features(state: torch.Tensor, *, flags: int = 0, obs_coord=None, padding_value: float = -1.0) -> torch.Tensor:
     """Observation features [B, N*d (+d)] float32 of a state (hk_features)."""
     dt = _require_state(state)
@@ -234,6 +272,18 @@ def dones(state: torch.Tensor, want_num_points: bool = False):
         rc = lib().hk_dones(_ptr(state), _ptr(done), _ptr(npts), B, N, d, dt, stream)
     check(rc, "hk_dones")
     return done.view(torch.bool), npts
+
+
+def overflow(state: torch.Tensor, value_threshold: float, strict: bool = False) -> torch.Tensor:
+    """Per-game overflow flags [B] bool: some entry >= value_threshold (> when strict) (hk_overflow)."""
+    dt = _require_state(state)
+    B, N, d = state.shape
+    out = torch.empty(B, dtype=torch.uint8, device=state.device)
+    with torch.cuda.device(state.device):
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        rc = lib().hk_overflow(_ptr(state), _ptr(out), B, N, d, dt, float(value_threshold), 1 if strict else 0, stream)
+    check(rc, "hk_overflow")
+    return out.view(torch.bool)
 
 
 def host_policy(state: torch.Tensor, host: str, padding_value: float = -1.0) -> torch.Tensor:

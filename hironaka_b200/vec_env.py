@@ -80,7 +80,7 @@ class _VecHironakaBase:
     def _exceeds(self, state: torch.Tensor) -> torch.Tensor:
         if self.value_threshold is None:
             return torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
-        return state.reshape(self.num_envs, -1).amax(dim=1) > self.value_threshold  # ListPoints.exceed_threshold: strict
+        return _ops.overflow(state, self.value_threshold, strict=True)  # ListPoints.exceed_threshold: strict
 
     @property
     def points(self) -> torch.Tensor:
@@ -206,16 +206,61 @@ class VecHironakaHostEnv(_VecHironakaBase):
         # an invalid move leaves the points alone (the filter is idempotent on a filtered state)
         r = _ops.step(self._state, self._coords, axis, ops=C.HK_OP_SHIFT | C.HK_OP_NEWTON, flags=C.HK_F_NOOP_INVALID,
                       inplace=True, want_done=True)
-        self._state = self._list_order(self._state)
+        self._state.copy_(self._list_order(self._state))  # (in place: the buffer stays put, so a step can be captured)
         ended = r.done
         reward = torch.where(valid, (~ended).float(), torch.full((B,), float(self.invalid_move_penalty),
                                                                   device=self.device))
         stopped = ended.clone()
         if self.stop_after_invalid_move:
             stopped |= ~valid
-        self.exceed_threshold = self._exceeds(self._state)
+        self.exceed_threshold.copy_(self._exceeds(self._state))
         stopped |= self.exceed_threshold
         choice = _ops.host_policy(self._state, self.host)
-        self._coords = torch.where(stopped, torch.zeros_like(choice), choice)
+        self._coords.copy_(torch.where(stopped, torch.zeros_like(choice), choice))
         self.last_action_taken = self._coords
         return self._obs(), reward, stopped, {}
+
+    def capture_step(self, warmup: int = 2) -> "GraphedHostEnvStep":
+        """One `step` of all B environments as a single CUDA-graph replay (the eager step is a dozen small
+        launches: the fused move, the ListPoints re-sort, the overflow flags, the host's next choice, the
+        observation, and the reward / stop bookkeeping).  Call after `reset`; see GraphedHostEnvStep."""
+        return GraphedHostEnvStep(self, warmup)
+
+
+class GraphedHostEnvStep:
+    """`VecHironakaHostEnv.step` captured once: write the agents' axes into `action` (int32 [B]), call the
+    object, read `points` [B,N,d] f32, `coords` [B,d] int8, `reward` [B] f32, `stopped` [B] bool (static
+    tensors, overwritten by every replay).  The environment object stays in sync (its state, coordinates,
+    step counter and overflow flags are the buffers the graph updates)."""
+
+    def __init__(self, env: VecHironakaHostEnv, warmup: int = 2):
+        self.env = env
+        dev = env.device
+        self.action = torch.zeros(env.num_envs, dtype=torch.int32, device=dev)
+        saved = (env._state.clone(), env._coords.clone(), env.current_step.clone(), env.exceed_threshold.clone())
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                env.step(self.action)
+            self._restore(saved)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            obs, self.reward, self.stopped, _ = env.step(self.action)
+            self.points, self.coords = obs["points"], obs["coords"]
+        self._restore(saved)  # the capture itself does not run the step
+
+    def _restore(self, saved):
+        env = self.env
+        env._state.copy_(saved[0])
+        env._coords.copy_(saved[1])
+        env.current_step.copy_(saved[2])
+        env.exceed_threshold.copy_(saved[3])
+
+    def __call__(self, action=None):
+        if action is not None:
+            self.action.copy_(torch.as_tensor(action, device=self.env.device).to(torch.int32).reshape(-1))
+        self.graph.replay()
+        return {"points": self.points, "coords": self.coords}, self.reward, self.stopped, {}

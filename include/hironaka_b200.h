@@ -98,6 +98,15 @@ extern "C" {
                                       nibble, 2i+1 in the high one); a nibble is the discrete host id (< 4) | axis (< 4) << 2.
                                       Half a byte of action stream per game-step; d <= 3 with HK_F_ACT_DISCRETE only; axis[] ignored. */
 
+/* Random players drawn inside the kernel (hk_rollout_seeded / hk_step_seeded), so that a random-play rollout needs no
+ * [T,B] action streams in memory.  Philox4x32-10 with counter (game index low, high, step, 0) and key (seed low,
+ * high): every (game, step) owns its random words whatever the launch geometry, the number of GPUs, or how the
+ * rollout is cut into calls.  Not jax.random's bits — the same distribution (RNG contract in DESIGN.md). */
+#define HK_F_HOST_RANDOM (1u << 17)  /* host: a discrete action id uniform over the 2^d - d - 1 coordinate sets,
+                                        floor(word0 * n / 2^32) (random_host_fn, hironaka/jax/players.py:28-39) */
+#define HK_F_AGENT_RANDOM (1u << 18) /* agent: an axis uniform over ALL d axes, floor(word1 * d / 2^32)
+                                        (random_agent_fn, players.py:142-153) */
+
 /* ---- introspection ------------------------------------------------------------------ */
 int hk_version(void);
 const char* hk_error_string(int code);
@@ -212,6 +221,17 @@ int hk_rollout(const void* state_in, void* state_out, const int32_t* host_action
                int32_t N, int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags,
                float padding_value, void* stream);
 
+/* hk_rollout / hk_step with the in-kernel random players: flags carry HK_F_HOST_RANDOM and / or HK_F_AGENT_RANDOM, the
+ * action array of a random player may be NULL, `seed` is the Philox key and step t of the call draws the words
+ * of step step_offset + t (so per-step calls and one fused call play the same game).  hk_random_actions writes
+ * the same streams out, [T,B] int32 each (either pointer nullable), for callers that want to see them. */
+int hk_rollout_seeded(const void* state_in, void* state_out, const int32_t* host_action_t, const int32_t* axis_t,
+                      uint8_t* done_t, float* reward_t, int32_t* done_count, int32_t* length, int64_t B, int32_t N,
+                      int32_t d, int32_t T, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value,
+                      uint64_t seed, int32_t step_offset, void* stream);
+int hk_random_actions(int32_t* host_action_t, int32_t* axis_t, int64_t B, int32_t d, int32_t T, uint64_t seed,
+                      int32_t step_offset, void* stream);
+
 /* ---- experience writer --------------------------------------------------------
  * Appends the rows with skip[b] == 0, IN BATCH ORDER, to circular replay buffers at
  * (pos + rank) mod capacity and advances the DEVICE-resident pos / full — the no-sync form of
@@ -238,6 +258,13 @@ int hk_experience_append(const uint8_t* skip, const float* obs, const float* nex
 int hk_value_targets(const float* obs, const int32_t* num_points, int32_t* num_points_out, float* value, int64_t B,
                      int32_t T, int32_t W, int32_t dimension, int32_t offset, float discount, int32_t est_sign,
                      int32_t reward_sign, int32_t unified, void* stream);
+
+/* ---- per-game overflow flags ------------------------------------------------------------------
+ * overflow [B] uint8: 1 iff some entry of the game reaches value_threshold (>=, or > when strict != 0): the per-game
+ * form of TensorPoints.exceed_threshold (hironaka/core/tensor_points.py:57-63) and the rule the gym environments
+ * stop on (ListPoints.exceed_threshold, strict; hironaka/gym_env/hironaka_host_env.py:57-58). */
+int hk_overflow(const void* state, uint8_t* overflow, int64_t B, int32_t N, int32_t d, int32_t dtype, float value_threshold,
+                int32_t strict, void* stream);
 
 /* ---- host action packing ----------------------------------------------------------------------
  * Multi-binary coordinate vectors coords[B, d] (what HostActionEncoder.decode_tensor and

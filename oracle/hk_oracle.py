@@ -419,6 +419,40 @@ def zeillinger_fn(pts: np.ndarray) -> np.ndarray:
     return np.stack([zeillinger_fn_slice(p) for p in pts]).astype(np.float32)
 
 
+# ---- the in-kernel random players (the library's RNG contract, include/hironaka_b200.h) ---------
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) on uint32
+    arrays; returns the four output words.  Known answers of the Random123 distribution are checked in
+    tests/test_oracle_golden.py."""
+    c = [np.asarray(x, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for x in (c0, c1, c2, c3)]
+    k = [np.uint64(int(k0) & 0xFFFFFFFF), np.uint64(int(k1) & 0xFFFFFFFF)]
+    M0, M1, LO, S = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF), np.uint64(32)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> S) ^ c[1] ^ k[0], p1 & LO, (p0 >> S) ^ c[3] ^ k[1], p0 & LO]
+        k = [(k[0] + np.uint64(0x9E3779B9)) & LO, (k[1] + np.uint64(0xBB67AE85)) & LO]
+    return [x.astype(np.uint32) for x in c]
+
+
+def random_player_actions(B: int, d: int, T: int, seed: int, step_offset: int = 0):
+    """Action streams [T, B] of the library's in-kernel random players (HK_F_HOST_RANDOM / HK_F_AGENT_RANDOM):
+    counter (game low, game high, step_offset + t, 0), key (seed low, seed high); host id = floor(word0 * ncls /
+    2^32) over the 2^d - d - 1 coordinate sets (random_host_fn, hironaka/jax/players.py:28-39), axis =
+    floor(word1 * d / 2^32) over all d axes (random_agent_fn, players.py:142-153)."""
+    g = np.arange(B, dtype=np.uint64)
+    ncls = 2 ** d - d - 1
+    ha = np.empty((T, B), np.int32)
+    ax = np.empty((T, B), np.int32)
+    for t in range(T):
+        r = philox4x32_10(g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), np.full(B, step_offset + t, np.uint64),
+                          np.zeros(B, np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        ha[t] = ((r[0].astype(np.uint64) * np.uint64(ncls)) >> np.uint64(32)).astype(np.int32)
+        ax[t] = ((r[1].astype(np.uint64) * np.uint64(d)) >> np.uint64(32)).astype(np.int32)
+    return ha, ax
+
+
 # --------------------------------------------------------------------------------------
 # unified step used by the parity tests (same flag vocabulary as include/hironaka_b200.h)
 # --------------------------------------------------------------------------------------

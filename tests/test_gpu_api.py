@@ -511,8 +511,67 @@ def test_compute_rho_matches_reference_loop():
             exp[max_len - 1] += B - done
         assert details == exp, (host, agent)
         assert abs(rho - sum(exp[1:]) / sum(i * v for i, v in enumerate(exp))) < 1e-12
-    rho, details = compute_rho("random", "random", 4096, (20, 3), 20, 20, num_of_loops=1)
-    assert 0 < rho < 1 and sum(details) <= 4096
+    # random vs random: the players are drawn in the kernel (Philox keyed by seed << 20 | loop); the oracle replays
+    # the documented streams
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rho, details = compute_rho("random", "random", 4096, (20, 3), 20, 20, num_of_loops=2, generator=g, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    exp = [0] * 20
+    for loop in range(2):
+        pts = torch.randint(0, 20, (4096, 20, 3), generator=g, device="cuda", dtype=torch.int32).cpu().numpy()
+        o = cport.step(pts, None, None, O.OP_NEWTON | O.OP_REPOSITION, 0)[0]
+        ha, ax = O.random_player_actions(4096, 3, 19, (5 << 20) + loop)
+        prev_done, done = 0, int(O.get_dones(o.astype(np.float32)).sum())
+        for step in range(19):
+            exp[step] += done - prev_done
+            o, od, _, _ = cport.step(o, ha[step], ax[step], O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE)
+            prev_done, done = done, int(od.sum())
+        exp[19] += 4096 - done
+    assert details == exp and 0 < rho < 1
+
+
+def test_in_kernel_random_players():
+    """HK_F_HOST_RANDOM / HK_F_AGENT_RANDOM (hk_rollout_seeded): the rollout with players drawn in the kernel equals
+    the rollout fed with the documented Philox streams (oracle restatement, and hk_random_actions), in one launch
+    or cut into calls with step_offset, on both kernel families, with one or both players random."""
+    from hironaka_b200 import constants as C, ops
+    rng = np.random.default_rng(31)
+    op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    for (B, N, d) in [(5000, 20, 3), (700, 10, 3), (600, 64, 5), (300, 16, 4)]:
+        Tn, seed = 9, 0x1234567890ABCDEF ^ B
+        x = rng.integers(0, 15, (B, N, d)).astype(np.int32)
+        ha, ax = O.random_player_actions(B, d, Tn, seed)
+        gha, gax = ops.random_actions(B, d, Tn, seed)
+        assert eq(gha, ha) and eq(gax, ax)
+        assert ha.min() >= 0 and ha.max() == 2 ** d - d - 2 and ax.min() == 0 and ax.max() == d - 1
+        o, counts = x, []
+        for t in range(Tn):
+            o, od, _, _ = cport.step(o, ha[t], ax[t], op_bits, O.F_ACT_DISCRETE)
+            counts.append(int(od.sum()))
+        out, _, _, dc, _ = ops.rollout_random(T(x), Tn, seed, ops=op_bits, flags=C.HK_F_HOST_RANDOM | C.HK_F_AGENT_RANDOM,
+                                              inplace=False)
+        assert eq(out, o) and dc.tolist() == counts, (B, N, d)
+        # cut into three calls: the step counter carries on
+        st = T(x)
+        got = []
+        for (t0, n) in ((0, 4), (4, 1), (5, 4)):
+            _, _, _, dc, _ = ops.rollout_random(st, n, seed, ops=op_bits, flags=C.HK_F_HOST_RANDOM | C.HK_F_AGENT_RANDOM,
+                                                step_offset=t0)
+            got += dc.tolist()
+        assert eq(st, o) and got == counts, (B, N, d)
+        # one player random, the other from a stream / fixed
+        o2 = x
+        ax_s = rng.integers(0, d, (Tn, B)).astype(np.int32)
+        for t in range(Tn):
+            o2 = cport.step(o2, ha[t], ax_s[t], op_bits, O.F_ACT_DISCRETE)[0]
+        out2, *_ = ops.rollout_random(T(x), Tn, seed, ops=op_bits, flags=C.HK_F_HOST_RANDOM, axes=T(ax_s), inplace=False)
+        assert eq(out2, o2), (B, N, d)
+        o3 = x
+        for t in range(Tn):
+            o3 = cport.step(o3, None, ax[t], op_bits, 1 << 9)[0]  # Zeillinger host, random agent
+        out3, *_ = ops.rollout_random(T(x), Tn, seed, ops=op_bits, flags=C.HK_F_HOST_ZEILLINGER | C.HK_F_AGENT_RANDOM,
+                                      inplace=False)
+        assert eq(out3, o3), (B, N, d)
 
 
 def test_host_session_numpy_only():

@@ -159,3 +159,45 @@ def test_vec_agent_env_random_agent_and_generated_points():
     assert bool((is1 | is2).all())
     frac = float((is1 & ~is2).float().sum() / ((is1 ^ is2).float().sum() + 1e-9))
     assert 0.45 < frac < 0.55, frac
+
+
+def test_overflow_flags_per_game():
+    """hk_overflow: per-game form of exceed_threshold (>= for TensorPoints, > for ListPoints), both dtypes and
+    kernel-independent shapes, against numpy."""
+    from hironaka_b200 import ops
+    rng = np.random.default_rng(9)
+    for (B, N, d) in [(1000, 20, 3), (77, 64, 5), (5, 1, 3)]:
+        x = rng.integers(-1, 50, size=(B, N, d)).astype(np.int32)
+        x[x < 0] = -1
+        for dtype in (np.int32, np.float32):
+            xv = torch.from_numpy(x.astype(dtype)).cuda()
+            for thr in (49.0, 48.0, 1e8):
+                mx = x.reshape(B, -1).max(1)
+                assert np.array_equal(ops.overflow(xv, thr).cpu().numpy(), mx >= thr)
+                assert np.array_equal(ops.overflow(xv, thr, strict=True).cpu().numpy(), mx > thr)
+
+
+@pytest.mark.parametrize("name", sorted(HOST_SETS))
+def test_vec_host_env_captured_step(golden_dir, name):
+    """VecHironakaHostEnv.capture_step: one CUDA-graph replay per environment step, against the eager step on
+    the same action sequence (observation, coordinates, reward, stop flags, and the environment's own state)."""
+    from hironaka_b200 import VecHironakaHostEnv
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = dict(HOST_SETS[name])
+    host = {"Zeillinger": "zeillinger", "AllCoordHost": "all_coord"}[cfg.pop("host")]
+    B, N, d = g["points"].shape
+    cfg["value_threshold"] = 300.0  # exercise the overflow flags too
+    eager = VecHironakaHostEnv(B, host=host, dimension=d, max_num_points=N, **cfg)
+    graphed = VecHironakaHostEnv(B, host=host, dimension=d, max_num_points=N, **cfg)
+    eager.reset(torch.from_numpy(g["points"]))
+    graphed.reset(torch.from_numpy(g["points"]))
+    step = graphed.capture_step()
+    assert torch.equal(graphed.points, eager.points) and torch.equal(graphed.current_step, eager.current_step)
+    rng = np.random.default_rng(3)
+    for t in range(8):
+        a = torch.from_numpy(rng.integers(0, d, B).astype(np.int32)).cuda()
+        eo, er, es, _ = eager.step(a)
+        go, gr, gs, _ = step(a)
+        assert torch.equal(go["points"], eo["points"]) and torch.equal(go["coords"], eo["coords"]), (name, t)
+        assert torch.equal(gr, er) and torch.equal(gs, es), (name, t)
+        assert torch.equal(graphed.points, eager.points) and torch.equal(graphed.exceed_threshold, eager.exceed_threshold)

@@ -282,3 +282,19 @@ def test_golden_tables(golden_dir):
         assert np.array_equal(O.decode_table(d), g[f"decode_{d}"].astype(np.int32))
         assert np.array_equal(O.encode(g[f"decode_{d}"]), g[f"encode_{d}"])
         assert np.array_equal(O.encode(O.decode_table(d)), np.arange(2 ** d - d - 1))
+
+
+def test_philox_known_answers():
+    """The counter-based generator of the in-kernel random players (include/hironaka_b200.h, HK_F_HOST_RANDOM):
+    Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors: philox4x32 10)."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kats:
+        got = O.philox4x32_10(*[np.array([v], np.uint64) for v in c], *k)
+        assert tuple(int(g[0]) for g in got) == want
+    ha, ax = O.random_player_actions(100000, 3, 4, 42)
+    assert set(np.unique(ha)) == {0, 1, 2, 3} and set(np.unique(ax)) == {0, 1, 2}
+    assert abs(np.bincount(ha.ravel()) / ha.size - 0.25).max() < 0.01  # uniform over the four coordinate sets
+    assert np.array_equal(O.random_player_actions(100000, 3, 2, 42, step_offset=2)[0], ha[2:])

@@ -359,11 +359,11 @@ def run_gpu_arm(args):
         secondary["C2_write_back"]["store_all"]["hbm_frac_algorithmic"],
         "algorithmic_bytes_per_launch": B * BYTES_PER_GAME_STEP, "avg_launch_ms": avg_launch_s * 1e3,
         "min_launch_ms": float(np.min(per_launch_ms)), "max_launch_ms": float(np.max(per_launch_ms)),
-        "int_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s,
-        # the same launch against the INT32 issue peak (dense algorithmic op count of SURVEY 8d; the tiered
-        # kernel executes fewer because it only visits live points)
-        "int32": {"achieved_ops_per_s": B * OPS_PER_GAME_STEP / avg_launch_s, "peak_ops_per_s": int32_peak()[0],
-                  "frac": B * OPS_PER_GAME_STEP / avg_launch_s / int32_peak()[0], "peak_source": int32_peak()[1]},
+        # Instruction issue, from EXECUTED instructions (ncu smsp__inst_executed.sum of the committed capture of this
+        # kernel on this workload, mean over the 20 launches of a rollout) over the live launch time, against the
+        # measured INT32 issue peak (profiles/int32_peak.json, lane-ops / 32).  The dense op count of SURVEY 8d is not
+        # used: the kernel visits live rows of games in play only.
+        "issue": executed_issue(avg_launch_s),
         # mean launch time by position in the 20-step rollout (live points thin out as play goes on)
         "launch_ms_by_rollout_step": [round(float(np.mean(per_launch_ms[t::T_ROLLOUT])), 5)
                                       for t in range(min(T_ROLLOUT, K))],
@@ -392,6 +392,18 @@ def run_gpu_arm(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def executed_issue(avg_launch_s):
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            per = json.load(f)["instructions_per_launch_M"]
+        inst = float(np.mean(per)) * 1e6
+    except Exception:
+        return None
+    peak = int32_peak()[0] / 32.0
+    return {"executed_warp_instructions_per_launch": inst, "achieved_per_s": inst / avg_launch_s, "peak_per_s": peak,
+            "frac": inst / avg_launch_s / peak, "source": "profiles/r2a_step_census_ncu_full_summary.csv"}
 
 
 def int32_peak():
@@ -576,8 +588,6 @@ def measure_secondary(torch, lib, C, dev):
                  "kernel": "hk::hk_generic_kernel<int,5,false>", "ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
                  "ms_by_rollout_step": [round(float(v), 4) for v in per],
                  "hbm_frac": B * bytes5 / (ms * 1e-3) / 1e9 / peak_hbm,
-                 # SURVEY 8d accounting for the ALU-bound shape: game-steps/s x dense OPS(N,d) / INT32 peak
-                 "int32_frac_algorithmic": B * ops5 / (ms * 1e-3) / peak_int,
                  "int_ops_per_game_step_dense": ops5, "int32_peak": peak_int, "int32_peak_source": int_src,
                  "census": {"api": "hk_step_census: hk_rows_kernel (games with <= 8 live rows, thread-per-game on live rows) + "
                                    "hk_generic_kernel (the rest), games at rest skipped",
@@ -585,8 +595,10 @@ def measure_secondary(torch, lib, C, dev):
                             "ms_by_rollout_step": [round(float(v), 4) for v in per_c],
                             "hbm_frac": B * bytes5 / (ms_c * 1e-3) / 1e9 / peak_hbm},
                  "root_filter_ms": ms_root, "root_filter_int_frac": B * ops5 / (ms_root * 1e-3) / peak_int,
-                 "note": "the kernel visits live rows only, so a step of real play costs far fewer int-ops than the "
-                         "dense count; the dense count is what the root filter (64 live points) executes"}
+                 "note": "root_filter_int_frac: the root filter (64 live points per game) is the one launch that executes "
+                         "the dense op count of SURVEY 8d, so dense ops / time / INT32 peak is meaningful there; steps of real "
+                         "play visit live rows only, and their executed-instruction counts are in "
+                         "profiles/r2a_c5_census_ncu_full_summary.csv"}
     # the same 20 steps as ONE launch (hk_rollout on the warp-per-game family: compact rows stay in registers)
     try:
         dcount5 = torch.zeros(T, dtype=torch.int32, device=dev)

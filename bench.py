@@ -679,12 +679,40 @@ def measure_secondary(torch, lib, C, dev):
         per = np.mean(np.array(per), axis=0)
         ms = float(per.mean())
         bytes_obs = 8 * N * d + 13 + 4 * N * d
+        # the same through hk_step_census_obs: games at rest get their constant observation from the census byte
+        census_o = torch.zeros(lib.hk_census_bytes(B, N, d), dtype=torch.uint8, device=dev)
+        per_c = []
+        for rep in range(4):
+            x.copy_(pristine)
+            census_o.zero_()
+            rc = lib.hk_step_census(x.data_ptr(), None, None, None, None, None, None, census_o.data_ptr(), None, None, B, N, d,
+                                    C.HK_DTYPE_I32, C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0, -1.0, 1e8, stream)
+            assert rc == 0
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+            ev[0].record()
+            for t in range(T):
+                rc = lib.hk_step_census_obs(x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), None, rew.data_ptr(),
+                                            None, obs.data_ptr(), None, census_o.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32,
+                                            C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON, oflags, -1.0, 1e8, stream)
+                assert rc == 0
+                ev[t + 1].record()
+            torch.cuda.synchronize()
+            if rep:
+                per_c.append([ev[t].elapsed_time(ev[t + 1]) for t in range(T)])
+        per_c = np.mean(np.array(per_c), axis=0)
+        ms_c = float(per_c.mean())
         out["C2_step_with_features"] = {
             "workload": "C2, 1 Mi games, random play T=20; one launch per step = shift + reposition + newton + done/reward + "
                         "host observation (rescaled, lexicographically sorted f32 rows)",
             "kernel": "hk::hk_small_kernel<int,20,3,true>", "ms_per_step": ms, "game_steps_per_s": B / (ms * 1e-3),
             "bytes_per_game_step": bytes_obs, "hbm_frac": B * bytes_obs / (ms * 1e-3) / 1e9 / peak_hbm,
-            "ms_by_rollout_step": [round(float(v), 4) for v in per]}
+            "ms_by_rollout_step": [round(float(v), 4) for v in per],
+            "census": {"api": "hk_step_census_obs (hk_sched_kernel<..., OBS>): the observation of a game at rest is a constant "
+                              "written from its census byte; only the games in play run the feature code",
+                       "ms_per_step": ms_c, "game_steps_per_s": B / (ms_c * 1e-3),
+                       "hbm_frac": B * bytes_obs / (ms_c * 1e-3) / 1e9 / peak_hbm,
+                       "ms_by_rollout_step": [round(float(v), 4) for v in per_c]}}
         del x, obs, pristine
     except Exception as e:
         out["C2_step_with_features"] = {"error": repr(e)}

@@ -27,6 +27,8 @@ SIGNATURES = {
     "hk_debug_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "hk_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
     "hk_step_census": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32, _f32, _p]),
+    "hk_step_census_obs": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _u32, _f32,
+                                          _f32, _p]),
     "hk_debug_set_sched_geometry": (ctypes.c_int, [ctypes.c_int]),
     "hk_census_bytes": (_i64, [_i64, _i32, _i32]),
     "hk_debug_set_rows_kernel": (ctypes.c_int, [ctypes.c_int]),

@@ -99,8 +99,15 @@ int run(StepParams& p, int dtype, int force_generic, cudaStream_t stream) {
     if (p.census) {
         // the census path: in-place single steps without fused observation or in-kernel players
         const bool policy = p.flags & (HK_F_HOST_ALL_COORD | HK_F_HOST_ZEILLINGER | HK_F_AGENT_FIRST | HK_F_AGENT_LAST);
-        if (p.out != p.in || p.T != 1 || obs || policy || p.host_out || p.ops == 0) return HK_ERR_UNSUPPORTED;
-        if (hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE))
+        if (p.out != p.in || p.T != 1 || policy || p.host_out || p.ops == 0) return HK_ERR_UNSUPPORTED;
+        const bool sched = hk::is_small_shape(p.N, p.d) && !force_generic && !(p.ops & HK_OP_DEDUPE);
+        // a fused observation rides on the census only for the thread-per-game shapes and the sorted modes (the
+        // observation of a game at rest is then a constant)
+        if (obs && !(sched && (p.flags & (HK_F_OBS_SORT_COORD0 | HK_F_OBS_SORT_LEX | HK_F_OBS_SORT_LEX_FIRST))))
+            return HK_ERR_UNSUPPORTED;
+        if (sched && obs)
+            return dtype == HK_DTYPE_I32 ? hk::launch_sched_i32_obs(p, dev, stream) : hk::launch_sched_f32_obs(p, dev, stream);
+        if (sched)
             return dtype == HK_DTYPE_I32 ? hk::launch_sched_i32(p, dev, stream) : hk::launch_sched_f32(p, dev, stream);
         // Large padded shapes with at most 64 rows: the census carries a live mask per game after the bytes, and the
         // games with few live rows are stepped thread-per-game on their live rows alone (hk_rows_kernel) before
@@ -215,6 +222,29 @@ int hk_step(const void* state_in, void* state_out, const int32_t* host_action, c
     p.num_points = num_points;
     p.obs = obs;
     p.obs_coord = obs_coord;
+    p.exceed_flag = exceed_flag;
+    p.ops = ops;
+    p.flags = flags;
+    p.threshold = value_threshold;
+    return run(p, dtype, g_force_generic.load(), (cudaStream_t)stream);
+}
+
+int hk_step_census_obs(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, uint32_t* done_bits,
+                       float* reward, int32_t* num_points, float* obs, const int32_t* obs_coord, uint8_t* census,
+                       int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                       uint32_t ops, uint32_t flags, float padding_value, float value_threshold, void* stream) {
+    if (census == nullptr || state == nullptr) return HK_ERR_BAD_ARG;
+    StepParams p = make_params(state, state, B, N, d, padding_value);
+    p.host_action = host_action;
+    p.axis = axis;
+    p.done = done;
+    p.done_bits = done_bits;
+    p.reward = reward;
+    p.num_points = num_points;
+    p.obs = obs;
+    p.obs_coord = obs_coord;
+    p.census = census;
+    p.done_count = done_count;
     p.exceed_flag = exceed_flag;
     p.ops = ops;
     p.flags = flags;

@@ -53,6 +53,8 @@ int launch_small_f32(const StepParams& p, bool obs, int dev, cudaStream_t stream
 // census-scheduled thread-per-game kernel (hk_sched.cuh): in-place single steps with p.census
 int launch_sched_i32(const StepParams& p, int dev, cudaStream_t stream);
 int launch_sched_f32(const StepParams& p, int dev, cudaStream_t stream);
+int launch_sched_i32_obs(const StepParams& p, int dev, cudaStream_t stream);  // + fused observation (sorted modes)
+int launch_sched_f32_obs(const StepParams& p, int dev, cudaStream_t stream);
 // small games of large padded shapes, thread-per-game on census masks (hk_rows.cuh)
 int launch_rows_i32(const StepParams& p, int dev, cudaStream_t stream);
 int launch_rows_f32(const StepParams& p, int dev, cudaStream_t stream);

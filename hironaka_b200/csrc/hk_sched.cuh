@@ -32,14 +32,15 @@ constexpr int SCHED_ROUND_TILES = 32;  // tiles (of 32 games) a warp schedules t
 #define SCHED_NATURAL_DEN 2  // its games are in play (tools/time_census.py)
 #endif
 
-template <int N, int D, int WARPS, int STAGES>
+template <int N, int D, int WARPS, int STAGES, bool OBS = false>
 struct SchedLayout {
     static constexpr int W = N * D;
     static constexpr int STAGE_WORDS = 32 * W;
+    static constexpr int OBS_WORDS = OBS ? 32 * (W + D) : 0;  // the observation rows of one chunk
     // per warp: STAGES game stages, the class bytes of a round (one per game), the sorted order (u16 per game)
     static constexpr int CLS_WORDS = SCHED_ROUND_TILES * 32 / 4;
     static constexpr int ORDER_WORDS = SCHED_ROUND_TILES * 32 / 2;
-    static constexpr int WARP_WORDS = STAGES * STAGE_WORDS + CLS_WORDS + ORDER_WORDS;
+    static constexpr int WARP_WORDS = STAGES * STAGE_WORDS + CLS_WORDS + ORDER_WORDS + OBS_WORDS;
     static constexpr int BAR_BYTES = 256;  // mbarriers first (WARPS * STAGES of them), then the warps' areas
     static_assert(WARPS * STAGES * 8 <= BAR_BYTES, "mbarrier area too small");
     static constexpr size_t SMEM_BYTES = BAR_BYTES + (size_t)WARPS * WARP_WORDS * 4;
@@ -51,9 +52,12 @@ __device__ __forceinline__ int census_class(uint32_t v) {
     return v <= 2 ? 1 : (v <= 4 ? 2 : (v <= 8 ? 3 : (v <= 12 ? 4 : (v <= 16 ? 5 : 6))));
 }
 
-template <typename T, int N, int D, int WARPS, int STAGES>
+// OBS: the instantiation that also builds the observation features of the new state (p.obs, sorted modes only):
+// a game at rest has a CONSTANT observation — its lone point, at the origin, sorts first, the rest is padding — so
+// it is written from the census byte like the other outputs, and only the games in play run the feature code.
+template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false>
 __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p) {
-    using L = SchedLayout<N, D, WARPS, STAGES>;
+    using L = SchedLayout<N, D, WARPS, STAGES, OBS>;
     constexpr int W = L::W;
     constexpr int CHW = (W % 4 == 0) ? 4 : ((W % 2 == 0) ? 2 : 1);  // words per copy piece
     constexpr int LPG = W / CHW;                                     // lanes per game
@@ -67,6 +71,9 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
     uint32_t* stages = wbase;
     uint8_t* clsb = reinterpret_cast<uint8_t*>(wbase + STAGES * L::STAGE_WORDS);
     uint16_t* order = reinterpret_cast<uint16_t*>(wbase + STAGES * L::STAGE_WORDS + L::CLS_WORDS);
+    float* obs_tile = reinterpret_cast<float*>(wbase + STAGES * L::STAGE_WORDS + L::CLS_WORDS + L::ORDER_WORDS);
+    const int OW = W + (p.obs_coord ? D : 0);
+    const bool obs_bulk = OBS && aligned16(p.obs) && ((OW & 3) == 0);
 
     const long long B = p.B;
     const long long ntiles = (B + 31) >> 5;
@@ -142,22 +149,14 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             }
             __syncwarp();
         }
+        // pass 1: class of every game (0 = at rest or no such game), what is in play
         for (int k = 0; k < nk; ++k) {
             const long long g = (tile_of(j0 + k) << 5) + lane;
             const bool valid = g < B;
             const uint32_t v = clsb[k * 32 + lane];
             const bool rest = valid && (v & 0x80u) && ((v & 2u) || frozen_rest);
-            if (rest) {
-                if (p.done) p.done[g] = 1;
-                if (p.reward) p.reward[g] = rest_reward;
-                if (p.num_points) p.num_points[g] = (int32_t)(v & 1u);
-            }
             const int c = (!valid || rest) ? 0 : census_class(v);
-            clsb[k * 32 + lane] = (uint8_t)c;
-            const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
-            settled_total += __popc(restmask);
-            // the tile's word of the done mask: the games at rest now, the games that finish in this step later
-            if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
+            clsb[k * 32 + lane] = (uint8_t)(c | (rest ? 0x80 : 0) | ((v & 1u) << 6));  // class | at rest | its live count
             const uint32_t play = __ballot_sync(0xffffffffu, c != 0);
             if (play) tilemask |= 1u << k;
             inplay += __popc(play);
@@ -165,19 +164,84 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             classes |= 1u << c;
         }
         classes = __reduce_or_sync(0xffffffffu, classes) & ~1u;
-        __syncwarp();
-        if (inplay == 0) continue;
         // While most games are still in play the tiles are stepped whole, in natural order: one bulk copy per
         // tile and coalesced actions / outputs beat the per-game gather, and there is little to skip.  Later the
         // games in play are sorted by class and gathered one by one.
-        const bool natural = inplay * SCHED_NATURAL_DEN >= ngames * SCHED_NATURAL_NUM;
+        // (with the fused observation the per-game stores of the sorted order cost more: natural order down to a quarter)
+        const bool natural = OBS ? (inplay * 4 >= ngames) : (inplay * SCHED_NATURAL_DEN >= ngames * SCHED_NATURAL_NUM);
+        // pass 2: the outputs of the games at rest, from their census bytes
+        for (int k = 0; k < nk; ++k) {
+            const long long g = (tile_of(j0 + k) << 5) + lane;
+            const uint32_t code = clsb[k * 32 + lane];
+            const bool rest = code & 0x80u;
+            const uint32_t v = (code >> 6) & 1u;  // live count of a game at rest
+            if (rest) {
+                if (p.done) p.done[g] = 1;
+                if (p.reward) p.reward[g] = rest_reward;
+                if (p.num_points) p.num_points[g] = (int32_t)v;
+            }
+            const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
+            settled_total += __popc(restmask);
+            if constexpr (OBS) {
+                // (warp-uniform) the constant observation of every game at rest of this tile — unless the tile is about to
+                // be stepped whole in natural order: its observation rows are then stored as one block, these included
+                if (p.obs && restmask && !(natural && ((tilemask >> k) & 1u))) {
+                    // staged in the observation tile like a chunk's rows, then ONE bulk store for a tile that is
+                    // at rest as a whole (the common case late in a rollout), one per game otherwise
+                    float* orow = obs_tile + lane * OW;
+                    bulk_wait_read<0>();  // earlier observation stores have read the tile
+                    __syncwarp();
+                    if (rest) {
+                        const float z = (v & 1u) ? 0.0f : p.pad;  // the lone point, at the origin, sorts first
+                        const uint32_t ocm = p.obs_coord ? action_mask(load_action(p.obs_coord, g, p.flags), p.flags) : 0u;
+                        if ((OW & 3) == 0 && D <= 4 && !p.obs_coord) {
+                            float4* o4 = reinterpret_cast<float4*>(orow);
+                            const float4 padv4 = make_float4(p.pad, p.pad, p.pad, p.pad);
+                            o4[0] = make_float4(z, D > 1 ? z : p.pad, D > 2 ? z : p.pad, D > 3 ? z : p.pad);
+#pragma unroll
+                            for (int q = 1; q < W / 4; ++q) o4[q] = padv4;
+                        } else {
+                            for (int w = 0; w < OW; ++w)
+                                orow[w] = (w < D) ? z : (w < W ? p.pad : (float)((ocm >> (w - W)) & 1u));
+                        }
+                    }
+                    const long long first = g - lane;
+                    const int cnt = (int)((B - first < 32) ? (B - first) : 32);
+                    const uint32_t allmask = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+                    if (obs_bulk) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (restmask == allmask) {
+                            if (lane == 0) bulk_store(p.obs + first * OW, obs_tile, (uint32_t)(cnt * OW) * 4u);
+                        } else if (rest) {
+                            bulk_store(p.obs + g * OW, orow, (uint32_t)OW * 4u);
+                        }
+                        bulk_commit();
+                    } else {
+                        __syncwarp();
+                        uint32_t m = restmask;
+                        while (m) {
+                            const int r = __ffs((int)m) - 1;
+                            m &= m - 1;
+                            warp_copy_words(reinterpret_cast<uint32_t*>(p.obs + (first + r) * OW),
+                                            reinterpret_cast<uint32_t*>(obs_tile + r * OW), OW, lane);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // the tile's word of the done mask: the games at rest now, the games that finish in this step later
+            if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
+        }
+        __syncwarp();
+        if (inplay == 0) continue;
         // ---- counting sort of the games in play by class: order[] lists them (tile slot * 32 + lane) ----
         int total = 0;
         for (int q = 1; q <= 6 && !natural; ++q) {
             if (!((classes >> q) & 1u)) continue;
             for (int k = 0; k < nk; ++k) {
                 if (!((tilemask >> k) & 1u)) continue;
-                const bool m = clsb[k * 32 + lane] == q;
+                const bool m = (clsb[k * 32 + lane] & 7u) == (uint32_t)q;
                 const uint32_t bal = __ballot_sync(0xffffffffu, m);
                 if (m) order[total + __popc(bal & lt)] = (uint16_t)(k * 32 + lane);
                 total += __popc(bal);
@@ -194,7 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
                 const int k = __ffs((int)tiles_left) - 1;
                 tiles_left &= tiles_left - 1;
                 g = (tile_of(j0 + k) << 5) + lane;
-                valid = (g < B) && (clsb[k * 32 + lane] != 0);
+                valid = (g < B) && ((clsb[k * 32 + lane] & 7u) != 0);
                 return;
             }
             const int idx = v * 32 + lane;
@@ -310,6 +374,63 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             if (p.exceed_flag) {
                 if (__any_sync(0xffffffffu, exceed && ls.valid) && lane == 0) *p.exceed_flag = 1;
             }
+            if constexpr (OBS) {
+                if (p.obs) {  // ---- observation features of the new state (in the lane's row area), as in K-small ----
+                    const bool ingrid = ls.g < B;  // (natural order: the games at rest of the tile ride along)
+                    float* orow = obs_tile + lane * OW;
+                    bulk_wait_read<0>();  // the previous chunk's observation stores have read the tile
+                    __syncwarp();
+                    {
+                        T z[W];
+                        load_game<T, W>(row, z);
+                        if constexpr (Elem<T>::is_float) {
+#pragma unroll
+                            for (int q = 0; q < W; ++q) z[q] = z[q] + 0.0f;
+                        }
+                        const uint32_t zl = live_mask<T, N, D>(z);
+                        const int zmax = __reduce_max_sync(0xffffffffu, ingrid ? __popc(zl) : 0);
+                        bool built = false;
+                        if constexpr (D <= 6) built = features_network<T, N, D>(z, zl, zmax, p.flags, p.pad, orow);
+                        if (!built) {
+                            const int gpow = (OW & -OW) > 32 ? 32 : (OW & -OW);
+                            features_rolled<T, N, D>(row, zl, zmax, p.flags, p.pad, orow, (lane * gpow) >> 5);
+                        }
+                    }
+                    if (p.obs_coord) {
+                        const uint32_t ocm = ingrid ? action_mask(load_action(p.obs_coord, ls.g, p.flags), p.flags) : 0u;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) orow[W + k] = (float)((ocm >> k) & 1u);
+                    }
+                    if (natural) {  // the tile's observations are contiguous
+                        const long long first = ls.g - lane;
+                        const int cnt = (int)((B - first < 32) ? (B - first) : 32);
+                        if (obs_bulk) {
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) bulk_store(p.obs + first * OW, obs_tile, (uint32_t)(cnt * OW) * 4u);
+                            bulk_commit();
+                        } else {
+                            __syncwarp();
+                            warp_copy_words(reinterpret_cast<uint32_t*>(p.obs + first * OW), reinterpret_cast<uint32_t*>(obs_tile),
+                                            cnt * OW, lane);
+                        }
+                    } else if (obs_bulk) {  // one bulk store per game
+                        fence_async_smem();
+                        __syncwarp();
+                        if (ls.valid) bulk_store(p.obs + ls.g * OW, orow, (uint32_t)OW * 4u);
+                        bulk_commit();
+                    } else {
+                        __syncwarp();
+                        for (int s2 = 0; s2 < 32; ++s2) {
+                            const long long gs = __shfl_sync(0xffffffffu, ls.g, s2);
+                            const bool vs = __shfl_sync(0xffffffffu, ls.valid ? 1 : 0, s2) != 0;
+                            if (vs) warp_copy_words(reinterpret_cast<uint32_t*>(p.obs + gs * OW),
+                                                    reinterpret_cast<uint32_t*>(obs_tile + s2 * OW), OW, lane);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
             // ---- write-back of the changed games, GPI games per instruction ----
             uint32_t dirty = __ballot_sync(0xffffffffu, ls.valid && chg);
             __syncwarp();
@@ -370,7 +491,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             v_cur = v_nxt;
         }
     }
-    if (bulk) bulk_wait_all<0>();  // this lane's bulk stores are globally complete before the warp retires
+    if (bulk || obs_bulk) bulk_wait_all<0>();  // this lane's bulk stores are globally complete before the warp retires
     if (p.done_count && settled_total && lane == 0) atomicAdd(p.done_count, settled_total);
 }
 

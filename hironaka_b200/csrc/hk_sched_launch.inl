@@ -5,11 +5,11 @@
 namespace hk {
 namespace {
 
-template <typename T, int N, int D, int WARPS, int STAGES>
+template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false>
 int launch_sched_geom(const StepParams& p, int dev, cudaStream_t stream) {
-    using L = SchedLayout<N, D, WARPS, STAGES>;
+    using L = SchedLayout<N, D, WARPS, STAGES, OBS>;
     static KernelFacts facts;
-    auto kernel = hk_sched_kernel<T, N, D, WARPS, STAGES>;
+    auto kernel = hk_sched_kernel<T, N, D, WARPS, STAGES, OBS>;
     cudaError_t err = cudaSuccess;
     const int threads = WARPS * 32;
     const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
@@ -22,8 +22,10 @@ int launch_sched_geom(const StepParams& p, int dev, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
-template <typename T, int N, int D>
+template <typename T, int N, int D, bool OBS>
 int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
+    // with the observation tile: 4 warps x 1 stage (12 warps per SM), as the step + features kernel of K-small
+    if constexpr (OBS) return launch_sched_geom<T, N, D, 4, 1, true>(p, dev, stream);
     // geometry (warps per CTA x stages per warp): see DESIGN.md "K-sched"; hk_debug_set_sched_geometry switches it
     switch (sched_geometry()) {
         case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
@@ -31,12 +33,12 @@ int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
     }
 }
 
-template <typename T>
+template <typename T, bool OBS>
 int dispatch_sched(const StepParams& p, int dev, cudaStream_t stream) {
     if (p.d == 3) {
-        if (p.N == 20) return launch_sched_shape<T, 20, 3>(p, dev, stream);
-        if (p.N == 10) return launch_sched_shape<T, 10, 3>(p, dev, stream);
-        if (p.N == 5) return launch_sched_shape<T, 5, 3>(p, dev, stream);
+        if (p.N == 20) return launch_sched_shape<T, 20, 3, OBS>(p, dev, stream);
+        if (p.N == 10) return launch_sched_shape<T, 10, 3, OBS>(p, dev, stream);
+        if (p.N == 5) return launch_sched_shape<T, 5, 3, OBS>(p, dev, stream);
     }
     return HK_ERR_UNSUPPORTED;
 }

@@ -144,15 +144,20 @@ def step(state: torch.Tensor, host_action=None, axis=None, *, ops: int, flags: i
         need = lib().hk_census_bytes(B, N, d)
         if census.dtype != torch.uint8 or census.numel() < need or census.device != dev or not census.is_contiguous():
             raise ValueError(f"census must be a contiguous uint8 tensor of {need} bytes (new_census) on the state's device")
-        if not (write_state and inplace) or want_obs:
-            raise ValueError("the census step runs in place and has no fused observation")
+        if not (write_state and inplace):
+            raise ValueError("the census step runs in place")
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib().hk_step_census(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(done_bits), _ptr(reward), _ptr(npts), _ptr(census),
-                                      _ptr(done_count), _ptr(exceed_flag), B, N, d, dt, ops, flags, float(padding_value),
-                                      float(value_threshold), stream)
+            if want_obs:  # thread-per-game shapes, sorted observation modes
+                rc = lib().hk_step_census_obs(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(done_bits), _ptr(reward),
+                                              _ptr(npts), _ptr(obs), _ptr(oc), _ptr(census), _ptr(done_count), _ptr(exceed_flag),
+                                              B, N, d, dt, ops, flags, float(padding_value), float(value_threshold), stream)
+            else:
+                rc = lib().hk_step_census(_ptr(state), _ptr(ha), _ptr(ax), _ptr(done), _ptr(done_bits), _ptr(reward), _ptr(npts),
+                                          _ptr(census), _ptr(done_count), _ptr(exceed_flag), B, N, d, dt, ops, flags,
+                                          float(padding_value), float(value_threshold), stream)
         check(rc, "hk_step_census")
-        return StepResult(dst, None if done is None else done.view(torch.bool), reward, npts, None)
+        return StepResult(dst, None if done is None else done.view(torch.bool), reward, npts, obs)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib().hk_step(_ptr(state), _ptr(dst), _ptr(ha), _ptr(ax), _ptr(done), _ptr(reward), _ptr(npts),

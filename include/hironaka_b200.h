@@ -183,6 +183,16 @@ int hk_step_census(void* state, const int32_t* host_action, const int32_t* axis,
                    int32_t d, int32_t dtype, uint32_t ops, uint32_t flags, float padding_value, float value_threshold,
                    void* stream);
 
+/* hk_step_census with the fused observation of the new state (obs [B, N*d (+d if obs_coord)] float, as hk_step's):
+ * thread-per-game shapes and the sorted observation modes only (HK_ERR_UNSUPPORTED otherwise).  A game at rest has a
+ * constant observation — its lone point, at the origin, sorts first; the rest is padding (get_feature_fn,
+ * hironaka/jax/util.py:186-196; TensorPoints.get_features tensor_points.py:72-74) — so it is written from the
+ * census byte and only the games in play run the feature code. */
+int hk_step_census_obs(void* state, const int32_t* host_action, const int32_t* axis, uint8_t* done, uint32_t* done_bits,
+                       float* reward, int32_t* num_points, float* obs, const int32_t* obs_coord, uint8_t* census,
+                       int32_t* done_count, int32_t* exceed_flag, int64_t B, int32_t N, int32_t d, int32_t dtype,
+                       uint32_t ops, uint32_t flags, float padding_value, float value_threshold, void* stream);
+
 /* ---- per-op entry points (the reference's hironaka.src op surface) ---------------------
  * Each is one launch of the same kernel family with a single op selected. */
 int hk_shift(const void* state_in, void* state_out, const int32_t* host_action, const int32_t* axis,

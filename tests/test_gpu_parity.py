@@ -796,3 +796,49 @@ def test_census_step_baseline_size(hb):
     c = census.cpu().numpy()[:B]
     at_rest = (c & 0x82) == 0x82
     assert np.array_equal(at_rest, od.astype(bool)) and at_rest.mean() > 0.99
+
+
+@pytest.mark.parametrize("shape", [(20011, 20, 3), (3001, 10, 3), (777, 5, 3), (31, 20, 3)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [np.int32, np.float32])
+def test_census_step_with_observation(hb, shape, dtype):
+    """hk_step_census_obs: the census step with the fused observation.  Games at rest get their constant
+    observation from the census byte, games in play run the feature code — every row of `obs` must equal the
+    oracle's features of the new state after EVERY step of a whole rollout, for the three sorted modes, host and
+    agent form (coordinates appended), with and without rescaling, with caller rewrites in between."""
+    from hironaka_b200 import ops
+    from hironaka_b200._lib import HironakaB200Error
+    B, N, d = shape
+    rng = np.random.default_rng(B + 7)
+    T = 12
+    x0 = random_state(rng, B, N, d, max_value=9, dead_frac=0.4, dup_frac=0.1).astype(dtype)
+    x0[::5] = -1
+    x0[1::5, 1:] = -1
+    x0[1::5, 0] = np.abs(x0[1::5, 0])
+    ncls = 2 ** d - d - 1
+    op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    for fflags, with_coord in ((O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, False), (O.F_OBS_SORT_LEX | O.F_OBS_RESCALE, True),
+                               (O.F_OBS_SORT_COORD0, False), (1 << 12, True)):
+        flags = O.F_ACT_DISCRETE | fflags
+        o = x0.copy()
+        g = dev(x0)
+        census = ops.new_census(g)
+        for t in range(T):
+            ha = rng.integers(0, ncls, B).astype(np.int32)
+            ax = rng.integers(0, d, B).astype(np.int32)
+            oc = rng.integers(0, ncls, B).astype(np.int32) if with_coord else None
+            o, od, orw, _ = cport.step(o, ha, ax, op_bits, flags)
+            r = ops.step(g, dev(ha), dev(ax), ops=op_bits, flags=flags, inplace=True, want_done=True, want_reward=True,
+                         want_obs=True, obs_coord=None if oc is None else dev(oc), census=census)
+            assert np.array_equal(g.cpu().numpy(), o), (fflags, t)
+            assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)) and np.array_equal(r.reward.cpu().numpy(), orw)
+            assert np.array_equal(r.obs.cpu().numpy(), cport.features(o, flags, obs_coord=oc)), (fflags, with_coord, t)
+            if t == 5:
+                idx = rng.permutation(B)[:max(1, B // 20)]
+                fresh = random_state(rng, len(idx), N, d, max_value=600, dead_frac=0.3).astype(dtype)  # values past the pack border
+                o[idx] = fresh
+                ti = torch.from_numpy(idx).cuda()
+                g[ti] = dev(fresh)
+                census[ti] = 0
+    with pytest.raises(HironakaB200Error):  # an unsorted observation of a game at rest is not a constant
+        ops.step(dev(x0), dev(np.zeros(B, np.int32)), dev(np.zeros(B, np.int32)), ops=op_bits, flags=O.F_ACT_DISCRETE,
+                 inplace=True, want_obs=True, census=ops.new_census(dev(x0)))

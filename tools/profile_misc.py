@@ -66,5 +66,28 @@ elif mode == "obs_c2":
             assert L.hk_step(x.data_ptr(), x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), rew.data_ptr(),
                              None, obs.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32, OPS, fl, -1.0, 1e8, stream) == 0
     print(json.dumps({mode + "_ms_per_20_steps": timed(run)}))
+elif mode == "obs_census_c2":
+    obs = torch.empty((B, N * d), dtype=torch.float32, device=dev)
+    done = torch.empty(B, dtype=torch.uint8, device=dev)
+    rew = torch.empty(B, dtype=torch.float32, device=dev)
+    census = torch.zeros(L.hk_census_bytes(B, N, d), dtype=torch.uint8, device=dev)
+    fl = C.HK_F_ACT_DISCRETE | C.HK_F_OBS_SORT_LEX | C.HK_F_OBS_RESCALE
+    per = []
+
+    def run():
+        census.zero_()
+        assert L.hk_step_census(x.data_ptr(), None, None, None, None, None, None, census.data_ptr(), None, None, B, N, d,
+                                C.HK_DTYPE_I32, C.HK_OP_NEWTON | C.HK_OP_REPOSITION, 0, -1.0, 1e8, stream) == 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+        ev[0].record()
+        for t in range(T):
+            assert L.hk_step_census_obs(x.data_ptr(), ha[t].data_ptr(), ax[t].data_ptr(), done.data_ptr(), None, rew.data_ptr(),
+                                        None, obs.data_ptr(), None, census.data_ptr(), None, None, B, N, d, C.HK_DTYPE_I32, OPS,
+                                        fl, -1.0, 1e8, stream) == 0
+            ev[t + 1].record()
+        torch.cuda.synchronize()
+        per.append([round(ev[t].elapsed_time(ev[t + 1]), 4) for t in range(T)])
+    tt = timed(run)
+    print(json.dumps({mode + "_ms_per_20_steps(+root)": tt, "by_step": per[-1], "mean_ms": float(np.mean(per[-1]))}))
 else:
     raise SystemExit("unknown mode")

@@ -842,3 +842,36 @@ def test_census_step_with_observation(hb, shape, dtype):
     with pytest.raises(HironakaB200Error):  # an unsorted observation of a game at rest is not a constant
         ops.step(dev(x0), dev(np.zeros(B, np.int32)), dev(np.zeros(B, np.int32)), ops=op_bits, flags=O.F_ACT_DISCRETE,
                  inplace=True, want_obs=True, census=ops.new_census(dev(x0)))
+
+
+@pytest.mark.parametrize("shape", [(3001, 20, 3), (1001, 10, 3), (600, 64, 5)], ids=lambda s: "x".join(map(str, s)))
+def test_census_step_unaligned_buffers(hb, shape):
+    """The census step on a state that is only 4-byte aligned and a census that is only 1-byte aligned: the bulk /
+    cp.async fast paths must step aside for the word and byte copies, with the same results."""
+    from hironaka_b200 import ops
+    from hironaka_b200._lib import check, lib
+    B, N, d = shape
+    rng = np.random.default_rng(B)
+    x0 = random_state(rng, B, N, d, max_value=9, dead_frac=0.4).astype(np.int32)
+    buf = torch.zeros(B * N * d + 1, dtype=torch.int32, device="cuda")
+    g = buf[1:].view(B, N, d)
+    g.copy_(dev(x0))
+    assert g.data_ptr() % 16 != 0
+    nbytes = lib().hk_census_bytes(B, N, d)
+    cbuf = torch.zeros(nbytes + 9, dtype=torch.uint8, device="cuda")
+    off = 1 if nbytes == B else 8  # (the live masks after the bytes need their 8-byte alignment)
+    census = cbuf[off:off + nbytes]
+    o = x0
+    ncls = 2 ** d - d - 1
+    op_bits = O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON
+    for t in range(10):
+        ha = rng.integers(0, ncls, B).astype(np.int32)
+        ax = rng.integers(0, d, B).astype(np.int32)
+        o, od, orw, _ = cport.step(o, ha, ax, op_bits, O.F_ACT_DISCRETE)
+        dn = torch.empty(B, dtype=torch.uint8, device="cuda")
+        rw = torch.empty(B, dtype=torch.float32, device="cuda")
+        check(lib().hk_step_census(g.data_ptr(), dev(ha).data_ptr(), dev(ax).data_ptr(), dn.data_ptr(), None, rw.data_ptr(), None,
+                                   census.data_ptr(), None, None, B, N, d, 0, op_bits, O.F_ACT_DISCRETE, -1.0, 1e8,
+                                   torch.cuda.current_stream().cuda_stream))
+        assert np.array_equal(g.cpu().numpy(), o), t
+        assert np.array_equal(dn.cpu().numpy(), od) and np.array_equal(rw.cpu().numpy(), orw), t

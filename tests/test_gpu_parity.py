@@ -870,7 +870,8 @@ def test_census_step_unaligned_buffers(hb, shape):
         o, od, orw, _ = cport.step(o, ha, ax, op_bits, O.F_ACT_DISCRETE)
         dn = torch.empty(B, dtype=torch.uint8, device="cuda")
         rw = torch.empty(B, dtype=torch.float32, device="cuda")
-        check(lib().hk_step_census(g.data_ptr(), dev(ha).data_ptr(), dev(ax).data_ptr(), dn.data_ptr(), None, rw.data_ptr(), None,
+        ha_d, ax_d = dev(ha), dev(ax)  # (kept alive: a temporary's block would be handed to the next temporary)
+        check(lib().hk_step_census(g.data_ptr(), ha_d.data_ptr(), ax_d.data_ptr(), dn.data_ptr(), None, rw.data_ptr(), None,
                                    census.data_ptr(), None, None, B, N, d, 0, op_bits, O.F_ACT_DISCRETE, -1.0, 1e8,
                                    torch.cuda.current_stream().cuda_stream))
         assert np.array_equal(g.cpu().numpy(), o), t

@@ -55,8 +55,8 @@ __device__ __forceinline__ int census_class(uint32_t v) {
 // OBS: the instantiation that also builds the observation features of the new state (p.obs, sorted modes only):
 // a game at rest has a CONSTANT observation — its lone point, at the origin, sorts first, the rest is padding — so
 // it is written from the census byte like the other outputs, and only the games in play run the feature code.
-template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false>
-__global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p) {
+template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepParams p) {
     using L = SchedLayout<N, D, WARPS, STAGES, OBS>;
     constexpr int W = L::W;
     constexpr int CHW = (W % 4 == 0) ? 4 : ((W % 2 == 0) ? 2 : 1);  // words per copy piece
@@ -169,72 +169,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
         // games in play are sorted by class and gathered one by one.
         // (with the fused observation the per-game stores of the sorted order cost more: natural order down to a quarter)
         const bool natural = OBS ? (inplay * 4 >= ngames) : (inplay * SCHED_NATURAL_DEN >= ngames * SCHED_NATURAL_NUM);
-        // pass 2: the outputs of the games at rest, from their census bytes
-        for (int k = 0; k < nk; ++k) {
-            const long long g = (tile_of(j0 + k) << 5) + lane;
-            const uint32_t code = clsb[k * 32 + lane];
-            const bool rest = code & 0x80u;
-            const uint32_t v = (code >> 6) & 1u;  // live count of a game at rest
-            if (rest) {
-                if (p.done) p.done[g] = 1;
-                if (p.reward) p.reward[g] = rest_reward;
-                if (p.num_points) p.num_points[g] = (int32_t)v;
-            }
-            const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
-            settled_total += __popc(restmask);
-            if constexpr (OBS) {
-                // (warp-uniform) the constant observation of every game at rest of this tile — unless the tile is about to
-                // be stepped whole in natural order: its observation rows are then stored as one block, these included
-                if (p.obs && restmask && !(natural && ((tilemask >> k) & 1u))) {
-                    // staged in the observation tile like a chunk's rows, then ONE bulk store for a tile that is
-                    // at rest as a whole (the common case late in a rollout), one per game otherwise
-                    float* orow = obs_tile + lane * OW;
-                    bulk_wait_read<0>();  // earlier observation stores have read the tile
-                    __syncwarp();
-                    if (rest) {
-                        const float z = (v & 1u) ? 0.0f : p.pad;  // the lone point, at the origin, sorts first
-                        const uint32_t ocm = p.obs_coord ? action_mask(load_action(p.obs_coord, g, p.flags), p.flags) : 0u;
-                        if ((OW & 3) == 0 && D <= 4 && !p.obs_coord) {
-                            float4* o4 = reinterpret_cast<float4*>(orow);
-                            const float4 padv4 = make_float4(p.pad, p.pad, p.pad, p.pad);
-                            o4[0] = make_float4(z, D > 1 ? z : p.pad, D > 2 ? z : p.pad, D > 3 ? z : p.pad);
-#pragma unroll
-                            for (int q = 1; q < W / 4; ++q) o4[q] = padv4;
-                        } else {
-                            for (int w = 0; w < OW; ++w)
-                                orow[w] = (w < D) ? z : (w < W ? p.pad : (float)((ocm >> (w - W)) & 1u));
-                        }
-                    }
-                    const long long first = g - lane;
-                    const int cnt = (int)((B - first < 32) ? (B - first) : 32);
-                    const uint32_t allmask = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-                    if (obs_bulk) {
-                        fence_async_smem();
-                        __syncwarp();
-                        if (restmask == allmask) {
-                            if (lane == 0) bulk_store(p.obs + first * OW, obs_tile, (uint32_t)(cnt * OW) * 4u);
-                        } else if (rest) {
-                            bulk_store(p.obs + g * OW, orow, (uint32_t)OW * 4u);
-                        }
-                        bulk_commit();
-                    } else {
-                        __syncwarp();
-                        uint32_t m = restmask;
-                        while (m) {
-                            const int r = __ffs((int)m) - 1;
-                            m &= m - 1;
-                            warp_copy_words(reinterpret_cast<uint32_t*>(p.obs + (first + r) * OW),
-                                            reinterpret_cast<uint32_t*>(obs_tile + r * OW), OW, lane);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            // the tile's word of the done mask: the games at rest now, the games that finish in this step later
-            if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
-        }
         __syncwarp();
-        if (inplay == 0) continue;
         // ---- counting sort of the games in play by class: order[] lists them (tile slot * 32 + lane) ----
         int total = 0;
         for (int q = 1; q <= 6 && !natural; ++q) {
@@ -327,10 +262,80 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             cp_async_commit();
         };
 
-        long long g_cur, g_nxt = 0;
-        bool v_cur, v_nxt = false;
-        chunk_game(0, g_cur, v_cur);
-        gather(g_cur, v_cur, stages, 0);
+        // the first chunk is requested BEFORE the outputs of the games at rest are written: pass 2 runs in the shadow of
+        // that load's DRAM latency (late in a rollout a warp has one short chunk: the load was the longest wait of the step)
+        long long g_cur = 0, g_nxt = 0;
+        bool v_cur = false, v_nxt = false;
+        if (inplay) {
+            chunk_game(0, g_cur, v_cur);
+            gather(g_cur, v_cur, stages, 0);
+        }
+        // pass 2: the outputs of the games at rest, from their census bytes
+        for (int k = 0; k < nk; ++k) {
+            const long long g = (tile_of(j0 + k) << 5) + lane;
+            const uint32_t code = clsb[k * 32 + lane];
+            const bool rest = code & 0x80u;
+            const uint32_t v = (code >> 6) & 1u;  // live count of a game at rest
+            if (rest) {
+                if (p.done) p.done[g] = 1;
+                if (p.reward) p.reward[g] = rest_reward;
+                if (p.num_points) p.num_points[g] = (int32_t)v;
+            }
+            const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
+            settled_total += __popc(restmask);
+            if constexpr (OBS) {
+                // (warp-uniform) the constant observation of every game at rest of this tile — unless the tile is about to
+                // be stepped whole in natural order: its observation rows are then stored as one block, these included
+                if (p.obs && restmask && !(natural && ((tilemask >> k) & 1u))) {
+                    // staged in the observation tile like a chunk's rows, then ONE bulk store for a tile that is
+                    // at rest as a whole (the common case late in a rollout), one per game otherwise
+                    float* orow = obs_tile + lane * OW;
+                    bulk_wait_read<0>();  // earlier observation stores have read the tile
+                    __syncwarp();
+                    if (rest) {
+                        const float z = (v & 1u) ? 0.0f : p.pad;  // the lone point, at the origin, sorts first
+                        const uint32_t ocm = p.obs_coord ? action_mask(load_action(p.obs_coord, g, p.flags), p.flags) : 0u;
+                        if ((OW & 3) == 0 && D <= 4 && !p.obs_coord) {
+                            float4* o4 = reinterpret_cast<float4*>(orow);
+                            const float4 padv4 = make_float4(p.pad, p.pad, p.pad, p.pad);
+                            o4[0] = make_float4(z, D > 1 ? z : p.pad, D > 2 ? z : p.pad, D > 3 ? z : p.pad);
+#pragma unroll
+                            for (int q = 1; q < W / 4; ++q) o4[q] = padv4;
+                        } else {
+                            for (int w = 0; w < OW; ++w)
+                                orow[w] = (w < D) ? z : (w < W ? p.pad : (float)((ocm >> (w - W)) & 1u));
+                        }
+                    }
+                    const long long first = g - lane;
+                    const int cnt = (int)((B - first < 32) ? (B - first) : 32);
+                    const uint32_t allmask = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+                    if (obs_bulk) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (restmask == allmask) {
+                            if (lane == 0) bulk_store(p.obs + first * OW, obs_tile, (uint32_t)(cnt * OW) * 4u);
+                        } else if (rest) {
+                            bulk_store(p.obs + g * OW, orow, (uint32_t)OW * 4u);
+                        }
+                        bulk_commit();
+                    } else {
+                        __syncwarp();
+                        uint32_t m = restmask;
+                        while (m) {
+                            const int r = __ffs((int)m) - 1;
+                            m &= m - 1;
+                            warp_copy_words(reinterpret_cast<uint32_t*>(p.obs + (first + r) * OW),
+                                            reinterpret_cast<uint32_t*>(obs_tile + r * OW), OW, lane);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // the tile's word of the done mask: the games at rest now, the games that finish in this step later
+            if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
+        }
+        __syncwarp();
+        if (inplay == 0) continue;
         for (int v = 0; v < nchunks; ++v) {
             const int sidx = (STAGES == 1) ? 0 : (v & 1);
             uint32_t* stage = stages + sidx * L::STAGE_WORDS;
@@ -342,6 +347,14 @@ __global__ void __launch_bounds__(WARPS * 32) hk_sched_kernel(const StepParams p
             ls.ax = 0;
             ls.origin = false;
             if (ls.shift) load_actions(p, p.flags, ls.g, 0, ls.ha, ls.ax);
+            if constexpr (STAGES == 1 && HK_L2_PREFETCH) {
+                // one stage: the next tile cannot be requested before this one has been stored, but it can wait in L2
+                if (bulk && natural && tiles_left && lane == 0) {
+                    const long long tn = tile_of(j0 + (__ffs((int)tiles_left) - 1));
+                    const long long left = B - (tn << 5);
+                    bulk_prefetch_l2(gst + (tn << 5) * W, (uint32_t)(left < 32 ? left : 32) * (uint32_t)(W * 4));
+                }
+            }
             if (bulk) {  // this chunk's games have landed (they were requested one chunk ago)
                 mbar_wait(&bar[sidx], (phase_bits >> sidx) & 1u);
                 phase_bits ^= (1u << sidx);

@@ -5,11 +5,11 @@
 namespace hk {
 namespace {
 
-template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false>
+template <typename T, int N, int D, int WARPS, int STAGES, bool OBS = false, int MINB = 1>
 int launch_sched_geom(const StepParams& p, int dev, cudaStream_t stream) {
     using L = SchedLayout<N, D, WARPS, STAGES, OBS>;
     static KernelFacts facts;
-    auto kernel = hk_sched_kernel<T, N, D, WARPS, STAGES, OBS>;
+    auto kernel = hk_sched_kernel<T, N, D, WARPS, STAGES, OBS, MINB>;
     cudaError_t err = cudaSuccess;
     const int threads = WARPS * 32;
     const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
@@ -27,6 +27,14 @@ int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
     // with the observation tile: 4 warps x 1 stage (12 warps per SM), as the step + features kernel of K-small
     if constexpr (OBS) return launch_sched_geom<T, N, D, 4, 1, true>(p, dev, stream);
     // geometry (warps per CTA x stages per warp): see DESIGN.md "K-sched"; hk_debug_set_sched_geometry switches it
+    if constexpr (!Elem<T>::is_float) {
+        // int32 state steps on packed rows (hk_small.cuh, tier_packed): few registers in the hot path, so the kernel is
+        // held to 128 registers (4 CTAs of 4 warps per SM, one stage each: 16 warps per SM against 12 with two stages)
+        switch (sched_geometry()) {
+            case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
+            default: return launch_sched_geom<T, N, D, 4, 1, false, 4>(p, dev, stream);
+        }
+    }
     switch (sched_geometry()) {
         case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
         default: return launch_sched_geom<T, N, D, 4, 2>(p, dev, stream);

@@ -395,8 +395,8 @@ __host__ __device__ constexpr int next_lower_tier(int K) {
 // (T, or earlier when every game of the warp fits the next lower tier).  The lane's game area in
 // shared memory (`row`) holds the current state on entry and on exit.
 template <typename T, int N, int D, int K, bool POLICY>
-__device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, const T (&x)[N * D],
-                                          uint32_t lm, int st, bool& exceed, bool& chg) {
+__device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, uint32_t* row, uint32_t lm, int st,
+                                          bool& exceed, bool& chg) {
     const long long B = p.B;
     const T padv = Elem<T>::pad(p.pad);
     const bool mutate = p.ops != 0;
@@ -409,8 +409,12 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
     int idx[K];
     uint32_t clm = 0, cvalid = 0;
     if constexpr (K == N) {
+        // (read again from the lane's game area: the caller keeps no register copy of the game across the tiers)
+        load_game<T, N * D>(row, y);
+        if constexpr (Elem<T>::is_float) {
 #pragma unroll
-        for (int q = 0; q < N * D; ++q) y[q] = x[q];
+            for (int q = 0; q < N * D; ++q) y[q] = y[q] + 0.0f;
+        }
         clm = lm;
         cvalid = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
     } else {
@@ -519,6 +523,219 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
         }
     }
     return st;
+}
+
+// ---- packed tiers: one 32-bit word per live row -------------------------------------------------------
+// While every live value of the warp's games stays small (after the shift: <= 2^(27/D - 1) - 1, i.e. 255
+// for D = 3 — true for whole warps through the first steps of real play, where the games with many rows
+// are), a row fits ONE word: coordinate c in a field of FB = 27/D bits at bit 5 + FB c, the field's top bit
+// kept clear as a guard, the row's slot index in the low 5 bits.  Then
+//   * a single unsigned sort of the K words (sorting network, two min/max per compare-exchange) orders the
+//     rows so that a row can only be dominated by rows BEFORE it: x_j <= x_i componentwise and x_j != x_i
+//     implies word_j < word_i whatever the slots, and equal rows sort by slot, so "an equal row with a lower
+//     slot kills" (remove_repeated, _fn.py:192-213) and "a dominating row kills" (_torch_ops.py:8-39,
+//     _jax_ops.py:32-73) become ONE rule: row b dies iff some row a < b (sorted order) has x_a <= x_b;
+//   * that test is one subtraction: (word_b | guards | 31) - word_a keeps every guard bit iff no field
+//     borrows, i.e. iff x_a <= x_b in every coordinate: K (K - 1) / 2 pairs of 2.5 instructions each (IADD,
+//     LOP3, half a three-input minimum) against K (K - 1) pairs of 5.5 - 7 in the exact tiers;
+//   * reposition (the per-coordinate minima do not depend on the filter) is one subtraction per row.
+// The tier's K words replace 3 K registers, nothing is rolled through shared memory, and the survivors go
+// back to their slots from the index bits.  The vote is warp-uniform; a warp that fails it (large values,
+// negative entries in live rows) has touched nothing and takes the exact tiers.  Single steps of int32
+// state only.
+#ifndef HK_L2_PREFETCH
+#define HK_L2_PREFETCH 0  // (measured, not kept: +5 % on the first steps at 16 warps per SM, -8 % only at 8) one-stage geometries prefetch their next tile into L2 (cp.async.bulk.prefetch.L2)
+#endif
+#ifndef HK_PACKED_TIERS
+#define HK_PACKED_TIERS 1
+#endif
+#ifndef HK_PACKED_ROLLOUT
+#define HK_PACKED_ROLLOUT 0
+#endif
+#ifndef HK_PACKED_MIN
+#define HK_PACKED_MIN 3  // smallest warp maximum of live rows that takes a packed tier
+#endif
+
+template <int N>
+__device__ __forceinline__ void sort_words_asc(uint32_t (&k)[N]) {
+#define HK_CE(i, j)                          \
+    {                                        \
+        const uint32_t a_ = k[i], b_ = k[j]; \
+        k[i] = min(a_, b_);                  \
+        k[j] = max(a_, b_);                  \
+    }
+#include "hk_sortnet.inc"
+#undef HK_CE
+}
+
+template <int D>
+struct PackedRow {
+    static constexpr int FB = 27 / D;
+    static constexpr uint32_t VMAX = (1u << (FB - 1)) - 1u;
+    static constexpr uint32_t FMASK = (1u << FB) - 1u;
+    __host__ __device__ static constexpr uint32_t guards() {
+        uint32_t g = 0;
+        for (int c = 0; c < D; ++c) g |= 1u << (5 + FB * c + FB - 1);
+        return g;
+    }
+};
+
+// One step (p.T == 1, ops include the Newton filter) of the tile on K packed rows, K >= the warp's largest
+// live count `lmax`.  Returns false, with nothing written, when the values of some game do not pack.
+template <int N, int D, int K>
+__device__ __forceinline__ bool tier_packed(const StepParams& p, LaneState& ls, uint32_t* row, uint32_t lm_in, int lmax, int st,
+                                            bool& exceed, bool& chg) {
+    using P = PackedRow<D>;
+    constexpr uint32_t G = P::guards();
+    const uint32_t lm = ls.valid ? lm_in : 0u;  // a lane without a game to step gathers and scatters nothing
+    const int cnt0 = __popc(lm);
+    // The shift and the packing are ONE multiply-add chain per row: with the chosen coordinates S and the axis a,
+    //   word = slot + sum_c x_c * M_c,   M_c = [c != a] 2^sh(c) + [c in S] 2^sh(a)   (shift applied)
+    //                                    M_c = 2^sh(c)                               (no shift),
+    // the M_c per-game constants.  The row sum s = sum_{c in S} x_c is formed beside it for the vote and the minima.
+    uint32_t M[D], csel[D];
+    const int ax = ls.ax;
+    bool apply = false;
+    {
+        uint32_t cm = 0;
+        if (p.ops & HK_OP_SHIFT) {
+            cm = action_mask(ls.ha, p.flags);
+            apply = (ax >= 0) && (ax < D);
+            if (p.flags & HK_F_NOOP_INVALID) apply = apply && ((cm >> (ax & 31)) & 1u);
+            if (p.flags & HK_F_FREEZE_ENDED) apply = apply && (cnt0 >= 2);
+        }
+        const uint32_t into = apply ? (1u << (5 + P::FB * ax)) : 0u;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            csel[c] = apply ? ((cm >> c) & 1u) : 0u;
+            M[c] = ((apply && c == ax) ? 0u : (1u << (5 + P::FB * c))) + csel[c] * into;
+        }
+    }
+    constexpr int KLOW = (K > 12) ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0));  // the tier below: lmax > KLOW
+    uint32_t w[K];
+    uint32_t uor = 0, orig0 = 0, orig_hi = 0;
+    uint32_t mn[D], mns = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < D; ++c) mn[c] = 0xffffffffu;
+    {
+        uint32_t m = lm;
+        int i = 0;
+        uint32_t pa[D], ps = 0xffffffffu;  // the previous row (the minima take rows in pairs: one three-input minimum each)
+#pragma unroll
+        for (int c = 0; c < D; ++c) pa[c] = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k >= KLOW && k >= lmax) {  // (warp-uniform) past the warp's largest live count: parked in every lane
+                w[k] = 0xffffffffu;
+                continue;
+            }
+            // compact rows fill from 0; past the last live row the last one is read again (its values change
+            // neither the vote nor the minima) and the word is parked above every live word
+            const bool v = m != 0;
+            i = v ? (__ffs((int)m) - 1) : i;
+            m &= m - 1;
+            uint32_t a[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) a[c] = row[i * D + c];
+            if (k == 0) {  // the first row as it was (a value that does not fit its field counts as moved)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    orig0 += a[c] << (5 + P::FB * c);
+                    orig_hi |= a[c];
+                }
+            }
+            uint32_t q = (uint32_t)i, sum = 0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                q += a[c] * M[c];
+                sum += a[c] * csel[c];
+                uor |= a[c];
+            }
+            uor |= sum;
+            if (k & 1) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) mn[c] = __vimin3_u32(mn[c], pa[c], a[c]);
+                mns = __vimin3_u32(mns, ps, sum);
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; ++c) pa[c] = a[c];
+                ps = sum;
+            }
+            w[k] = v ? q : 0xffffffffu;
+        }
+        // (an odd row count: the last row is still pending)
+#pragma unroll
+        for (int c = 0; c < D; ++c) mn[c] = min(mn[c], pa[c]);
+        mns = min(mns, ps);
+    }
+    // every value of the game, before and after the shift, fits a field (the OR of values <= 2^n - 1 is <= 2^n - 1)
+    if (!__all_sync(0xffffffffu, cnt0 == 0 || uor <= P::VMAX)) return false;
+    if (p.ops & HK_OP_REPOSITION) {
+        uint32_t pm = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) pm += ((apply && c == ax) ? mns : mn[c]) << (5 + P::FB * c);
+        pm = cnt0 ? pm : 0u;
+        // (parked words keep their top guard: every field stays >= 2^(FB-1), above every live word)
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] -= pm;
+    }
+    sort_words_asc<K>(w);
+    // the lone row of an ended game, before and after: everything else counts as changed
+    const bool lone_moved = (((w[0] ^ orig0) >> 5) != 0) || (orig_hi > P::VMAX);
+    uint32_t kill = 0;
+#pragma unroll
+    for (int b = 1; b < K; ++b) {
+        if (b < lmax) {  // (warp-uniform) rows past the warp's largest live count are parked in every lane
+            const uint32_t pb = w[b] | (G | 31u);
+            uint32_t acc = 0xffffffffu;
+#pragma unroll
+            for (int a = 0; a + 1 < b; a += 2) acc = __vimin3_u32(acc, ~(pb - w[a]) & G, ~(pb - w[a + 1]) & G);
+            if (b & 1) acc = min(acc, ~(pb - w[b - 1]) & G);
+            kill |= (acc == 0u) ? (1u << b) : 0u;
+        }
+    }
+    const uint32_t live0 = (cnt0 >= 32) ? 0xffffffffu : ((1u << cnt0) - 1u);
+    const uint32_t alive = live0 & ~kill;
+    const int cnt = __popc(alive);
+    const bool prev_done = cnt0 < 2, dn = cnt < 2;
+    if (ls.valid) {
+        if (p.done) p.done[(long long)st * p.B + ls.g] = dn ? 1 : 0;
+        if (p.reward) {
+            const float r = (dn && !prev_done) ? 1.0f : 0.0f;
+            p.reward[(long long)st * p.B + ls.g] = (p.flags & HK_F_ROLE_AGENT) ? -r : r;
+        }
+    }
+    if (p.done_count) {
+        const int c = __popc(__ballot_sync(0xffffffffu, ls.valid && dn));
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(p.done_count + st, c);
+    }
+    if (dn && !prev_done) ls.len = st + 1;
+    ls.cnt = cnt;
+    ls.origin = (cnt == 0) || (cnt == 1 && (w[0] >> 5) == 0u);
+    const bool gchg = (cnt0 >= 2) || (cnt0 == 1 && lone_moved);
+    chg = chg || gchg;
+    if (p.exceed_flag && st + 1 >= p.T) {
+        uint32_t hi = 0;
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) hi = ((alive >> b) & 1u) ? max(hi, (w[b] >> (5 + P::FB * c)) & P::VMAX) : hi;
+        }
+        exceed = (cnt > 0) && ((float)hi >= p.threshold);
+    }
+    const uint32_t padw = (uint32_t)(int32_t)p.pad;
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+        if (b < lmax) {
+            if (gchg && b < cnt0) {
+                const bool lv = (alive >> b) & 1u;
+                const int i = (int)(w[b] & 31u);
+#pragma unroll
+                for (int c = 0; c < D; ++c) row[i * D + c] = lv ? ((w[b] >> (5 + P::FB * c)) & P::FMASK) : padw;
+            }
+        }
+    }
+    return true;
 }
 
 // Descending sort of N 32-bit keys in registers by a merge-exchange network (tools/gen_sortnet.py):
@@ -886,6 +1103,10 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
     ls.len = -1;
     int st = 0;
     do {
+        bool any_junk = false;
+        uint32_t lm;
+        {
+        // (block scope: the register copy of the game lives for this pass only; the tiers read the lane's game area)
         T x[W];
         load_game<T, W>(row, x);
         if constexpr (Elem<T>::is_float) {
@@ -902,8 +1123,6 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
         // kernels already satisfy that, so the tile is only CHECKED here (a dead row that holds anything
         // else counts as a change of its game) and the rewrite below runs only if some game needs it.
         // One pass yields the live mask (sign of coordinate 0) and the check.
-        bool any_junk = false;
-        uint32_t lm;
         {
             const bool check = mutate && !normalised;
             const uint32_t pbits = (uint32_t)Elem<T>::bits(padv);
@@ -923,6 +1142,7 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
                 any_junk = __any_sync(0xffffffffu, diff != 0);
             }
         }
+        }
         ls.cnt = __popc(lm);
         if (ls.len < 0) ls.len = (ls.cnt < 2) ? 0 : p.T + 1;
         const int lmax = __reduce_max_sync(0xffffffffu, ls.valid ? ls.cnt : 0);
@@ -930,6 +1150,12 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
         auto prestore = [&]() {
             if (mutate && !normalised) {
                 if (any_junk) {
+                    T x[W];
+                    load_game<T, W>(row, x);
+                    if constexpr (Elem<T>::is_float) {
+#pragma unroll
+                        for (int q = 0; q < W; ++q) x[q] = x[q] + 0.0f;
+                    }
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -940,25 +1166,48 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
                 normalised = true;
             }
         };
+        if constexpr (HK_PACKED_TIERS && !Elem<T>::is_float && !POLICY && D == 3) {
+            // (warp-uniform) single steps with the filter: packed rows while the values allow it.  (Measured and not kept
+            // for one-launch rollouts, HK_PACKED_ROLLOUT: the game would go back to the lane's game area after every
+            // packed step and be gathered again for the next one, 1.07 ms per 20-step C2 rollout against 0.64 ms with the
+            // exact tiers, which keep their rows in registers from step to step.)
+            if ((p.ops & HK_OP_NEWTON) && lmax <= 16 &&
+                ((p.T == 1 && lmax >= HK_PACKED_MIN) || (HK_PACKED_ROLLOUT && p.T > 1 && lmax >= 2))) {
+                prestore();
+                int32_t ha_n = 3, ax_n = 0;
+                if (ls.shift && st + 1 < p.T) load_actions(p, p.flags, ls.g, st + 1, ha_n, ax_n);  // the next step's actions
+                bool ok;
+                if (lmax <= 4) ok = tier_packed<N, D, 4>(p, ls, row, lm, lmax, st, exceed, chg);
+                else if (lmax <= 8) ok = tier_packed<N, D, 8>(p, ls, row, lm, lmax, st, exceed, chg);
+                else if (lmax <= 12) ok = tier_packed<N, D, 12>(p, ls, row, lm, lmax, st, exceed, chg);
+                else ok = tier_packed<N, D, 16>(p, ls, row, lm, lmax, st, exceed, chg);
+                if (ok) {
+                    ls.ha = ha_n;
+                    ls.ax = ax_n;
+                    ++st;
+                    continue;
+                }
+            }
+        }
         if (N > 2 && p.T == 1 && lmax <= 2) {  // the tail of a rollout driven step by step: ended games and two-point games only
             prestore();
-            st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, (N > 2 ? 2 : N), POLICY>(p, ls, row, lm, st, exceed, chg);
         } else if (N > 4 && lmax <= 4) {
             prestore();
-            st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, (N > 4 ? 4 : N), POLICY>(p, ls, row, lm, st, exceed, chg);
         } else if (N > 8 && lmax <= 8) {
             prestore();
-            st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, (N > 8 ? 8 : N), POLICY>(p, ls, row, lm, st, exceed, chg);
         } else if (N > 12 && lmax <= 12) {
             if (W % 4 != 0) prestore();
-            st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, (N > 12 ? 12 : N), POLICY>(p, ls, row, lm, st, exceed, chg);
             normalised = normalised || (W % 4 == 0);
         } else if (N > 16 && lmax <= 16) {
             if (W % 4 != 0) prestore();
-            st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, (N > 16 ? 16 : N), POLICY>(p, ls, row, lm, st, exceed, chg);
             normalised = normalised || (W % 4 == 0);
         } else {
-            st = tier_steps<T, N, D, N, POLICY>(p, ls, row, x, lm, st, exceed, chg);
+            st = tier_steps<T, N, D, N, POLICY>(p, ls, row, lm, st, exceed, chg);
             normalised = true;
         }
     } while (st < p.T);
@@ -1042,6 +1291,11 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
             load_actions(p, p.flags, ls.g, 0, ls.ha, ls.ax);
         }
 
+        if constexpr (SMALL_STAGES == 1 && HK_L2_PREFETCH) {
+            // one stage: this stage's next tile cannot be requested before this one has been stored, but it can wait in L2
+            if (lane == 0 && t + nw < ntiles && tile_tma(t + nw))
+                bulk_prefetch_l2(gin + (t + nw) * (long long)L::TILE_WORDS, (uint32_t)tile_words(t + nw) * 4u);
+        }
         if (tma) {
             mbar_wait(&bar[s], (phase_bits >> s) & 1u);
             phase_bits ^= (1u << s);

@@ -876,3 +876,71 @@ def test_census_step_unaligned_buffers(hb, shape):
                                    torch.cuda.current_stream().cuda_stream))
         assert np.array_equal(g.cpu().numpy(), o), t
         assert np.array_equal(dn.cpu().numpy(), od) and np.array_equal(rw.cpu().numpy(), orw), t
+
+
+@pytest.mark.parametrize("N", [5, 10, 20])
+def test_packed_tier_borders(hb, N):
+    """Single steps of int32 state take the packed tiers of the thread-per-game kernels while every live value of a
+    warp's games fits one field after the shift (<= 255 for d = 3) and the exact tiers otherwise: values that
+    straddle that border warp by warp and game by game, sums that land on 255 / 256, duplicates of every
+    multiplicity, negative entries in live rows (never packed; filter-only calls), games with 0 / 1 / all rows live, junk in dead
+    rows, both flavours, with and without reposition, with the exceed flag and with the census."""
+    from hironaka_b200 import ops
+    B, d = 4099, 3
+    rng = np.random.default_rng(255 + N)
+    ncls = 2 ** d - d - 1
+    for trial, (ops_bits, flags) in enumerate([
+        (O.OP_SHIFT | O.OP_REPOSITION | O.OP_NEWTON, O.F_ACT_DISCRETE),
+        (O.OP_SHIFT | O.OP_NEWTON, TORCH_FLAGS | O.F_ACT_DISCRETE | O.F_ROLE_AGENT),
+        (O.OP_SHIFT | O.OP_NEWTON, 0),
+        (O.OP_REPOSITION | O.OP_NEWTON, 0),
+        (O.OP_NEWTON, 0),
+    ]):
+        x = np.empty((B, N, d), np.int32)
+        # per warp of 32 games a value scale: tiny, just below the border (85 * 3 = 255), just above, large
+        scale = np.repeat(rng.choice([3, 20, 85, 86, 128, 255, 256, 300, 70000], (B + 31) // 32), 32)[:B]
+        x[:] = rng.integers(0, scale[:, None, None] + 1, (B, N, d))
+        x[rng.random(B) < 0.3] //= 7                                  # small games inside large-valued warps
+        hi = rng.random(B) < 0.15                                     # whole rows at the scale itself: sums on the border
+        x[hi, : max(1, N // 2)] = scale[hi, None, None]
+        dup = rng.integers(0, N, (B, 4))
+        for k in range(3):                                            # duplicates, up to four copies of a row
+            x[np.arange(B), dup[:, k + 1]] = x[np.arange(B), dup[:, 0]]
+        dead = rng.random((B, N)) < rng.choice([0.0, 0.3, 0.7, 0.95], B)[:, None]
+        x[dead] = -1
+        x[dead & (rng.random((B, N)) < 0.2)] = -9                     # junk in dead rows
+        x[::97] = -1                                                  # empty games
+        if not ops_bits & O.OP_SHIFT:                                 # a negative entry in a live row (a shift could make
+            neg = np.arange(B) % 53 == 7                              # coordinate 0 negative: not a state of the game)
+            x[neg, 0, 0] = 4
+            x[neg, 0, 1] = -2
+        if flags & O.F_ACT_DISCRETE:
+            ha = rng.integers(0, ncls, B)
+        else:
+            ha = rng.integers(0, 2 ** d, B)
+        ax = rng.integers(0, d, B)
+        got = run_step(hb, x, ha, ax, ops_bits, flags)
+        exp = cport.step(x, ha, ax, ops_bits, flags)
+        assert np.array_equal(got[0], exp[0]), (trial, "state")
+        assert np.array_equal(got[1], exp[1].astype(bool)), (trial, "done")
+        assert np.array_equal(got[2], exp[2]), (trial, "reward")
+        assert np.array_equal(got[3], exp[3]), (trial, "num_points")
+        # the exceed flag at a threshold inside the packed range, and the census route on the same inputs
+        for thr in (40.0, 1e9):
+            flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            ops.step(dev(x), dev(ha.astype(np.int32)), dev(ax.astype(np.int32)), ops=ops_bits, flags=flags, inplace=True,
+                     exceed_flag=flag, value_threshold=thr)
+            live = exp[0][:, :, 0] >= 0
+            assert bool(flag.item()) == bool((exp[0][live] >= thr).any()), (trial, thr)
+        g = dev(x)
+        census = ops.new_census(g)
+        o = x
+        for t in range(3):
+            ha = rng.integers(0, ncls if flags & O.F_ACT_DISCRETE else 2 ** d, B).astype(np.int32)
+            ax = rng.integers(0, d, B).astype(np.int32)
+            o, od, orw, onp = cport.step(o, ha, ax, ops_bits, flags)
+            r = ops.step(g, dev(ha), dev(ax), ops=ops_bits, flags=flags, inplace=True, want_done=True, want_reward=True,
+                         want_num_points=True, census=census)
+            assert np.array_equal(g.cpu().numpy(), o), (trial, t, "census state")
+            assert np.array_equal(r.done.cpu().numpy(), od.astype(bool)) and np.array_equal(r.num_points.cpu().numpy(), onp)
+            assert np.array_equal(r.reward.cpu().numpy().view(np.int32), orw.view(np.int32))

@@ -24,6 +24,10 @@
 namespace hk {
 
 constexpr int SCHED_ROUND_TILES = 32;  // tiles (of 32 games) a warp schedules together
+#ifndef SCHED_PASS_UNROLL
+#define SCHED_PASS_UNROLL 2
+#endif
+constexpr int kSchedPassUnroll = SCHED_PASS_UNROLL;
 #ifndef SCHED_TILE_GROUP
 #define SCHED_TILE_GROUP 0  // 0: a warp owns one contiguous run of tiles; G > 0: runs of G tiles, dealt round-robin to the warps
 #endif
@@ -149,7 +153,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             }
             __syncwarp();
         }
-        // pass 1: class of every game (0 = at rest or no such game), what is in play
+        // pass 1: class of every game (0 = at rest or no such game), what is in play; without the fused observation
+        // also the outputs of the games at rest, from their census bytes (with it they are a second pass, below, that
+        // knows which tiles are about to be stepped whole).  Late in a rollout this loop IS the step (a warp walks its
+        // tiles, finds a handful of games in play): unrolled by two so that the tiles' dependency chains interleave.
+#pragma unroll kSchedPassUnroll
         for (int k = 0; k < nk; ++k) {
             const long long g = (tile_of(j0 + k) << 5) + lane;
             const bool valid = g < B;
@@ -162,6 +170,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             inplay += __popc(play);
             ngames += __popc(__ballot_sync(0xffffffffu, valid));
             classes |= 1u << c;
+            if constexpr (!OBS) {
+                if (rest) {
+                    if (p.done) p.done[g] = 1;
+                    if (p.reward) p.reward[g] = rest_reward;
+                    if (p.num_points) p.num_points[g] = (int32_t)(v & 1u);
+                }
+                const uint32_t restmask = __ballot_sync(0xffffffffu, rest);
+                settled_total += __popc(restmask);
+                // the tile's word of the done mask: the games at rest now, the games that finish in this step later
+                if (p.done_bits && lane == 0) p.done_bits[tile_of(j0 + k)] = restmask;
+            }
         }
         classes = __reduce_or_sync(0xffffffffu, classes) & ~1u;
         // While most games are still in play the tiles are stepped whole, in natural order: one bulk copy per
@@ -172,7 +191,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
         __syncwarp();
         // ---- counting sort of the games in play by class: order[] lists them (tile slot * 32 + lane) ----
         int total = 0;
-        for (int q = 1; q <= 6 && !natural; ++q) {
+        if (!natural && inplay <= 32) {  // one chunk whatever the order: a single compaction pass
+#pragma unroll kSchedPassUnroll
+            for (int k = 0; k < nk; ++k) {
+                if (!((tilemask >> k) & 1u)) continue;
+                const bool m = (clsb[k * 32 + lane] & 7u) != 0u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                if (m) order[total + __popc(bal & lt)] = (uint16_t)(k * 32 + lane);
+                total += __popc(bal);
+            }
+        }
+        for (int q = 1; q <= 6 && !natural && inplay > 32; ++q) {
             if (!((classes >> q) & 1u)) continue;
             for (int k = 0; k < nk; ++k) {
                 if (!((tilemask >> k) & 1u)) continue;
@@ -270,8 +299,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             chunk_game(0, g_cur, v_cur);
             gather(g_cur, v_cur, stages, 0);
         }
-        // pass 2: the outputs of the games at rest, from their census bytes
-        for (int k = 0; k < nk; ++k) {
+        // pass 2 (fused observation only): the outputs of the games at rest, from their census bytes
+        for (int k = 0; OBS && k < nk; ++k) {
             const long long g = (tile_of(j0 + k) << 5) + lane;
             const uint32_t code = clsb[k * 32 + lane];
             const bool rest = code & 0x80u;

@@ -25,9 +25,10 @@ int launch_sched_geom(const StepParams& p, int dev, cudaStream_t stream) {
 template <typename T, int N, int D, bool OBS>
 int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
     // with the observation tile: 4 warps x 1 stage (12 warps per SM), as the step + features kernel of K-small
-    if constexpr (OBS) return launch_sched_geom<T, N, D, 4, 1, true>(p, dev, stream);
+    // (held to 3 CTAs per SM: with the packed tiers ptxas would take 242 registers and leave room for two)
+    if constexpr (OBS) return launch_sched_geom<T, N, D, 4, 1, true, Elem<T>::is_float ? 1 : 3>(p, dev, stream);
     // geometry (warps per CTA x stages per warp): see DESIGN.md "K-sched"; hk_debug_set_sched_geometry switches it
-    if constexpr (!Elem<T>::is_float) {
+    else if constexpr (!Elem<T>::is_float) {
         // int32 state steps on packed rows (hk_small.cuh, tier_packed): few registers in the hot path, so the kernel is
         // held to 128 registers (4 CTAs of 4 warps per SM, one stage each: 16 warps per SM against 12 with two stages)
         switch (sched_geometry()) {
@@ -35,9 +36,11 @@ int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
             default: return launch_sched_geom<T, N, D, 4, 1, false, 4>(p, dev, stream);
         }
     }
-    switch (sched_geometry()) {
-        case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
-        default: return launch_sched_geom<T, N, D, 4, 2>(p, dev, stream);
+    else {
+        switch (sched_geometry()) {
+            case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
+            default: return launch_sched_geom<T, N, D, 4, 2>(p, dev, stream);
+        }
     }
 }
 

@@ -1093,7 +1093,7 @@ __device__ __noinline__ void features_rolled(const uint32_t* row, uint32_t lm, i
 // On return `row` holds the new state, ls.cnt / ls.len / ls.origin describe it, `chg` says whether the
 // game must be written back.  Shared by the tile-ring kernel below and the census-scheduled kernel
 // (hk_sched.cuh).
-template <typename T, int N, int D, bool POLICY>
+template <typename T, int N, int D, bool POLICY, bool PACKED = true>
 __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneState& ls, uint32_t* row, bool& exceed,
                                                    bool& chg) {
     constexpr int W = N * D;
@@ -1166,7 +1166,7 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
                 normalised = true;
             }
         };
-        if constexpr (HK_PACKED_TIERS && !Elem<T>::is_float && !POLICY && D == 3) {
+        if constexpr (HK_PACKED_TIERS && PACKED && !Elem<T>::is_float && !POLICY && D == 3) {
             // (warp-uniform) single steps with the filter: packed rows while the values allow it.  (Measured and not kept
             // for one-launch rollouts, HK_PACKED_ROLLOUT: the game would go back to the lane's game area after every
             // packed step and be gathered again for the next one, 1.07 ms per 20-step C2 rollout against 0.64 ms with the
@@ -1219,7 +1219,9 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* dst, const uint32_t* s
     for (int w = lane; w < words; w += 32) dst[w] = src[w];
 }
 
-template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES>
+// PACKED = false: the instantiation of the one-launch rollouts (p.T > 1), which never take the packed tiers and are bound
+// by instruction fetch: they do not carry that code
+template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES, bool PACKED = true>
 __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p) {
     using L = SmallLayout<N, D, OBS, WARPS, STAGES>;
     constexpr int SMALL_WARPS = WARPS;
@@ -1308,7 +1310,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         // Did this lane's game change?  Unchanged games of an in-place call are not written back
         // (everything is when out != in).
         bool chg = !inplace;
-        small_process_tile<T, N, D, POLICY>(p, ls, row, exceed, chg);
+        small_process_tile<T, N, D, POLICY, PACKED>(p, ls, row, exceed, chg);
 
         if (ls.valid) {
             if (p.num_points) p.num_points[ls.g] = ls.cnt;

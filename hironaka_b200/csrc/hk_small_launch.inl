@@ -18,11 +18,11 @@ struct SmallTune {
     static constexpr int STAGES = 1;
 };
 
-template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES>
+template <typename T, int N, int D, bool OBS, bool POLICY, int WARPS, int STAGES, bool PACKED = true>
 int launch_small_geom(const StepParams& p, int dev, cudaStream_t stream) {
     using L = SmallLayout<N, D, OBS, WARPS, STAGES>;
     static KernelFacts facts;
-    auto kernel = hk_small_kernel<T, N, D, OBS, POLICY, WARPS, STAGES>;
+    auto kernel = hk_small_kernel<T, N, D, OBS, POLICY, WARPS, STAGES, PACKED>;
     cudaError_t err = cudaSuccess;
     const int threads = WARPS * 32;
     const int per_sm = kernel_ctas_per_sm(kernel, facts, dev, threads, L::SMEM_BYTES, &err);
@@ -57,7 +57,8 @@ int launch_small_shape(const StepParams& p, int dev, cudaStream_t stream) {
     // issue rate, not by bytes in flight: one stage per warp and twice the warps
     // (tools/tune_small.cu: 8x1 = 0.648 ms, 4x1 = 0.661, 4x2 = 0.733, 4x3 = 0.808 per 20-step rollout).
     if constexpr (!OBS) {
-        if (p.T > 1) return launch_small_geom<T, N, D, false, POLICY, 8, 1>(p, dev, stream);
+        // (its own instantiation without the packed tiers where those exist: int32 state, no fixed players)
+        if (p.T > 1) return launch_small_geom<T, N, D, false, POLICY, 8, 1, Elem<T>::is_float || POLICY>(p, dev, stream);
     }
     return launch_small_geom<T, N, D, OBS, POLICY, SmallTune<N, D, OBS>::WARPS, SmallTune<N, D, OBS>::STAGES>(p, dev, stream);
 }

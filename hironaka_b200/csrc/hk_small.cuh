@@ -1166,7 +1166,11 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
                 normalised = true;
             }
         };
-        if constexpr (HK_PACKED_TIERS && PACKED && !Elem<T>::is_float && !POLICY && D == 3) {
+        // (Measured and not kept: dropping the exact 12- and 16-row tiers from the kernels that have packed ones — 3k
+        // instructions less — sends warps whose values no longer pack, common from the fifth step on, to all N rows:
+        // rollout mean 0.0449 -> 0.0470 ms per step.)
+        constexpr bool HAS_PACKED = HK_PACKED_TIERS && PACKED && !Elem<T>::is_float && !POLICY && D == 3;
+        if constexpr (HAS_PACKED) {
             // (warp-uniform) single steps with the filter: packed rows while the values allow it.  (Measured and not kept
             // for one-launch rollouts, HK_PACKED_ROLLOUT: the game would go back to the lane's game area after every
             // packed step and be gathered again for the next one, 1.07 ms per 20-step C2 rollout against 0.64 ms with the

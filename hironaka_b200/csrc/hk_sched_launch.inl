@@ -33,6 +33,8 @@ int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
         // held to 128 registers (4 CTAs of 4 warps per SM, one stage each: 16 warps per SM against 12 with two stages)
         switch (sched_geometry()) {
             case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
+            // (measured: 3 warps x 6 CTAs and 6 warps x 3 CTAs, 18 warps per SM: ptxas settles on 96 registers with 136 bytes
+            // of stack, 0.0498 - 0.0511 ms per step against 0.0448)
             default: return launch_sched_geom<T, N, D, 4, 1, false, 4>(p, dev, stream);
         }
     }

@@ -35,6 +35,9 @@ int launch_sched_shape(const StepParams& p, int dev, cudaStream_t stream) {
             case 1: return launch_sched_geom<T, N, D, 8, 1>(p, dev, stream);
             // (measured: 3 warps x 6 CTAs and 6 warps x 3 CTAs, 18 warps per SM: ptxas settles on 96 registers with 136 bytes
             // of stack, 0.0498 - 0.0511 ms per step against 0.0448)
+            // (timing experiment with the exact 8/12/16-row tiers compiled out — 11.2k instructions instead of 15.2k, 96
+            // registers with 52 bytes of spills at 20 warps per SM: first steps 135 107 109 107 us, no better than 16 warps
+            // with the full kernel; neither code size nor occupancy is what holds the first steps)
             default: return launch_sched_geom<T, N, D, 4, 1, false, 4>(p, dev, stream);
         }
     }

@@ -611,7 +611,7 @@ __device__ __forceinline__ bool tier_packed(const StepParams& p, LaneState& ls, 
             M[c] = ((apply && c == ax) ? 0u : (1u << (5 + P::FB * c))) + csel[c] * into;
         }
     }
-    constexpr int KLOW = (K > 12) ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0));  // the tier below: lmax > KLOW
+    constexpr int KLOW = (K > 16) ? 16 : ((K > 12) ? 12 : (K > 8 ? 8 : (K > 4 ? 4 : 0)));  // the tier below: lmax > KLOW
     uint32_t w[K];
     uint32_t uor = 0, orig0 = 0, orig_hi = 0;
     uint32_t mn[D], mns = 0xffffffffu;
@@ -1175,7 +1175,7 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
             // for one-launch rollouts, HK_PACKED_ROLLOUT: the game would go back to the lane's game area after every
             // packed step and be gathered again for the next one, 1.07 ms per 20-step C2 rollout against 0.64 ms with the
             // exact tiers, which keep their rows in registers from step to step.)
-            if ((p.ops & HK_OP_NEWTON) && lmax <= 16 &&
+            if ((p.ops & HK_OP_NEWTON) && lmax <= 20 &&
                 ((p.T == 1 && lmax >= HK_PACKED_MIN) || (HK_PACKED_ROLLOUT && p.T > 1 && lmax >= 2))) {
                 prestore();
                 int32_t ha_n = 3, ax_n = 0;
@@ -1184,7 +1184,8 @@ __device__ __forceinline__ void small_process_tile(const StepParams& p, LaneStat
                 if (lmax <= 4) ok = tier_packed<N, D, 4>(p, ls, row, lm, lmax, st, exceed, chg);
                 else if (lmax <= 8) ok = tier_packed<N, D, 8>(p, ls, row, lm, lmax, st, exceed, chg);
                 else if (lmax <= 12) ok = tier_packed<N, D, 12>(p, ls, row, lm, lmax, st, exceed, chg);
-                else ok = tier_packed<N, D, 16>(p, ls, row, lm, lmax, st, exceed, chg);
+                else if (N <= 16 || lmax <= 16) ok = tier_packed<N, D, 16>(p, ls, row, lm, lmax, st, exceed, chg);
+                else ok = tier_packed<N, D, (N > 16 ? 20 : 16)>(p, ls, row, lm, lmax, st, exceed, chg);  // (the root filter of (20,3))
                 if (ok) {
                     ls.ha = ha_n;
                     ls.ax = ax_n;

@@ -27,7 +27,11 @@ OPS = C.HK_OP_SHIFT | C.HK_OP_REPOSITION | C.HK_OP_NEWTON
 ROOT = C.HK_OP_NEWTON | C.HK_OP_REPOSITION
 
 
+root_ms = []
+
+
 def run(census_mode, geometry=0):
+    root_ms.clear()
     L.hk_debug_set_sched_geometry(geometry)
     per = []
     final = None
@@ -35,6 +39,9 @@ def run(census_mode, geometry=0):
         x = x0.clone()
         census = torch.zeros(L.hk_census_bytes(B, N, d), dtype=torch.uint8, device=dev)
         cp = census.data_ptr() if census_mode else None
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
         if census_mode:
             rc = L.hk_step_census(x.data_ptr(), None, None, None, None, None, None, cp, None, None, B, N, d, C.HK_DTYPE_I32, ROOT, 0,
                                   -1.0, 1e8, stream)
@@ -42,7 +49,10 @@ def run(census_mode, geometry=0):
             rc = L.hk_step(x.data_ptr(), x.data_ptr(), None, None, None, None, None, None, None, None, B, N, d,
                            C.HK_DTYPE_I32, ROOT, 0, -1.0, 1e8, stream)
         assert rc == 0, rc
+        r1.record()
         torch.cuda.synchronize()
+        if rep:
+            root_ms.append(r0.elapsed_time(r1))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
         ev[0].record()
         for t in range(T):
@@ -70,11 +80,11 @@ if only.startswith("census"):  # profiling runs: one mode only
     print(json.dumps({only: [round(float(v), 4) for v in per]}))
     sys.exit(0)
 base, xb = run(False)
-out["hk_step"] = {"mean_ms": float(base.mean()), "by_step": [round(float(v), 4) for v in base]}
+out["hk_step"] = {"mean_ms": float(base.mean()), "by_step": [round(float(v), 4) for v in base], "root_filter_ms": round(float(np.mean(root_ms)), 4)}
 for geo in [int(g) for g in os.environ.get('HK_GEOS', '0,1').split(',')]:
     per, xc = run(True, geo)
     assert os.environ.get("HK_NOASSERT") or torch.equal(xc, xb), "census rollout differs from hk_step rollout"
-    out[f"hk_step_census_geometry{geo}"] = {"mean_ms": float(per.mean()), "by_step": [round(float(v), 4) for v in per]}
+    out[f"hk_step_census_geometry{geo}"] = {"mean_ms": float(per.mean()), "by_step": [round(float(v), 4) for v in per], "root_filter_ms": round(float(np.mean(root_ms)), 4)}
 L.hk_debug_set_sched_geometry(0)
 out["workload"] = f"{which}: B={B} N={N} d={d} T={T}"
 print(json.dumps(out))

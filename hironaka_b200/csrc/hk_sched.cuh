@@ -31,6 +31,9 @@ constexpr int kSchedPassUnroll = SCHED_PASS_UNROLL;
 #ifndef SCHED_TILE_GROUP
 #define SCHED_TILE_GROUP 0  // 0: a warp owns one contiguous run of tiles; G > 0: runs of G tiles, dealt round-robin to the warps
 #endif
+#ifndef SCHED_SPECULATE
+#define SCHED_SPECULATE 0  // (measured, not kept: no gain on the first steps, 3-5 % slower in the middle of a rollout) the first tile of a round is requested before the census pass has finished (see pass 1)
+#endif
 #ifndef SCHED_NATURAL_NUM
 #define SCHED_NATURAL_NUM 1  // a round is stepped tile by tile in natural order while at least NUM / DEN of
 #define SCHED_NATURAL_DEN 2  // its games are in play (tools/time_census.py)
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
 #endif
         uint32_t tilemask = 0, classes = 0;
         int inplay = 0, ngames = 0;
+        bool spec = false;  // the round's first tile has been requested ahead of the schedule
         // The round's census bytes are staged in shared memory (the class array doubles as the landing zone):
         // cp.async in 4-byte pieces, 8 lanes per tile, all requests in flight at once, then ONE rolled loop
         // over the tiles (an unrolled register version was 16 KB of straight-line code in a kernel whose hot
@@ -168,8 +172,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             const uint32_t play = __ballot_sync(0xffffffffu, c != 0);
             if (play) tilemask |= 1u << k;
             inplay += __popc(play);
-            ngames += __popc(__ballot_sync(0xffffffffu, valid));
+            const uint32_t vbal = __ballot_sync(0xffffffffu, valid);
+            ngames += __popc(vbal);
             classes |= 1u << c;
+            if constexpr (SCHED_SPECULATE) {
+                // The round's first tile predicts the round: when at least half of ITS games are in play the tile is
+                // requested now, as the natural order would, and the rest of this pass runs in the shadow of that
+                // load (early in a rollout the pass was a bubble of ~3 us in front of every warp's first tile).  A
+                // wrong guess (the round turns out to be sorted) costs one tile of traffic; its arrival is awaited
+                // below before the stage is used again.
+                if (k == 0 && bulk && play && __popc(play) * 2 >= __popc(vbal)) {
+                    spec = true;
+                    const long long first = g - lane;
+                    bulk_wait_read<0>();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(&bar[0], (uint32_t)__popc(vbal) * (uint32_t)(W * 4));
+                        bulk_load(stages, gst + first * W, (uint32_t)__popc(vbal) * (uint32_t)(W * 4), &bar[0]);
+                    }
+                }
+            }
             if constexpr (!OBS) {
                 if (rest) {
                     if (p.done) p.done[g] = 1;
@@ -237,6 +260,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
                 const int cnt = (int)((B - first < 32) ? (B - first) : 32);
                 if (bulk) {
                     bulk_wait_read<0>();
+                    // the lanes wrote this stage with st.shared (results, scratch) and it may not have been stored: order
+                    // those generic-proxy writes before the async-proxy write of the refill
+                    fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         mbar_expect_tx(&bar[sidx], (uint32_t)cnt * (uint32_t)(W * 4));
@@ -259,6 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             if (bulk) {
                 // the lane's own earlier bulk store from this stage must have finished READING it
                 bulk_wait_read<0>();
+                fence_async_smem();  // (as above: earlier st.shared writes of this stage before the async-proxy refill)
                 const int nvalid = __popc(__ballot_sync(0xffffffffu, valid));
                 if (lane == 0) mbar_expect_tx(&bar[sidx], (uint32_t)nvalid * (uint32_t)(W * 4));
                 __syncwarp();
@@ -295,9 +322,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
         // that load's DRAM latency (late in a rollout a warp has one short chunk: the load was the longest wait of the step)
         long long g_cur = 0, g_nxt = 0;
         bool v_cur = false, v_nxt = false;
+        if (spec && !natural) {  // the guess was wrong: let the tile land, then forget it
+            mbar_wait(&bar[0], phase_bits & 1u);
+            phase_bits ^= 1u;
+            spec = false;
+        }
         if (inplay) {
             chunk_game(0, g_cur, v_cur);
-            gather(g_cur, v_cur, stages, 0);
+            if (!spec) gather(g_cur, v_cur, stages, 0);  // (natural order and a good guess: chunk 0 IS the tile in flight)
         }
         // pass 2 (fused observation only): the outputs of the games at rest, from their census bytes
         for (int k = 0; OBS && k < nk; ++k) {

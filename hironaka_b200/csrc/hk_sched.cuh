@@ -31,6 +31,9 @@ constexpr int kSchedPassUnroll = SCHED_PASS_UNROLL;
 #ifndef SCHED_TILE_GROUP
 #define SCHED_TILE_GROUP 0  // 0: a warp owns one contiguous run of tiles; G > 0: runs of G tiles, dealt round-robin to the warps
 #endif
+#ifndef SCHED_DIRECT
+#define SCHED_DIRECT 1  // packed tiers release the stage after the gather and store changed rows straight to global memory
+#endif
 #ifndef SCHED_SPECULATE
 #define SCHED_SPECULATE 0  // (measured, not kept: no gain on the first steps, 3-5 % slower in the middle of a rollout) the first tile of a round is requested before the census pass has finished (see pass 1)
 #endif
@@ -437,7 +440,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             uint32_t* row = stage + lane * W;
             bool exceed = false;
             bool chg = false;  // in place: only changed games go back
-            small_process_tile<T, N, D, false>(p, ls, row, exceed, chg);
+            bool released = false;  // the stage has been handed back (and refilled) in the middle of the step
+            if constexpr (SCHED_DIRECT && !OBS && STAGES == 1 && !Elem<T>::is_float) {
+                // packed tiers, direct route (hk_small.cuh): once the rows are gathered the stage is refilled — the next
+                // chunk's load runs behind this chunk's arithmetic — and the changed rows go straight to global memory
+                auto release = [&]() {
+                    released = true;
+                    __syncwarp();
+                    if (v + 1 < nchunks) {
+                        chunk_game(v + 1, g_nxt, v_nxt);
+                        gather(g_nxt, v_nxt, stages, 0);
+                    }
+                };
+                small_process_tile<T, N, D, false, true, decltype(release)>(p, ls, row, exceed, chg, gst + ls.g * W,
+                                                                            release);
+            } else {
+                small_process_tile<T, N, D, false>(p, ls, row, exceed, chg);
+            }
             if (ls.valid) {
                 if (p.num_points) p.num_points[ls.g] = ls.cnt;
                 if (p.done_bits && ls.cnt < 2) atomicOr(p.done_bits + (ls.g >> 5), 1u << (ls.g & 31));
@@ -556,7 +575,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) hk_sched_kernel(const StepPa
             }
             __syncwarp();  // every lane is done with this stage before a later gather overwrites it
             if constexpr (STAGES == 1) {
-                if (v + 1 < nchunks) {
+                if (v + 1 < nchunks && !released) {
                     chunk_game(v + 1, g_nxt, v_nxt);
                     gather(g_nxt, v_nxt, stages, 0);
                 }

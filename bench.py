@@ -403,7 +403,7 @@ def executed_issue(avg_launch_s):
         return None
     peak = int32_peak()[0] / 32.0
     return {"executed_warp_instructions_per_launch": inst, "achieved_per_s": inst / avg_launch_s, "peak_per_s": peak,
-            "frac": inst / avg_launch_s / peak, "source": "profiles/r2b_step_census_ncu_full_summary.csv"}
+            "frac": inst / avg_launch_s / peak, "source": "profiles/r2c_step_census_ncu_full_summary.csv"}
 
 
 def int32_peak():

@@ -551,6 +551,9 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
 #ifndef HK_PACKED_TIERS
 #define HK_PACKED_TIERS 1
 #endif
+#ifndef HK_SMALL_DIRECT
+#define HK_SMALL_DIRECT 0  // (measured, not kept: the tile-ring kernel with the direct route: C2 steps 2-4 94 92 79 -> 82 73 67 us, but every later step 68 us instead of 50-60: rollout mean 0.0658 -> 0.0672 ms)
+#endif
 #ifndef HK_DIRECT_MAX_ROWS
 #define HK_DIRECT_MAX_ROWS 8
 #endif
@@ -1350,7 +1353,24 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
         // Did this lane's game change?  Unchanged games of an in-place call are not written back
         // (everything is when out != in).
         bool chg = !inplace;
-        small_process_tile<T, N, D, POLICY, PACKED>(p, ls, row, exceed, chg);
+        bool released = false;  // the stage has been handed back (and refilled) in the middle of the step
+        if constexpr (HK_SMALL_DIRECT && PACKED && !OBS && !POLICY && SMALL_STAGES == 1 && !Elem<T>::is_float) {
+            // packed tiers, direct route (tier_packed, DIRECT) of an in-place single step: the stage is refilled as soon as
+            // the rows are gathered and the changed rows go straight to global memory
+            if (inplace && tma && p.T == 1) {  // (warp-uniform)
+                auto release = [&]() {
+                    released = true;
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) issue_load(t + nw, s);
+                };
+                small_process_tile<T, N, D, POLICY, PACKED, decltype(release)>(p, ls, row, exceed, chg, gout + ls.g * W, release);
+            } else {
+                small_process_tile<T, N, D, POLICY, PACKED>(p, ls, row, exceed, chg);
+            }
+        } else {
+            small_process_tile<T, N, D, POLICY, PACKED>(p, ls, row, exceed, chg);
+        }
 
         if (ls.valid) {
             if (p.num_points) p.num_points[ls.g] = ls.cnt;
@@ -1455,7 +1475,7 @@ __global__ void __launch_bounds__(WARPS * 32) hk_small_kernel(const StepParams p
                     bulk_commit();
                     bulk_wait_read<0>();  // the stage (and obs tile) may be overwritten from here on
                 }
-                issue_load(t + SMALL_STAGES * nw, s);
+                if (!released) issue_load(t + SMALL_STAGES * nw, s);
             }
         }
         __syncwarp();

@@ -551,6 +551,9 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
 #ifndef HK_PACKED_TIERS
 #define HK_PACKED_TIERS 1
 #endif
+#ifndef HK_DIRECT_PAIR_STORES
+#define HK_DIRECT_PAIR_STORES 1
+#endif
 #ifndef HK_SMALL_DIRECT
 #define HK_SMALL_DIRECT 0  // (measured, not kept: the tile-ring kernel with the direct route: C2 steps 2-4 94 92 79 -> 82 73 67 us, but every later step 68 us instead of 50-60: rollout mean 0.0658 -> 0.0672 ms)
 #endif
@@ -751,8 +754,18 @@ __device__ __forceinline__ bool tier_packed(const StepParams& p, LaneState& ls, 
                 const bool lv = (alive >> b) & 1u;
                 const int i = (int)(w[b] & 31u);
                 uint32_t* dst = DIRECT ? (gdst + i * D) : (row + i * D);
+                if constexpr (DIRECT && D == 3 && HK_DIRECT_PAIR_STORES) {
+                    // a 12-byte row is one 8-byte and one 4-byte store whatever its alignment (two requests instead of three)
+                    uint32_t v[3];
 #pragma unroll
-                for (int c = 0; c < D; ++c) dst[c] = lv ? ((w[b] >> (5 + P::FB * c)) & P::FMASK) : padw;
+                    for (int c = 0; c < 3; ++c) v[c] = lv ? ((w[b] >> (5 + P::FB * c)) & P::FMASK) : padw;
+                    const bool ev = ((reinterpret_cast<uintptr_t>(dst) >> 2) & 1u) == 0;
+                    *reinterpret_cast<uint2*>(dst + (ev ? 0 : 1)) = ev ? make_uint2(v[0], v[1]) : make_uint2(v[1], v[2]);
+                    dst[ev ? 2 : 0] = ev ? v[2] : v[0];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) dst[c] = lv ? ((w[b] >> (5 + P::FB * c)) & P::FMASK) : padw;
+                }
             }
         }
     }
@@ -1212,6 +1225,9 @@ __device__ __forceinline__ bool small_process_tile(const StepParams& p, LaneStat
                     // 25 % SLOWER at 12 and 2.5 times slower on the 20-row root filter)
                     if (gdst != nullptr && p.T == 1 && lmax <= HK_DIRECT_MAX_ROWS && !any_junk && !__any_sync(0xffffffffu, chg)) {
                         if (lmax <= 4) ok = tier_packed<N, D, 4, true, Release>(p, ls, row, lm, lmax, st, exceed, chg, gdst, release);
+#if HK_DIRECT_MAX_ROWS > 8
+                        else if (lmax > 8) ok = tier_packed<N, D, 12, true, Release>(p, ls, row, lm, lmax, st, exceed, chg, gdst, release);
+#endif
                         else ok = tier_packed<N, D, 8, true, Release>(p, ls, row, lm, lmax, st, exceed, chg, gdst, release);
                         if (ok) return true;
                         tried = true;  // (the values do not pack: the exact tiers below)

@@ -564,7 +564,7 @@ __device__ __forceinline__ int tier_steps(const StepParams& p, LaneState& ls, ui
 #define HK_PACKED_ROLLOUT 0
 #endif
 #ifndef HK_PACKED_MIN
-#define HK_PACKED_MIN 3  // smallest warp maximum of live rows that takes a packed tier
+#define HK_PACKED_MIN 2  // smallest warp maximum of live rows that takes a packed tier (2 against 3: C2 steps 4-6 77 61 50 -> 72 52 44 us, the direct route serves the two-row chunks of the sorted order)
 #endif
 
 template <int N>

@@ -12,6 +12,10 @@
 // coalesced copy per game when few did, nothing when none did.  The fused observation features
 // (OBS) are a second phase on the new state: a sorting network on packed row keys.  No CTA-wide
 // barrier exists anywhere; warps drift freely, which overlaps one warp's loads with another's ALU phase.
+// Single steps of int32 state with small values run on PACKED tiers instead (tier_packed below: one 32-bit word per
+// row, one sort after which only earlier rows can dominate, dominance as one subtraction), and in-place callers that
+// own the stage (the census kernel) may take their DIRECT route: stage handed back after the gather, changed rows
+// stored straight to global memory.
 #pragma once
 #include <type_traits>
 

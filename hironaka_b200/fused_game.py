@@ -9,6 +9,10 @@ change is below the surface: the reference's three point operations per move
 ``[B,N,N,d]`` temporaries) are ONE launch of the fused step kernel.
 
 The policy networks are the caller's (torch modules); only the env step is this package's.
+
+Interface glue (constructor arguments, the order in which the torch RNG is consumed by exploration, the experience
+tuple) is adapted from the reference file cited above so that a trainer sees identical behaviour; the point
+operations, ``step_into`` and ``graphed_step_into`` are new.
 """
 from __future__ import annotations
 

@@ -7,6 +7,9 @@
 .reposition() .get_num_points() .copy()`` — all present with the reference's meaning.  The
 point tensor stays a float32 (or int32) CUDA tensor owned by the object and mutated in place;
 every operation is one kernel launch through the C-ABI.
+
+Constructor argument handling is adapted from the reference file cited above (same names, defaults and error
+behaviour); everything behavioural dispatches to the CUDA kernels.
 """
 from __future__ import annotations
 
